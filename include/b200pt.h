@@ -1,0 +1,263 @@
+/*
+ * b200pt.h — C ABI of the B200-native path-tracing integrator.
+ *
+ * Drop-in boundary.  The reference has no FFI; the seam this
+ * ABI replaces is
+ *
+ *     csrt::RendererConfig  (include/csrt/renderer/renderer.hpp:18-28)
+ *         -> csrt::Renderer::Renderer(const RendererConfig&)   (src/renderer/renderer.cpp:259)
+ *         -> csrt::Renderer::Draw(float *frame)                (src/renderer/renderer.cpp:678)
+ *
+ * i.e. everything the reference does between "the XML parser has produced a
+ * RendererConfig" and "frame[] holds w*h*3 linear-RGB floats".  Every struct
+ * below is a plain-C mirror of the reference struct cited next to it; enum
+ * values are numerically identical to the reference enums so that the glue
+ * (oracle/ref_glue.cpp) is a field-by-field copy.
+ *
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.
+ * All functions return 0 on success and a negative B200PT_E* code on failure;
+ * b200pt_last_error() returns the message (the C++ glue rethrows it as
+ * csrt::MyException, matching renderer.cpp:696-710).
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PT_ABI_VERSION 1u
+#define B200PT_INVALID_ID 0xFFFFFFFFu              /* csrt::kInvalidId, defs.hpp:22 */
+#define B200PT_NO_OFFSET 0xFFFFFFFFFFFFFFFFull     /* "attribute array absent" */
+
+/* error codes */
+#define B200PT_OK 0
+#define B200PT_EINVAL (-1)   /* bad argument / inconsistent scene description */
+#define B200PT_ECUDA (-2)    /* CUDA runtime failure (message holds the code)  */
+#define B200PT_ENOMEM (-3)
+#define B200PT_EIO (-4)      /* scene-pack read/write failure */
+#define B200PT_EUNSUPPORTED (-5)
+
+/* csrt::TextureType, include/csrt/renderer/textures/texture.hpp:13-19 */
+enum { B200PT_TEX_NONE = 0, B200PT_TEX_CONSTANT = 1, B200PT_TEX_CHECKERBOARD = 2, B200PT_TEX_BITMAP = 3 };
+/* csrt::BsdfType, include/csrt/renderer/bsdfs/bsdf.hpp:17-27 */
+enum {
+    B200PT_BSDF_NONE = 0, B200PT_BSDF_AREA_LIGHT = 1, B200PT_BSDF_DIFFUSE = 2, B200PT_BSDF_ROUGH_DIFFUSE = 3,
+    B200PT_BSDF_CONDUCTOR = 4, B200PT_BSDF_DIELECTRIC = 5, B200PT_BSDF_THIN_DIELECTRIC = 6, B200PT_BSDF_PLASTIC = 7
+};
+/* csrt::InstanceType, include/csrt/rtcore/instance.hpp:13-22 */
+enum {
+    B200PT_INST_NONE = 0, B200PT_INST_CUBE = 1, B200PT_INST_RECTANGLE = 2, B200PT_INST_MESHES = 3,
+    B200PT_INST_SPHERE = 4, B200PT_INST_DISK = 5, B200PT_INST_CYLINDER = 6
+};
+/* csrt::EmitterType, include/csrt/renderer/emitters/emitter.hpp:19-28 */
+enum {
+    B200PT_EMIT_NONE = 0, B200PT_EMIT_POINT = 1, B200PT_EMIT_SPOT = 2, B200PT_EMIT_DIRECTIONAL = 3,
+    B200PT_EMIT_SUN = 4, B200PT_EMIT_ENVMAP = 5, B200PT_EMIT_CONSTANT = 6
+};
+/* csrt::IntegratorType, include/csrt/renderer/integrators/integrator.hpp:10-14 */
+enum { B200PT_INTEGRATOR_PATH = 0, B200PT_INTEGRATOR_VOLPATH = 1 };
+/* csrt::PhaseFunctionType, include/csrt/renderer/medium/medium.hpp:12-16 */
+enum { B200PT_PHASE_ISOTROPIC = 0, B200PT_PHASE_HG = 1 };
+
+/* csrt::Camera::Info, include/csrt/renderer/camera.hpp:12-21 */
+typedef struct b200pt_camera {
+    uint32_t spp;
+    int32_t width;
+    int32_t height;
+    float fov_x;      /* degrees; fov_y = fov_x*height/width (camera.cpp:30, quirk Q7) */
+    float eye[3];
+    float look_at[3];
+    float up[3];
+} b200pt_camera;
+
+/* csrt::IntegratorInfo, include/csrt/renderer/integrators/integrator.hpp:16-27 */
+typedef struct b200pt_integrator {
+    uint32_t type;
+    uint32_t hide_emitters;
+    float pdf_rr;
+    uint32_t depth_rr;
+    uint32_t depth_max;
+} b200pt_integrator;
+
+/* csrt::TextureInfo, include/csrt/renderer/textures/texture.hpp:21-27.
+ * Matrices are row-major 4x4 exactly as csrt::Mat4::rows (mat4.hpp). */
+typedef struct b200pt_texture {
+    uint32_t type;
+    float color0[3];        /* constant colour, or checkerboard color0 */
+    float color1[3];        /* checkerboard color1 */
+    float to_uv[16];        /* checkerboard / bitmap to_uv */
+    int32_t width, height, channels; /* bitmap only */
+    uint32_t reserved;
+    uint64_t pixel_offset;  /* bitmap only: first float of this bitmap in scene.pixels[] */
+} b200pt_texture;
+
+/* csrt::BsdfInfo, include/csrt/renderer/bsdfs/bsdf.hpp:40-58 (union flattened) */
+typedef struct b200pt_bsdf {
+    uint32_t type;
+    uint32_t twosided;
+    uint32_t id_opacity;
+    uint32_t id_bump_map;
+    uint32_t id_radiance;               /* area light  */
+    uint32_t id_diffuse_reflectance;    /* diffuse, rough diffuse, plastic */
+    uint32_t id_roughness_u;            /* conductor, (thin) dielectric; rough diffuse / plastic: roughness */
+    uint32_t id_roughness_v;
+    uint32_t id_specular_reflectance;   /* conductor, dielectrics, plastic */
+    uint32_t id_specular_transmittance; /* dielectrics */
+    float eta;                          /* dielectrics, plastic: int_ior/ext_ior */
+    float reflectivity[3];              /* conductor */
+    float edgetint[3];                  /* conductor */
+    float area_light_weight;            /* AreaLightInfo::weight */
+    uint32_t use_fast_approx;           /* RoughDiffuseInfo::use_fast_approx (ignored by the reference) */
+} b200pt_bsdf;
+
+/* csrt::MediumInfo, include/csrt/renderer/medium/medium.hpp:40-45 */
+typedef struct b200pt_medium {
+    uint32_t type;          /* 0 = homogeneous */
+    float sigma_a[3];
+    float sigma_s[3];
+    uint32_t phase_type;
+    float g[3];
+} b200pt_medium;
+
+/* csrt::InstanceInfo, include/csrt/rtcore/instance.hpp:24-51.  Mesh attribute
+ * vectors of all instances live in the shared pools of b200pt_scene_desc;
+ * offsets are in elements (vertices / triangles), B200PT_NO_OFFSET if the
+ * reference vector is empty. */
+typedef struct b200pt_instance {
+    uint32_t type;
+    uint32_t id_bsdf;
+    uint32_t id_medium_int;
+    uint32_t id_medium_ext;
+    uint32_t flip_normals;   /* parsed, never used by the reference (Q14) */
+    float to_world[16];
+    float sphere_radius;
+    float sphere_center[3];
+    float cylinder_radius;
+    float cylinder_p0[3];
+    float cylinder_p1[3];
+    uint32_t reserved;
+    uint64_t num_vertices;
+    uint64_t num_triangles;
+    uint64_t position_offset;
+    uint64_t normal_offset;
+    uint64_t texcoord_offset;
+    uint64_t tangent_offset;
+    uint64_t bitangent_offset;
+    uint64_t index_offset;
+} b200pt_instance;
+
+/* csrt::EmitterInfo, include/csrt/renderer/emitters/emitter.hpp:30-47 (union flattened) */
+typedef struct b200pt_emitter {
+    uint32_t type;
+    float position[3];       /* point */
+    float direction[3];      /* directional, sun */
+    float radiance[3];       /* directional/sun/constant radiance; point/spot intensity */
+    float cutoff_angle;      /* spot (radians) */
+    float beam_width;        /* spot (radians) */
+    float cos_cutoff_angle;  /* sun */
+    uint32_t id_texture;     /* spot texture, sun texture, envmap radiance */
+    float to_world[16];      /* spot, envmap */
+} b200pt_emitter;
+
+/* csrt::RendererConfig, include/csrt/renderer/renderer.hpp:18-28.
+ * All pointers are HOST pointers owned by the caller; b200pt_create copies. */
+typedef struct b200pt_scene_desc {
+    uint32_t abi_version;    /* B200PT_ABI_VERSION */
+    uint32_t reserved;
+    b200pt_camera camera;
+    b200pt_integrator integrator;
+
+    uint64_t num_textures;  const b200pt_texture *textures;
+    uint64_t num_pixels;    const float *pixels;             /* bitmap pool (renderer.cpp:371-392) */
+    uint64_t num_bsdfs;     const b200pt_bsdf *bsdfs;
+    uint64_t num_media;     const b200pt_medium *media;
+    uint64_t num_instances; const b200pt_instance *instances;
+    uint64_t num_emitters;  const b200pt_emitter *emitters;
+
+    uint64_t num_positions;  const float *positions;    /* xyz */
+    uint64_t num_normals;    const float *normals;      /* xyz */
+    uint64_t num_texcoords;  const float *texcoords;    /* uv  */
+    uint64_t num_tangents;   const float *tangents;     /* xyz */
+    uint64_t num_bitangents; const float *bitangents;   /* xyz */
+    uint64_t num_triangles;  const uint32_t *indices;   /* 3 per triangle, relative to the instance's vertex range */
+} b200pt_scene_desc;
+
+typedef struct b200pt_context *b200pt_handle;
+
+typedef struct b200pt_create_opts {
+    int32_t device;          /* CUDA ordinal; -1 = current device */
+    uint32_t max_leaf_size;  /* BVH leaf size, 0 = default (4) */
+    uint64_t max_paths_in_flight; /* wavefront capacity in paths, 0 = default */
+} b200pt_create_opts;
+
+/* What to render.  width/height/spp = 0 take the value from the scene's camera
+ * (the reference CLI overrides them after parsing: apps/main.cpp:46-52). */
+typedef struct b200pt_render_opts {
+    uint32_t width, height, spp;
+    uint64_t seed;              /* Philox key */
+    uint32_t tile_rank;         /* this process renders tiles t with t % tile_world == tile_rank */
+    uint32_t tile_world;        /* 0 or 1 = whole frame */
+    uint32_t collect_stats;     /* count node visits / primitive tests (slower) */
+    uint32_t reserved;
+} b200pt_render_opts;
+
+typedef struct b200pt_stats {
+    double render_ms;            /* device time of the last render (CUDA events) */
+    double upload_ms, bvh_build_ms;
+    uint64_t samples;            /* width*height*spp rendered by this rank */
+    uint64_t closest_rays, shadow_rays;
+    uint64_t node_visits, prim_tests;   /* only when collect_stats */
+    uint64_t kernel_launches;    /* kernels launched by the last render */
+    uint64_t num_bvh_nodes, num_triangles, num_prims;
+    double traverse_ms;          /* device time inside closest-hit + any-hit kernels (collect_stats) */
+    uint64_t reserved[4];
+} b200pt_stats;
+
+/* ---- lifecycle: replaces csrt::Renderer ctor/dtor (renderer.cpp:259-369) ---- */
+int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts, b200pt_handle *out);
+void b200pt_destroy(b200pt_handle h);
+
+/* ---- render: replaces csrt::Renderer::Draw(float*) (renderer.cpp:678-721) ----
+ * frame_host: width*height*3 floats, linear RGB, row 0 = top, caller-owned.
+ * Blocking.  With tile_world > 1 only this rank's tiles are written (others untouched). */
+int b200pt_render(b200pt_handle h, const b200pt_render_opts *opts, float *frame_host);
+
+/* Same, but the frame stays in HBM: frame_dev is a DEVICE pointer to
+ * width*height*3 floats; `stream` is a cudaStream_t (NULL = default stream).
+ * Asynchronous with respect to the host. */
+int b200pt_render_device(b200pt_handle h, const b200pt_render_opts *opts, float *frame_dev, void *stream);
+
+/* Multi-GPU tile path: render this rank's interleaved tiles into
+ * a compact DEVICE buffer of b200pt_tile_buffer_floats() floats (equal on every
+ * rank, so one all-gather moves it), then scatter the gathered [world][floats]
+ * buffer to the final frame. */
+uint64_t b200pt_tile_buffer_floats(uint32_t width, uint32_t height, uint32_t tile_world);
+int b200pt_render_tiles_device(b200pt_handle h, const b200pt_render_opts *opts, float *tiles_dev, void *stream);
+int b200pt_assemble_tiles_device(b200pt_handle h, uint32_t width, uint32_t height, uint32_t tile_world,
+                                 const float *gathered_dev, float *frame_dev, void *stream);
+
+int b200pt_get_stats(b200pt_handle h, b200pt_stats *out);
+const char *b200pt_last_error(b200pt_handle h);   /* h may be NULL: last error of a failed create/load */
+
+/* ---- derived tables the reference computes on the host between config and kernel
+ * (renderer.cpp:311-314, 571-611); exposed so tests can compare them. ---- */
+int b200pt_get_kulla_conty(b200pt_handle h, float *brdf_avg_128x128, float *albedo_avg_128);
+int b200pt_get_envmap_tables(b200pt_handle h, float *out, uint64_t capacity_floats, uint64_t *num_floats,
+                             float *normalization);
+
+/* ---- scene packs: a lossless binary serialisation of b200pt_scene_desc, so a
+ * scene parsed once by the reference's XML parser can travel without it. ---- */
+typedef struct b200pt_scene b200pt_scene;
+int b200pt_scene_load(const char *path, b200pt_scene **out);
+int b200pt_scene_save(const b200pt_scene_desc *scene, const char *path);
+const b200pt_scene_desc *b200pt_scene_get_desc(const b200pt_scene *s);
+void b200pt_scene_free(b200pt_scene *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

@@ -1,0 +1,161 @@
+// ref_glue.cpp — TEST INFRASTRUCTURE ONLY.  C entry points into the UNMODIFIED reference.
+//
+// Compiled by oracle/Makefile together with the reference's own sources (where they lie under
+// /root/reference) into oracle/_ref/libcsrt_ref_{mt,woop}.so.  Nothing in the product links this.
+// It is the checker the parity tests and bench.py's cpu_baseline / --impl reference arm call:
+//   ref_pack_from_xml : csrt::LoadConfig (src/parser/parser.cpp:94) + CLI overrides
+//                       (apps/main.cpp:46-52) -> scene pack on disk
+//   ref_render        : csrt::Renderer(config).Draw(frame) on the CPU backend
+//                       (src/renderer/renderer.cpp:259, 678; DispathRaysCpu :142-253)
+//   ref_* KAT helpers : direct calls of reference leaf functions for known-answer tests.
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "csrt/parser/parser.hpp"
+#include "csrt/renderer/bsdfs/kulla_conty.hpp"
+#include "csrt/renderer/renderer.hpp"
+#include "csrt/rtcore/accel/bvh_builder.hpp"
+
+#include "b200pt.h"
+#include "csrc/host_util.hpp"
+#include "host/csrt_glue.hpp"
+
+namespace {
+
+std::string g_error;
+
+// The reference prints a progress line per 64-pixel patch to stderr (renderer.cpp:235-238).
+class StderrSilencer {
+public:
+    StderrSilencer() {
+        if (getenv("B200PT_REF_VERBOSE")) return;
+        fflush(stderr);
+        saved_ = dup(2);
+        const int null_fd = open("/dev/null", O_WRONLY);
+        if (null_fd >= 0) {
+            dup2(null_fd, 2);
+            close(null_fd);
+        }
+    }
+    ~StderrSilencer() {
+        if (saved_ >= 0) {
+            fflush(stderr);
+            dup2(saved_, 2);
+            close(saved_);
+        }
+    }
+
+private:
+    int saved_ = -1;
+};
+
+double Seconds(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+}
+
+} // namespace
+
+extern "C" {
+
+const char *ref_last_error() { return g_error.c_str(); }
+
+// 1 if this build uses Woop's watertight triangle test (src/rtcore/primitives/triangle.cpp:23-87).
+int ref_is_watertight() {
+#ifdef WATERTIGHT_TRIANGLES
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+int ref_pack_from_xml(const char *xml_path, int width, int height, int spp, const char *out_pack) {
+    try {
+        csrt::RendererConfig cfg;
+        {
+            StderrSilencer quiet;
+            cfg = csrt::LoadConfig(xml_path);
+        }
+        cfg.backend_type = csrt::BackendType::kCpu;
+        // apps/main.cpp:46-52 — overrides are applied after fov_x was derived from the XML size (Q7).
+        if (width > 0) cfg.camera.width = width;
+        if (height > 0) cfg.camera.height = height;
+        if (spp > 0) cfg.camera.spp = spp;
+        std::unique_ptr<b200pt_scene> scene = b200pt_glue::FlattenConfig(cfg);
+        if (b200pt_scene_save(&scene->desc, out_pack) != B200PT_OK) {
+            g_error = b200pt::GlobalError();
+            return -1;
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+int ref_render(const b200pt_scene_desc *desc, int width, int height, int spp, float *frame, double *build_seconds,
+               double *render_seconds) {
+    try {
+        csrt::RendererConfig cfg = b200pt_glue::InflateScene(*desc);
+        if (width > 0) cfg.camera.width = width;
+        if (height > 0) cfg.camera.height = height;
+        if (spp > 0) cfg.camera.spp = spp;
+        StderrSilencer quiet;
+        const auto t0 = std::chrono::steady_clock::now();
+        csrt::Renderer renderer(cfg);
+        const auto t1 = std::chrono::steady_clock::now();
+        renderer.Draw(frame);
+        const auto t2 = std::chrono::steady_clock::now();
+        if (build_seconds) *build_seconds = Seconds(t0, t1);
+        if (render_seconds) *render_seconds = Seconds(t1, t2);
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// ---- known-answer helpers: reference leaf functions, called directly ----
+
+uint32_t ref_tea4(uint32_t v0, uint32_t v1) { return csrt::Tea<4>(v0, v1); }
+
+float ref_random_float(uint32_t *seed) { return csrt::RandomFloat(seed); }
+
+float ref_van_der_corput2(uint32_t index) { return csrt::GetVanDerCorputSequence<2>(index); }
+
+float ref_mis_weight(float a, float b) { return csrt::MisWeight(a, b); }
+
+void ref_sample_hemis_cos(float xi0, float xi1, float *vec3, float *pdf) {
+    csrt::Vec3 v;
+    csrt::SampleHemisCos(xi0, xi1, &v, pdf);
+    vec3[0] = v.x, vec3[1] = v.y, vec3[2] = v.z;
+}
+
+void ref_kulla_conty(float *brdf_avg, float *albedo_avg) { csrt::ComputeKullaConty(brdf_avg, albedo_avg); }
+
+// LBVH topology for `n` boxes: out_nodes[i] = {leaf, id_left, id_right, id_object}; returns node count.
+uint32_t ref_build_bvh(uint32_t n, const float *aabb_min_max, const float *areas, uint32_t *out_nodes,
+                       float *out_area, uint32_t capacity) {
+    std::vector<csrt::AABB> aabbs(n);
+    std::vector<float> area_list(areas, areas + n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float *b = aabb_min_max + 6 * i;
+        aabbs[i] = csrt::AABB(csrt::Vec3(b[0], b[1], b[2]), csrt::Vec3(b[3], b[4], b[5]));
+    }
+    const std::vector<csrt::BvhNode> nodes = csrt::BvhBuilder::Build(aabbs, area_list);
+    for (uint32_t i = 0; i < nodes.size() && i < capacity; ++i) {
+        out_nodes[4 * i + 0] = nodes[i].leaf ? 1u : 0u;
+        out_nodes[4 * i + 1] = nodes[i].id_left;
+        out_nodes[4 * i + 2] = nodes[i].id_right;
+        out_nodes[4 * i + 3] = nodes[i].id_object;
+        out_area[i] = nodes[i].area;
+    }
+    return static_cast<uint32_t>(nodes.size());
+}
+
+} // extern "C"

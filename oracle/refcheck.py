@@ -1,0 +1,65 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes access to the reference build (oracle/_ref/libcsrt_ref_*.so),
+the C restatement (oracle/_ref/liboracle.so).  Imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference arm; never by the product package."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+class RefLib:
+    """The unmodified reference CPU renderer (csrt::Renderer, src/renderer/renderer.cpp:259,678)."""
+
+    def __init__(self, variant="woop"):
+        path = os.path.join(REF_DIR, f"libcsrt_ref_{variant}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        os.environ.setdefault("B200PT_EXR_SIDECAR_DIR", os.path.join(REF_DIR, "exr"))
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.ref_last_error.restype = ctypes.c_char_p
+        L.ref_pack_from_xml.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+        L.ref_render.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                 ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.b200pt_scene_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.b200pt_scene_get_desc.argtypes = [ctypes.c_void_p]
+        L.b200pt_scene_get_desc.restype = ctypes.c_void_p
+        L.b200pt_scene_free.argtypes = [ctypes.c_void_p]
+        L.ref_tea4.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+        L.ref_tea4.restype = ctypes.c_uint32
+        L.ref_random_float.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
+        L.ref_random_float.restype = ctypes.c_float
+        L.ref_van_der_corput2.argtypes = [ctypes.c_uint32]
+        L.ref_van_der_corput2.restype = ctypes.c_float
+        L.ref_mis_weight.argtypes = [ctypes.c_float, ctypes.c_float]
+        L.ref_mis_weight.restype = ctypes.c_float
+
+    def error(self):
+        return self.lib.ref_last_error().decode()
+
+    def pack_from_xml(self, xml, out_pack, width=0, height=0, spp=0):
+        rc = self.lib.ref_pack_from_xml(xml.encode(), width, height, spp, out_pack.encode())
+        if rc != 0:
+            raise RuntimeError(self.error())
+
+    def render_pack(self, pack_path, width=0, height=0, spp=0):
+        """Returns (frame[h,w,3] float32, build_seconds, render_seconds)."""
+        scene = ctypes.c_void_p()
+        if self.lib.b200pt_scene_load(pack_path.encode(), ctypes.byref(scene)) != 0:
+            raise RuntimeError(f"cannot load {pack_path}")
+        try:
+            desc = self.lib.b200pt_scene_get_desc(scene)
+            cam = np.ctypeslib.as_array(ctypes.cast(desc + 8, ctypes.POINTER(ctypes.c_int32)), shape=(3,))
+            w = width or int(cam[1])
+            h = height or int(cam[2])
+            frame = np.zeros((h, w, 3), dtype=np.float32)
+            b, r = ctypes.c_double(), ctypes.c_double()
+            rc = self.lib.ref_render(desc, width, height, spp, frame.ctypes.data, ctypes.byref(b), ctypes.byref(r))
+            if rc != 0:
+                raise RuntimeError(self.error())
+            return frame, b.value, r.value
+        finally:
+            self.lib.b200pt_scene_free(scene)
