@@ -1,0 +1,220 @@
+"""b200pt — host-side mirror of the reference's renderer interface over the C ABI (include/b200pt.h).
+
+The reference exposes, behind its XML parser, exactly two things:
+
+    csrt::Renderer(const RendererConfig&)     src/renderer/renderer.cpp:259
+    csrt::Renderer::Draw(float *frame)        src/renderer/renderer.cpp:678
+    csrt::RayTracer(config).Draw(filename)    src/ray_tracer.cpp:124,155   (Draw + sRGB PNG)
+
+`Renderer` / `RayTracer` below have the same names, argument meaning and error behaviour (a failing call
+raises `MyException`, the reference's only exception type, include/csrt/utils/misc.hpp:54-63), but every
+sample is computed by the CUDA library `libb200pt.so`.  There is no CPU fallback: importing works anywhere,
+constructing a Renderer without the built library or without a GPU raises.
+
+PyTorch is used only as plumbing (device buffers, streams, torch.distributed for the tile gather).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+INVALID_ID = 0xFFFFFFFF
+
+
+class MyException(RuntimeError):
+    """Mirror of csrt::MyException (include/csrt/utils/misc.hpp:54-63)."""
+
+
+class RenderOpts(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("spp", ctypes.c_uint32),
+                ("seed", ctypes.c_uint64), ("tile_rank", ctypes.c_uint32), ("tile_world", ctypes.c_uint32),
+                ("collect_stats", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class CreateOpts(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int32), ("max_leaf_size", ctypes.c_uint32),
+                ("max_paths_in_flight", ctypes.c_uint64)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double), ("bvh_build_ms", ctypes.c_double),
+                ("samples", ctypes.c_uint64), ("closest_rays", ctypes.c_uint64), ("shadow_rays", ctypes.c_uint64),
+                ("node_visits", ctypes.c_uint64), ("prim_tests", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
+                ("num_bvh_nodes", ctypes.c_uint64), ("num_triangles", ctypes.c_uint64), ("num_prims", ctypes.c_uint64),
+                ("traverse_ms", ctypes.c_double), ("reserved", ctypes.c_uint64 * 4)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+
+
+# Every symbol include/b200pt.h declares; tests check the library exports all of them.
+EXPORTED_SYMBOLS = [
+    "b200pt_create", "b200pt_destroy", "b200pt_render", "b200pt_render_device", "b200pt_tile_buffer_floats",
+    "b200pt_render_tiles_device", "b200pt_assemble_tiles_device", "b200pt_get_stats", "b200pt_last_error",
+    "b200pt_get_kulla_conty", "b200pt_get_envmap_tables", "b200pt_scene_load", "b200pt_scene_save",
+    "b200pt_scene_get_desc", "b200pt_scene_free",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libb200pt.so (built in-tree by __graft_entry__.build()).  Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MyException(f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                          "There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
+    L.b200pt_create.argtypes = [vp, ctypes.POINTER(CreateOpts), ctypes.POINTER(vp)]
+    L.b200pt_destroy.argtypes = [vp]
+    L.b200pt_destroy.restype = None
+    L.b200pt_render.argtypes = [vp, ctypes.POINTER(RenderOpts), vp]
+    L.b200pt_render_device.argtypes = [vp, ctypes.POINTER(RenderOpts), vp, vp]
+    L.b200pt_tile_buffer_floats.argtypes = [u32, u32, u32]
+    L.b200pt_tile_buffer_floats.restype = u64
+    L.b200pt_render_tiles_device.argtypes = [vp, ctypes.POINTER(RenderOpts), vp, vp]
+    L.b200pt_assemble_tiles_device.argtypes = [vp, u32, u32, u32, vp, vp, vp]
+    L.b200pt_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.b200pt_last_error.argtypes = [vp]
+    L.b200pt_last_error.restype = ctypes.c_char_p
+    L.b200pt_get_kulla_conty.argtypes = [vp, vp, vp]
+    L.b200pt_get_envmap_tables.argtypes = [vp, vp, u64, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_float)]
+    L.b200pt_scene_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.b200pt_scene_save.argtypes = [vp, ctypes.c_char_p]
+    L.b200pt_scene_get_desc.argtypes = [vp]
+    L.b200pt_scene_get_desc.restype = vp
+    L.b200pt_scene_free.argtypes = [vp]
+    L.b200pt_scene_free.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc, handle=None):
+    if rc != 0:
+        raise MyException(lib().b200pt_last_error(handle).decode(errors="replace"))
+
+
+class Scene:
+    """A parsed scene (the flattened csrt::RendererConfig, renderer.hpp:18-28) loaded from a scene pack."""
+
+    def __init__(self, path):
+        self._ptr = ctypes.c_void_p()
+        self.path = path
+        _check(lib().b200pt_scene_load(os.fsencode(path), ctypes.byref(self._ptr)))
+        self.desc = lib().b200pt_scene_get_desc(self._ptr)
+        # b200pt_scene_desc: {u32 abi, u32 reserved, camera{u32 spp, i32 w, i32 h, f32 fov_x, ...}}
+        head = np.ctypeslib.as_array(ctypes.cast(self.desc + 8, ctypes.POINTER(ctypes.c_int32)), shape=(3,))
+        self.spp, self.width, self.height = int(head[0]), int(head[1]), int(head[2])
+
+    def save(self, path):
+        _check(lib().b200pt_scene_save(self.desc, os.fsencode(path)))
+
+    def close(self):
+        if self._ptr:
+            lib().b200pt_scene_free(self._ptr)
+            self._ptr = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Renderer:
+    """csrt::Renderer (renderer.hpp:30-82): construct from a config, Draw(frame) fills w*h*3 linear floats."""
+
+    def __init__(self, scene, device=-1, max_paths_in_flight=0, max_leaf_size=0):
+        self.scene = scene
+        self._h = ctypes.c_void_p()
+        opts = CreateOpts(device, max_leaf_size, max_paths_in_flight)
+        _check(lib().b200pt_create(scene.desc, ctypes.byref(opts), ctypes.byref(self._h)))
+
+    def _opts(self, width, height, spp, seed, tile_rank=0, tile_world=1, stats=False):
+        return RenderOpts(width or 0, height or 0, spp or 0, seed, tile_rank, tile_world, 1 if stats else 0, 0)
+
+    def Draw(self, frame=None, width=0, height=0, spp=0, seed=0, stats=False):
+        """Host-buffer render (the reference's Draw(float*)): H2D/D2H copies happen inside the call."""
+        w, h = width or self.scene.width, height or self.scene.height
+        if frame is None:
+            frame = np.zeros((h, w, 3), dtype=np.float32)
+        if frame.dtype != np.float32 or frame.size != w * h * 3 or not frame.flags["C_CONTIGUOUS"]:
+            raise MyException("frame must be a C-contiguous float32 array of width*height*3 elements.")
+        opts = self._opts(width, height, spp, seed, stats=stats)
+        _check(lib().b200pt_render(self._h, ctypes.byref(opts), frame.ctypes.data), self._h)
+        return frame
+
+    def draw_device(self, frame_tensor, width=0, height=0, spp=0, seed=0, stream=None, stats=False):
+        """Frame stays in HBM: `frame_tensor` is a CUDA float32 tensor with width*height*3 elements."""
+        opts = self._opts(width, height, spp, seed, stats=stats)
+        _check(lib().b200pt_render_device(self._h, ctypes.byref(opts), frame_tensor.data_ptr(), stream), self._h)
+
+    def draw_tiles_device(self, tiles_tensor, tile_rank, tile_world, width=0, height=0, spp=0, seed=0, stream=None):
+        opts = self._opts(width, height, spp, seed, tile_rank, tile_world)
+        _check(lib().b200pt_render_tiles_device(self._h, ctypes.byref(opts), tiles_tensor.data_ptr(), stream), self._h)
+
+    def assemble_tiles_device(self, gathered_tensor, frame_tensor, width, height, tile_world, stream=None):
+        _check(lib().b200pt_assemble_tiles_device(self._h, width, height, tile_world, gathered_tensor.data_ptr(),
+                                                  frame_tensor.data_ptr(), stream), self._h)
+
+    def stats(self):
+        s = Stats()
+        _check(lib().b200pt_get_stats(self._h, ctypes.byref(s)), self._h)
+        return s.as_dict()
+
+    def kulla_conty(self):
+        brdf = np.zeros((128, 128), dtype=np.float32)
+        albedo = np.zeros(128, dtype=np.float32)
+        _check(lib().b200pt_get_kulla_conty(self._h, brdf.ctypes.data, albedo.ctypes.data), self._h)
+        return brdf, albedo
+
+    def envmap_tables(self):
+        n, norm = ctypes.c_uint64(), ctypes.c_float()
+        _check(lib().b200pt_get_envmap_tables(self._h, None, 0, ctypes.byref(n), ctypes.byref(norm)), self._h)
+        out = np.zeros(n.value, dtype=np.float32)
+        if n.value:
+            _check(lib().b200pt_get_envmap_tables(self._h, out.ctypes.data, n.value, ctypes.byref(n), ctypes.byref(norm)), self._h)
+        return out, norm.value
+
+    def close(self):
+        if self._h:
+            lib().b200pt_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def tile_buffer_floats(width, height, tile_world):
+    return int(lib().b200pt_tile_buffer_floats(width, height, tile_world))
+
+
+def linear_to_srgb8(frame):
+    """image_io::Write's transfer function (src/utils/image_io.cpp:25-38): sRGB OETF, truncation to 8 bit."""
+    f = np.asarray(frame, dtype=np.float32)
+    with np.errstate(invalid="ignore"):
+        v = np.where(f <= 0.0031308, 12.92 * f, 1.055 * np.power(np.maximum(f, 0.0), 1.0 / 2.4) - 0.055)
+    return np.where(v > 1.0, 255.0, v * 255.0).astype(np.int32).astype(np.uint8)
+
+
+class RayTracer:
+    """csrt::RayTracer (include/csrt/ray_tracer.hpp:12-36): owns a Renderer and the frame; Draw(filename) writes a PNG."""
+
+    def __init__(self, scene, width=0, height=0, spp=0, device=-1):
+        self.width, self.height, self.spp = width or scene.width, height or scene.height, spp or scene.spp
+        self.renderer = Renderer(scene, device=device)
+        self.frame = np.zeros((self.height, self.width, 3), dtype=np.float32)
+
+    def Draw(self, output_filename):
+        self.renderer.Draw(self.frame, self.width, self.height, self.spp)
+        from PIL import Image
+        Image.fromarray(linear_to_srgb8(self.frame)).save(output_filename)
+        return self.frame

@@ -1,0 +1,45 @@
+// host_scene.hpp — host-side staging of DeviceScene: everything the reference's
+// Renderer/Scene constructors derive from a RendererConfig (renderer.cpp:259-348,
+// scene.cpp:118-533), rebuilt here for a GPU-friendly layout.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "b200pt.h"
+#include "device_scene.h"
+
+namespace b200pt {
+
+struct HostScene {
+    std::vector<BvhNode> nodes;
+    std::vector<TriVerts> tri_verts;
+    std::vector<TriShade> tri_shade;
+    std::vector<AnalyticPrim> analytic;
+    std::vector<DInstance> instances;
+    std::vector<DBsdf> bsdfs;
+    std::vector<DTexture> textures;
+    std::vector<DMedium> media;
+    std::vector<DEmitter> emitters;
+    std::vector<float> envmap_tables;
+    float envmap_normalization = 0.0f;
+    std::vector<float> kc_brdf_avg, kc_albedo_avg;
+    std::vector<float> cdf_area_light;
+    std::vector<uint32_t> map_area_light_instance;
+    std::vector<float> light_tri_cdf;
+    std::vector<uint32_t> light_tri_ids;
+    float scene_bmin[3], scene_bmax[3];
+    DIntegrator integrator{};
+    b200pt_camera camera{};
+    double bvh_build_ms = 0.0;
+};
+
+// Returns false and sets *error on an inconsistent description.
+bool BuildHostScene(const b200pt_scene_desc &desc, uint32_t max_leaf_size, HostScene *out, std::string *error);
+
+// camera.cpp:26-37 for an arbitrary output size (the CLI may override width/height, Q7).
+DCamera MakeCamera(const b200pt_camera &cam, uint32_t width, uint32_t height);
+
+// kulla_conty.cpp:62-80, multi-threaded restatement (bit-identical tables).
+void ComputeKullaContyTables(float *brdf_avg, float *albedo_avg);
+
+} // namespace b200pt

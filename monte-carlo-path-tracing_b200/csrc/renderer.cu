@@ -1,0 +1,465 @@
+// renderer.cu — the C ABI (include/b200pt.h) and the host side of the wavefront loop.
+//
+// b200pt_create  replaces csrt::Renderer::Renderer (src/renderer/renderer.cpp:259-348): flatten, build the
+//                BVH, derive the tables, upload once to HBM.
+// b200pt_render  replaces csrt::Renderer::Draw (renderer.cpp:678-721): runs the wavefront rounds and
+//                leaves width*height*3 linear floats in the caller's frame.
+// There is no CPU fallback: every entry point that needs the GPU fails with B200PT_ECUDA when CUDA is unusable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "b200pt.h"
+#include "host_scene.hpp"
+#include "host_util.hpp"
+#include "wavefront.cuh"
+
+using namespace b200pt;
+
+namespace {
+
+constexpr uint64_t kDefaultPathsInFlight = 1ull << 24; // 16 Mi sample slots per batch
+constexpr uint32_t kMaxRounds = 4096;                  // hard stop for max_depth = -1 scenes (RR ends paths long before)
+
+template <typename T>
+struct DeviceArray {
+    T *ptr = nullptr;
+    size_t count = 0;
+    ~DeviceArray() { Free(); }
+    void Free() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+    }
+    cudaError_t Alloc(size_t n) {
+        Free();
+        count = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(&ptr, n * sizeof(T));
+    }
+    cudaError_t Upload(const std::vector<T> &src) {
+        cudaError_t e = Alloc(src.size());
+        if (e != cudaSuccess || src.empty()) return e;
+        return cudaMemcpy(ptr, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+} // namespace
+
+struct b200pt_context {
+    int device = 0;
+    std::string error;
+    HostScene host;
+    DeviceScene scene{};
+    b200pt_stats stats{};
+
+    DeviceArray<BvhNode> nodes;
+    DeviceArray<TriVerts> tri_verts;
+    DeviceArray<TriShade> tri_shade;
+    DeviceArray<AnalyticPrim> analytic;
+    DeviceArray<DInstance> instances;
+    DeviceArray<DBsdf> bsdfs;
+    DeviceArray<DTexture> textures;
+    DeviceArray<float> pixels;
+    DeviceArray<DMedium> media;
+    DeviceArray<DEmitter> emitters;
+    DeviceArray<float> envmap_tables, kc_brdf, kc_albedo, cdf_area_light, light_tri_cdf;
+    DeviceArray<uint32_t> map_area_light_instance, light_tri_ids;
+
+    // wavefront state
+    uint64_t capacity = 0;        // sample slots per batch
+    uint32_t shadow_per_vertex = 1;
+    DeviceArray<float> wave;      // one allocation carved into the SoA queues
+    PathQueue queue[2]{};
+    ShadowQueue shadow{};
+    float *radiance = nullptr;
+    DeviceArray<Counters> counters;
+    DeviceArray<float> accum;     // per local pixel RGB sums
+    DeviceArray<float> frame;     // staging for b200pt_render (host frame)
+    uint32_t *pinned_count = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool timing_pending = false;
+    int num_sms = 148;
+    bool kc_ready = false;
+
+    ~b200pt_context() {
+        if (pinned_count) cudaFreeHost(pinned_count);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int Fail(int code, const std::string &msg) {
+        error = msg;
+        SetGlobalError(code, msg);
+        return code;
+    }
+    int CudaFail(cudaError_t e, const char *what) {
+        // same wording as the reference's CUDA path (renderer.cpp:696-710)
+        return Fail(B200PT_ECUDA, std::string("CUDA error : \"") + cudaGetErrorString(e) + "\" (" + what + ").");
+    }
+};
+
+namespace {
+
+#define CU_CHECK(ctx, call)                                         \
+    do {                                                            \
+        const cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return (ctx)->CudaFail(e_, #call);   \
+    } while (0)
+
+int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
+    HostScene &h = c->host;
+    CU_CHECK(c, c->nodes.Upload(h.nodes));
+    CU_CHECK(c, c->tri_verts.Upload(h.tri_verts));
+    CU_CHECK(c, c->tri_shade.Upload(h.tri_shade));
+    CU_CHECK(c, c->analytic.Upload(h.analytic));
+    CU_CHECK(c, c->instances.Upload(h.instances));
+    CU_CHECK(c, c->bsdfs.Upload(h.bsdfs));
+    CU_CHECK(c, c->textures.Upload(h.textures));
+    CU_CHECK(c, c->media.Upload(h.media));
+    CU_CHECK(c, c->emitters.Upload(h.emitters));
+    CU_CHECK(c, c->envmap_tables.Upload(h.envmap_tables));
+    CU_CHECK(c, c->kc_brdf.Upload(h.kc_brdf_avg));
+    CU_CHECK(c, c->kc_albedo.Upload(h.kc_albedo_avg));
+    CU_CHECK(c, c->cdf_area_light.Upload(h.cdf_area_light));
+    CU_CHECK(c, c->map_area_light_instance.Upload(h.map_area_light_instance));
+    CU_CHECK(c, c->light_tri_cdf.Upload(h.light_tri_cdf));
+    CU_CHECK(c, c->light_tri_ids.Upload(h.light_tri_ids));
+    CU_CHECK(c, c->pixels.Alloc(desc.num_pixels));
+    if (desc.num_pixels)
+        CU_CHECK(c, cudaMemcpy(c->pixels.ptr, desc.pixels, desc.num_pixels * sizeof(float), cudaMemcpyHostToDevice));
+
+    DeviceScene &s = c->scene;
+    s.nodes = c->nodes.ptr, s.num_nodes = static_cast<uint32_t>(h.nodes.size());
+    s.tri_verts = c->tri_verts.ptr, s.num_tris = static_cast<uint32_t>(h.tri_verts.size());
+    s.tri_shade = c->tri_shade.ptr;
+    s.analytic = c->analytic.ptr, s.num_analytic = static_cast<uint32_t>(h.analytic.size());
+    s.instances = c->instances.ptr, s.num_instances = static_cast<uint32_t>(h.instances.size());
+    s.bsdfs = c->bsdfs.ptr, s.num_bsdfs = static_cast<uint32_t>(h.bsdfs.size());
+    s.textures = c->textures.ptr, s.num_textures = static_cast<uint32_t>(h.textures.size());
+    s.pixels = c->pixels.ptr;
+    s.media = c->media.ptr, s.num_media = static_cast<uint32_t>(h.media.size());
+    s.emitters = c->emitters.ptr;
+    s.envmap_tables = c->envmap_tables.ptr;
+    s.kc_brdf_avg = c->kc_brdf.ptr, s.kc_albedo_avg = c->kc_albedo.ptr;
+    s.cdf_area_light = c->cdf_area_light.ptr;
+    s.map_area_light_instance = c->map_area_light_instance.ptr;
+    s.light_tri_cdf = c->light_tri_cdf.ptr, s.light_tri_ids = c->light_tri_ids.ptr;
+    memcpy(s.scene_bmin, h.scene_bmin, 12), memcpy(s.scene_bmax, h.scene_bmax, 12);
+    s.integrator = h.integrator;
+
+    c->stats.num_bvh_nodes = h.nodes.size();
+    c->stats.num_triangles = h.tri_verts.size();
+    c->stats.num_prims = h.tri_verts.size() + h.analytic.size();
+    c->stats.bvh_build_ms = h.bvh_build_ms;
+    // the big host copies are not needed any more
+    std::vector<BvhNode>().swap(h.nodes);
+    std::vector<TriVerts>().swap(h.tri_verts);
+    std::vector<TriShade>().swap(h.tri_shade);
+    return B200PT_OK;
+}
+
+// Carve the SoA queues out of one allocation.
+int AllocWavefront(b200pt_context *c, uint64_t capacity) {
+    const bool vol = c->scene.integrator.type == B200PT_INTEGRATOR_VOLPATH;
+    c->shadow_per_vertex = c->scene.integrator.num_emitters + (c->scene.integrator.num_area_lights ? 1u : 0u);
+    const uint64_t shadow_cap = capacity * std::max(1u, c->shadow_per_vertex);
+    const uint64_t words_per_queue = 11 + (vol ? 4 : 0) + 4; // 10 floats + slot (+ medium, wo) + HitRec
+    const uint64_t total = 2 * words_per_queue * capacity + 11 * shadow_cap + 3 * capacity;
+    CU_CHECK(c, c->wave.Alloc(total));
+    float *p = c->wave.ptr;
+    auto take = [&](uint64_t n) {
+        float *r = p;
+        p += n;
+        return r;
+    };
+    for (int k = 0; k < 2; ++k) {
+        PathQueue &q = c->queue[k];
+        q.hit = reinterpret_cast<HitRec *>(take(4 * capacity)); // first: keeps 16-byte alignment
+        q.ox = take(capacity), q.oy = take(capacity), q.oz = take(capacity);
+        q.dx = take(capacity), q.dy = take(capacity), q.dz = take(capacity);
+        q.tr = take(capacity), q.tg = take(capacity), q.tb = take(capacity);
+        q.pdf = take(capacity);
+        q.slot = reinterpret_cast<uint32_t *>(take(capacity));
+        q.medium = nullptr, q.wx = q.wy = q.wz = nullptr;
+        if (vol) {
+            q.medium = reinterpret_cast<uint32_t *>(take(capacity));
+            q.wx = take(capacity), q.wy = take(capacity), q.wz = take(capacity);
+        }
+    }
+    ShadowQueue &sq = c->shadow;
+    sq.ox = take(shadow_cap), sq.oy = take(shadow_cap), sq.oz = take(shadow_cap);
+    sq.dx = take(shadow_cap), sq.dy = take(shadow_cap), sq.dz = take(shadow_cap);
+    sq.tmax = take(shadow_cap);
+    sq.cr = take(shadow_cap), sq.cg = take(shadow_cap), sq.cb = take(shadow_cap);
+    sq.slot = reinterpret_cast<uint32_t *>(take(shadow_cap));
+    c->radiance = take(3 * capacity);
+    c->capacity = capacity;
+    return B200PT_OK;
+}
+
+struct ResolvedOpts {
+    uint32_t width, height, spp, tile_rank, tile_world;
+    uint64_t seed;
+    bool stats;
+};
+
+int ResolveOpts(b200pt_context *c, const b200pt_render_opts *o, ResolvedOpts *r) {
+    const b200pt_camera &cam = c->host.camera;
+    r->width = (o && o->width) ? o->width : static_cast<uint32_t>(cam.width);
+    r->height = (o && o->height) ? o->height : static_cast<uint32_t>(cam.height);
+    r->spp = (o && o->spp) ? o->spp : cam.spp;
+    r->seed = o ? o->seed : 0;
+    r->tile_world = (o && o->tile_world) ? o->tile_world : 1;
+    r->tile_rank = o ? o->tile_rank : 0;
+    r->stats = o && o->collect_stats;
+    if (r->width == 0 || r->height == 0 || r->spp == 0) return c->Fail(B200PT_EINVAL, "width, height and spp must be positive.");
+    if (r->tile_rank >= r->tile_world) return c->Fail(B200PT_EINVAL, "tile_rank must be < tile_world.");
+    if (static_cast<uint64_t>(r->width) * r->height > (1ull << 30)) return c->Fail(B200PT_EINVAL, "frame too large.");
+    return B200PT_OK;
+}
+
+uint32_t PixelsPerRank(uint32_t width, uint32_t height, uint32_t world) {
+    const uint32_t tiles = ((width + kTileSize - 1) / kTileSize) * ((height + kTileSize - 1) / kTileSize);
+    return ((tiles + world - 1) / world) * kTilePixels;
+}
+
+// The wavefront loop.  Everything is enqueued on `stream`; the host only synchronises to poll the
+// survivor count once RR is active (every 4 rounds), so shallow scenes run without host round trips.
+int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, float *tiles_dev, cudaStream_t stream) {
+    CU_CHECK(c, cudaSetDevice(c->device));
+    BatchParams bp{};
+    bp.camera = MakeCamera(c->host.camera, ro.width, ro.height);
+    bp.width = ro.width, bp.height = ro.height, bp.spp = ro.spp;
+    bp.spp_inv = 1.0f / ro.spp;
+    bp.key = make_uint2(static_cast<uint32_t>(ro.seed), static_cast<uint32_t>(ro.seed >> 32) ^ 0xB200C0DEu);
+    bp.tiles_x = (ro.width + kTileSize - 1) / kTileSize;
+    bp.num_tiles = bp.tiles_x * ((ro.height + kTileSize - 1) / kTileSize);
+    bp.tile_rank = ro.tile_rank, bp.tile_world = ro.tile_world;
+    const uint32_t local_pixels = PixelsPerRank(ro.width, ro.height, ro.tile_world);
+
+    if (c->accum.count < 3ull * local_pixels) CU_CHECK(c, c->accum.Alloc(3ull * local_pixels));
+    LaunchConfig lc;
+    lc.blocks = c->num_sms * 4;
+    lc.threads = 256;
+    lc.stream = stream;
+    lc.stats = ro.stats;
+
+    uint64_t launches = 0;
+    CU_CHECK(c, cudaEventRecord(c->ev_begin, stream));
+    CU_CHECK(c, cudaMemsetAsync(c->accum.ptr, 0, 3ull * local_pixels * sizeof(float), stream));
+    CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, sizeof(Counters), stream));
+
+    const DIntegrator &ig = c->scene.integrator;
+    const uint32_t capacity = static_cast<uint32_t>(c->capacity);
+    const uint32_t pixels_per_chunk = std::min<uint32_t>(local_pixels, capacity);
+    const uint32_t samples_per_batch = std::max<uint32_t>(1, std::min<uint32_t>(ro.spp, capacity / pixels_per_chunk));
+    const uint32_t max_rounds = std::min<uint32_t>(ig.depth_max, kMaxRounds);
+
+    for (uint32_t pixel_begin = 0; pixel_begin < local_pixels; pixel_begin += pixels_per_chunk) {
+        bp.pixel_begin = pixel_begin;
+        bp.pixel_count = std::min(pixels_per_chunk, local_pixels - pixel_begin);
+        for (uint32_t sample_begin = 0; sample_begin < ro.spp; sample_begin += samples_per_batch) {
+            bp.sample_begin = sample_begin;
+            bp.sample_count = std::min(samples_per_batch, ro.spp - sample_begin);
+            const uint64_t nslots = static_cast<uint64_t>(bp.pixel_count) * bp.sample_count;
+            for (int ch = 0; ch < 3; ++ch)
+                CU_CHECK(c, cudaMemsetAsync(c->radiance + static_cast<uint64_t>(ch) * capacity, 0, nslots * sizeof(float), stream));
+            CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, 16, stream)); // queue[0], queue[1], shadow
+            LaunchPrimary(lc, c->scene, bp, c->queue[0], c->radiance, capacity, c->counters.ptr);
+            ++launches;
+            int which = 0;
+            for (uint32_t depth = 1; depth <= max_rounds; ++depth) {
+                if (depth > 1) {
+                    LaunchResetCounters(lc, c->counters.ptr, which ^ 1, true);
+                    ++launches;
+                }
+                LaunchShade(lc, c->scene, bp, depth, c->queue[which], which, c->queue[which ^ 1], c->shadow, c->radiance,
+                            c->counters.ptr, capacity);
+                ++launches;
+                if (c->shadow_per_vertex > 0) {
+                    LaunchShadow(lc, c->scene, c->shadow, c->radiance, capacity, c->counters.ptr);
+                    ++launches;
+                }
+                which ^= 1;
+                if (depth == max_rounds) break;
+                if (depth >= 8 && (depth & 3) == 0) { // poll the survivor count
+                    CU_CHECK(c, cudaMemcpyAsync(c->pinned_count, &c->counters.ptr->queue[which], sizeof(uint32_t),
+                                                cudaMemcpyDeviceToHost, stream));
+                    CU_CHECK(c, cudaStreamSynchronize(stream));
+                    if (*c->pinned_count == 0) break;
+                }
+                LaunchExtend(lc, c->scene, c->queue[which], which, c->counters.ptr);
+                ++launches;
+            }
+            LaunchResolve(lc, bp, c->radiance, capacity, c->accum.ptr);
+            ++launches;
+        }
+    }
+    LaunchFinalize(lc, bp, local_pixels, c->accum.ptr, frame_dev, tiles_dev);
+    ++launches;
+    CU_CHECK(c, cudaEventRecord(c->ev_end, stream));
+    CU_CHECK(c, cudaGetLastError());
+    c->timing_pending = true;
+    c->stats.kernel_launches = launches;
+    c->stats.samples = 0;
+    // samples actually owned by this rank (edge tiles excluded)
+    {
+        uint64_t owned = 0;
+        for (uint32_t t = ro.tile_rank; t < bp.num_tiles; t += ro.tile_world) {
+            const uint32_t x0 = (t % bp.tiles_x) * kTileSize, y0 = (t / bp.tiles_x) * kTileSize;
+            owned += static_cast<uint64_t>(std::min<uint32_t>(kTileSize, ro.width - x0)) * std::min<uint32_t>(kTileSize, ro.height - y0);
+        }
+        c->stats.samples = owned * ro.spp;
+    }
+    return B200PT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts, b200pt_handle *out) {
+    if (!scene || !out) return SetGlobalError(B200PT_EINVAL, "b200pt_create: null argument");
+    *out = nullptr;
+    std::unique_ptr<b200pt_context> c(new b200pt_context());
+    int device = opts ? opts->device : -1;
+    cudaError_t e = cudaSuccess;
+    if (device < 0) e = cudaGetDevice(&device);
+    if (e == cudaSuccess) e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return SetGlobalError(B200PT_ECUDA, std::string("CUDA error : \"") + cudaGetErrorString(e) + "\" (no usable GPU; there is no CPU fallback).");
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+
+    std::string err;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!BuildHostScene(*scene, opts ? opts->max_leaf_size : 0, &c->host, &err)) {
+        // same prefix as renderer.cpp:343-346
+        return SetGlobalError(B200PT_EINVAL, "error when commit renderer.\n\t" + err);
+    }
+    int rc = UploadScene(c.get(), *scene);
+    if (rc != B200PT_OK) return rc;
+    uint64_t capacity = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : kDefaultPathsInFlight;
+    capacity = std::max<uint64_t>(capacity, 1024);
+    capacity = std::min<uint64_t>(capacity, 1ull << 28);
+    rc = AllocWavefront(c.get(), capacity);
+    if (rc != B200PT_OK) return rc;
+    if ((e = c->counters.Alloc(1)) != cudaSuccess) return c->CudaFail(e, "cudaMalloc counters");
+    if ((e = cudaMallocHost(&c->pinned_count, sizeof(uint32_t))) != cudaSuccess) return c->CudaFail(e, "cudaMallocHost");
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return c->CudaFail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return c->CudaFail(e, "scene upload");
+    c->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() - c->stats.bvh_build_ms;
+    *out = c.release();
+    return B200PT_OK;
+}
+
+void b200pt_destroy(b200pt_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+int b200pt_render_device(b200pt_handle h, const b200pt_render_opts *opts, float *frame_dev, void *stream) {
+    if (!h || !frame_dev) return SetGlobalError(B200PT_EINVAL, "b200pt_render_device: null argument");
+    ResolvedOpts ro;
+    int rc = ResolveOpts(h, opts, &ro);
+    if (rc != B200PT_OK) return rc;
+    return RenderOnStream(h, ro, frame_dev, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int b200pt_render(b200pt_handle h, const b200pt_render_opts *opts, float *frame_host) {
+    if (!h || !frame_host) return SetGlobalError(B200PT_EINVAL, "b200pt_render: null argument");
+    ResolvedOpts ro;
+    int rc = ResolveOpts(h, opts, &ro);
+    if (rc != B200PT_OK) return rc;
+    const size_t n = static_cast<size_t>(ro.width) * ro.height * 3;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    if (h->frame.count < n) CU_CHECK(h, h->frame.Alloc(n));
+    if (ro.tile_world > 1) CU_CHECK(h, cudaMemcpyAsync(h->frame.ptr, frame_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    rc = RenderOnStream(h, ro, h->frame.ptr, nullptr, h->stream);
+    if (rc != B200PT_OK) return rc;
+    CU_CHECK(h, cudaMemcpyAsync(frame_host, h->frame.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    return B200PT_OK;
+}
+
+uint64_t b200pt_tile_buffer_floats(uint32_t width, uint32_t height, uint32_t tile_world) {
+    if (tile_world == 0) tile_world = 1;
+    return 3ull * PixelsPerRank(width, height, tile_world);
+}
+
+int b200pt_render_tiles_device(b200pt_handle h, const b200pt_render_opts *opts, float *tiles_dev, void *stream) {
+    if (!h || !tiles_dev) return SetGlobalError(B200PT_EINVAL, "b200pt_render_tiles_device: null argument");
+    ResolvedOpts ro;
+    int rc = ResolveOpts(h, opts, &ro);
+    if (rc != B200PT_OK) return rc;
+    return RenderOnStream(h, ro, nullptr, tiles_dev, static_cast<cudaStream_t>(stream));
+}
+
+int b200pt_assemble_tiles_device(b200pt_handle h, uint32_t width, uint32_t height, uint32_t tile_world, const float *gathered_dev,
+                                 float *frame_dev, void *stream) {
+    if (!h || !gathered_dev || !frame_dev || tile_world == 0)
+        return SetGlobalError(B200PT_EINVAL, "b200pt_assemble_tiles_device: bad argument");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    LaunchConfig lc;
+    lc.blocks = h->num_sms * 4, lc.threads = 256, lc.stream = static_cast<cudaStream_t>(stream), lc.stats = false;
+    LaunchAssemble(lc, width, height, tile_world, PixelsPerRank(width, height, tile_world), gathered_dev, frame_dev);
+    CU_CHECK(h, cudaGetLastError());
+    return B200PT_OK;
+}
+
+int b200pt_get_stats(b200pt_handle h, b200pt_stats *out) {
+    if (!h || !out) return SetGlobalError(B200PT_EINVAL, "b200pt_get_stats: null argument");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    if (h->timing_pending) {
+        CU_CHECK(h, cudaEventSynchronize(h->ev_end));
+        float ms = 0.0f;
+        CU_CHECK(h, cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end));
+        h->stats.render_ms = ms;
+        Counters host_counters;
+        CU_CHECK(h, cudaMemcpy(&host_counters, h->counters.ptr, sizeof(Counters), cudaMemcpyDeviceToHost));
+        h->stats.closest_rays = host_counters.closest_rays;
+        h->stats.shadow_rays = host_counters.shadow_rays;
+        h->stats.node_visits = host_counters.node_visits;
+        h->stats.prim_tests = host_counters.prim_tests;
+        h->timing_pending = false;
+    }
+    *out = h->stats;
+    return B200PT_OK;
+}
+
+const char *b200pt_last_error(b200pt_handle h) { return h ? h->error.c_str() : GlobalError(); }
+
+int b200pt_get_kulla_conty(b200pt_handle h, float *brdf_avg, float *albedo_avg) {
+    if (!h || !brdf_avg || !albedo_avg) return SetGlobalError(B200PT_EINVAL, "b200pt_get_kulla_conty: null argument");
+    // The tables are only built at create time when a conductor/dielectric BSDF reads them.
+    bool built = false;
+    for (float v : h->host.kc_albedo_avg) built = built || v != 0.0f;
+    if (!built) ComputeKullaContyTables(h->host.kc_brdf_avg.data(), h->host.kc_albedo_avg.data());
+    memcpy(brdf_avg, h->host.kc_brdf_avg.data(), sizeof(float) * kLutResolution * kLutResolution);
+    memcpy(albedo_avg, h->host.kc_albedo_avg.data(), sizeof(float) * kLutResolution);
+    return B200PT_OK;
+}
+
+int b200pt_get_envmap_tables(b200pt_handle h, float *out, uint64_t capacity_floats, uint64_t *num_floats, float *normalization) {
+    if (!h || !num_floats) return SetGlobalError(B200PT_EINVAL, "b200pt_get_envmap_tables: null argument");
+    *num_floats = h->host.envmap_tables.size();
+    if (normalization) *normalization = h->host.envmap_normalization;
+    if (out && capacity_floats >= h->host.envmap_tables.size() && !h->host.envmap_tables.empty())
+        memcpy(out, h->host.envmap_tables.data(), h->host.envmap_tables.size() * sizeof(float));
+    return B200PT_OK;
+}
+
+} // extern "C"

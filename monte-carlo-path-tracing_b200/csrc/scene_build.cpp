@@ -1,0 +1,1032 @@
+// scene_build.cpp — b200pt_scene_desc -> HostScene (host side of b200pt_create).
+//
+// Restates, for a GPU layout, what the reference derives on the host between the
+// parsed config and the first ray:
+//   geometry bake + per-triangle attributes   src/rtcore/scene.cpp:15-111, 247-324
+//   analytic primitives and their "areas"     src/rtcore/scene.cpp:326-472 (Q3)
+//   per-instance 1/area                       src/rtcore/scene.cpp:493-495
+//   area-light maps + un-normalised CDF       src/renderer/renderer.cpp:271-304 (Q4)
+//   BSDF / medium / emitter derived fields    bsdfs/bsdf.cpp:112-186, medium/medium.cpp:6-39,
+//                                             emitters/emitter.cpp:122-175
+//   env-map tables                            emitters/envmap.cpp:20-68, renderer.cpp:571-611 (Q9)
+//   Kulla-Conty LUTs                          bsdfs/kulla_conty.cpp:13-80
+// The acceleration structure is NOT the reference's per-instance LBVH: one binned-SAH
+// BVH2 over all world-space triangles, 2 child boxes per 64-byte node, BFS-ordered top.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <numeric>
+#include <thread>
+
+#include "host_scene.hpp"
+
+namespace b200pt {
+
+namespace {
+
+constexpr float kPi = 3.141592653589793f;
+constexpr float k2Pi = kPi * 2.0f;
+constexpr float k1DivPi = 1.0f / kPi;
+constexpr float kFltMax = 3.402823466e+38f;
+
+struct V3 {
+    float x, y, z;
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(float s, V3 a) { return {a.x * s, a.y * s, a.z * s}; }
+inline float Dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 Cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, -a.x * b.z + a.z * b.x, a.x * b.y - a.y * b.x}; }
+inline float Length(V3 a) { return sqrtf(Dot(a, a)); }
+inline V3 Normalize(V3 a) { return a * (1.0f / Length(a)); }
+inline V3 Min(V3 a, V3 b) { return {fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)}; }
+inline V3 Max(V3 a, V3 b) { return {fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}; }
+inline V3 Load3(const float *p) { return {p[0], p[1], p[2]}; }
+
+struct M4 {
+    float m[4][4];
+};
+
+M4 Identity() {
+    M4 r{};
+    for (int i = 0; i < 4; ++i) r.m[i][i] = 1.0f;
+    return r;
+}
+M4 LoadM4(const float *p) {
+    M4 r;
+    memcpy(r.m, p, sizeof(r.m));
+    return r;
+}
+M4 Transpose(const M4 &a) {
+    M4 r;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) r.m[i][j] = a.m[j][i];
+    return r;
+}
+M4 Mul(const M4 &a, const M4 &b) {
+    M4 r;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j] + a.m[i][3] * b.m[3][j];
+    return r;
+}
+// General 4x4 inverse by cofactor expansion (same quantity as Mat4::Inverse, mat4.cpp:110-168).
+M4 Inverse(const M4 &a) {
+    const float *s = &a.m[0][0];
+    float inv[16];
+    inv[0] = s[5] * s[10] * s[15] - s[5] * s[11] * s[14] - s[9] * s[6] * s[15] + s[9] * s[7] * s[14] + s[13] * s[6] * s[11] - s[13] * s[7] * s[10];
+    inv[4] = -s[4] * s[10] * s[15] + s[4] * s[11] * s[14] + s[8] * s[6] * s[15] - s[8] * s[7] * s[14] - s[12] * s[6] * s[11] + s[12] * s[7] * s[10];
+    inv[8] = s[4] * s[9] * s[15] - s[4] * s[11] * s[13] - s[8] * s[5] * s[15] + s[8] * s[7] * s[13] + s[12] * s[5] * s[11] - s[12] * s[7] * s[9];
+    inv[12] = -s[4] * s[9] * s[14] + s[4] * s[10] * s[13] + s[8] * s[5] * s[14] - s[8] * s[6] * s[13] - s[12] * s[5] * s[10] + s[12] * s[6] * s[9];
+    inv[1] = -s[1] * s[10] * s[15] + s[1] * s[11] * s[14] + s[9] * s[2] * s[15] - s[9] * s[3] * s[14] - s[13] * s[2] * s[11] + s[13] * s[3] * s[10];
+    inv[5] = s[0] * s[10] * s[15] - s[0] * s[11] * s[14] - s[8] * s[2] * s[15] + s[8] * s[3] * s[14] + s[12] * s[2] * s[11] - s[12] * s[3] * s[10];
+    inv[9] = -s[0] * s[9] * s[15] + s[0] * s[11] * s[13] + s[8] * s[1] * s[15] - s[8] * s[3] * s[13] - s[12] * s[1] * s[11] + s[12] * s[3] * s[9];
+    inv[13] = s[0] * s[9] * s[14] - s[0] * s[10] * s[13] - s[8] * s[1] * s[14] + s[8] * s[2] * s[13] + s[12] * s[1] * s[10] - s[12] * s[2] * s[9];
+    inv[2] = s[1] * s[6] * s[15] - s[1] * s[7] * s[14] - s[5] * s[2] * s[15] + s[5] * s[3] * s[14] + s[13] * s[2] * s[7] - s[13] * s[3] * s[6];
+    inv[6] = -s[0] * s[6] * s[15] + s[0] * s[7] * s[14] + s[4] * s[2] * s[15] - s[4] * s[3] * s[14] - s[12] * s[2] * s[7] + s[12] * s[3] * s[6];
+    inv[10] = s[0] * s[5] * s[15] - s[0] * s[7] * s[13] - s[4] * s[1] * s[15] + s[4] * s[3] * s[13] + s[12] * s[1] * s[7] - s[12] * s[3] * s[5];
+    inv[14] = -s[0] * s[5] * s[14] + s[0] * s[6] * s[13] + s[4] * s[1] * s[14] - s[4] * s[2] * s[13] - s[12] * s[1] * s[6] + s[12] * s[2] * s[5];
+    inv[3] = -s[1] * s[6] * s[11] + s[1] * s[7] * s[10] + s[5] * s[2] * s[11] - s[5] * s[3] * s[10] - s[9] * s[2] * s[7] + s[9] * s[3] * s[6];
+    inv[7] = s[0] * s[6] * s[11] - s[0] * s[7] * s[10] - s[4] * s[2] * s[11] + s[4] * s[3] * s[10] + s[8] * s[2] * s[7] - s[8] * s[3] * s[6];
+    inv[11] = -s[0] * s[5] * s[11] + s[0] * s[7] * s[9] + s[4] * s[1] * s[11] - s[4] * s[3] * s[9] - s[8] * s[1] * s[7] + s[8] * s[3] * s[5];
+    inv[15] = s[0] * s[5] * s[10] - s[0] * s[6] * s[9] - s[4] * s[1] * s[10] + s[4] * s[2] * s[9] + s[8] * s[1] * s[6] - s[8] * s[2] * s[5];
+    const float det = s[0] * inv[0] + s[1] * inv[4] + s[2] * inv[8] + s[3] * inv[12];
+    const float k = 1.0f / det;
+    M4 r;
+    for (int i = 0; i < 16; ++i) (&r.m[0][0])[i] = inv[i] * k;
+    return r;
+}
+V3 TransformPoint(const M4 &m, V3 p) {
+    return {m.m[0][0] * p.x + m.m[0][1] * p.y + m.m[0][2] * p.z + m.m[0][3],
+            m.m[1][0] * p.x + m.m[1][1] * p.y + m.m[1][2] * p.z + m.m[1][3],
+            m.m[2][0] * p.x + m.m[2][1] * p.y + m.m[2][2] * p.z + m.m[2][3]};
+}
+V3 TransformVector(const M4 &m, V3 v) {
+    return {m.m[0][0] * v.x + m.m[0][1] * v.y + m.m[0][2] * v.z, m.m[1][0] * v.x + m.m[1][1] * v.y + m.m[1][2] * v.z,
+            m.m[2][0] * v.x + m.m[2][1] * v.y + m.m[2][2] * v.z};
+}
+Affine ToAffine(const M4 &m) {
+    Affine a;
+    memcpy(a.m, m.m, sizeof(a.m));
+    return a;
+}
+M4 Translate(V3 v) {
+    M4 r = Identity();
+    r.m[0][3] = v.x, r.m[1][3] = v.y, r.m[2][3] = v.z;
+    return r;
+}
+// math.cpp:148-165 (the Mat4 flavour of LocalToWorld used for cylinders)
+M4 LocalToWorldMat(V3 up) {
+    V3 C;
+    if (sqrtf(up.x * up.x + up.z * up.z) > 1.1920929e-7f) {
+        const float len_inv = 1.0f / sqrtf(up.x * up.x + up.z * up.z);
+        C = {-up.z * len_inv, 0, up.x * len_inv};
+    } else {
+        const float len_inv = 1.0f / sqrtf(up.y * up.y + up.z * up.z);
+        C = {0, -up.z * len_inv, up.y * len_inv};
+    }
+    const V3 B = Normalize(Cross(C, up));
+    M4 r = Identity();
+    r.m[0][0] = B.x, r.m[0][1] = B.y, r.m[0][2] = B.z;
+    r.m[1][0] = C.x, r.m[1][1] = C.y, r.m[1][2] = C.z;
+    r.m[2][0] = up.x, r.m[2][1] = up.y, r.m[2][2] = up.z;
+    return r;
+}
+
+F3 ToF3(V3 v) { return {v.x, v.y, v.z}; }
+
+// ---------------------------------------------------------------------------------------------
+// Geometry
+// ---------------------------------------------------------------------------------------------
+struct RawTriangle {
+    V3 p[3], n[3], t[3];
+    float uv[3][2];
+    uint32_t inst;
+    float area; // |e1 x e2| : twice the true area, as the reference uses (scene.cpp:48-49, Q3)
+};
+
+struct MeshView {
+    const float *positions = nullptr, *normals = nullptr, *texcoords = nullptr, *tangents = nullptr,
+                *bitangents = nullptr;
+    const uint32_t *indices = nullptr;
+    uint64_t num_vertices = 0, num_triangles = 0;
+};
+
+// scene.cpp:200-245: the built-in rectangle and cube meshes.
+const float kRectUv[] = {0, 0, 1, 0, 1, 1, 0, 1};
+const float kRectPos[] = {-1, -1, 0, 1, -1, 0, 1, 1, 0, -1, 1, 0};
+const float kRectNrm[] = {0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 1};
+const uint32_t kRectIdx[] = {0, 1, 2, 2, 3, 0};
+const float kCubeUv[] = {0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0,
+                         0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0};
+const float kCubePos[] = {1,  -1, -1, 1,  -1, 1,  -1, -1, 1,  -1, -1, -1, 1,  1,  -1, -1, 1,  -1, -1, 1,  1,  1,  1,  1,
+                          1,  -1, -1, 1,  1,  -1, 1,  1,  1,  1,  -1, 1,  1,  -1, 1,  1,  1,  1,  -1, 1,  1,  -1, -1, 1,
+                          -1, -1, 1,  -1, 1,  1,  -1, 1,  -1, -1, -1, -1, 1,  1,  -1, 1,  -1, -1, -1, -1, -1, -1, 1,  -1};
+const float kCubeNrm[] = {0,  -1, 0, 0,  -1, 0, 0,  -1, 0, 0,  -1, 0, 0, 1, 0,  0, 1, 0,  0, 1, 0,  0, 1, 0,
+                          1,  0,  0, 1,  0,  0, 1,  0,  0, 1,  0,  0, 0, 0, 1,  0, 0, 1,  0, 0, 1,  0, 0, 1,
+                          -1, 0,  0, -1, 0,  0, -1, 0,  0, -1, 0,  0, 0, 0, -1, 0, 0, -1, 0, 0, -1, 0, 0, -1};
+const uint32_t kCubeIdx[] = {0,  1,  2,  3,  0,  2,  4,  5,  6,  7,  4,  6,  8,  9,  10, 11, 8,  10,
+                             12, 13, 14, 15, 12, 14, 16, 17, 18, 19, 16, 18, 20, 21, 22, 23, 20, 22};
+
+// scene.cpp:247-324 (bake to_world) + scene.cpp:15-111 (SetupMeshes).
+bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::vector<RawTriangle> *tris,
+                float *area_sum, std::string *error) {
+    if (mesh.num_triangles == 0 || mesh.indices == nullptr) {
+        *error = "cannot find vertex index info when adding instance to scene.";
+        return false;
+    }
+    if (mesh.num_vertices == 0 || mesh.positions == nullptr) {
+        *error = "cannot find vertex position info when adding instance to scene.";
+        return false;
+    }
+    const uint64_t nv = mesh.num_vertices;
+    std::vector<V3> pos(nv), nrm, tan, bit;
+    for (uint64_t i = 0; i < nv; ++i) pos[i] = TransformPoint(to_world, Load3(mesh.positions + 3 * i));
+    if (mesh.normals) {
+        const M4 normal_to_world = Inverse(Transpose(to_world));
+        nrm.resize(nv);
+        for (uint64_t i = 0; i < nv; ++i) nrm[i] = TransformVector(normal_to_world, Load3(mesh.normals + 3 * i));
+    }
+    if (mesh.tangents) {
+        tan.resize(nv);
+        for (uint64_t i = 0; i < nv; ++i) tan[i] = TransformVector(to_world, Load3(mesh.tangents + 3 * i));
+    }
+    if (mesh.bitangents) {
+        bit.resize(nv);
+        for (uint64_t i = 0; i < nv; ++i) bit[i] = TransformVector(to_world, Load3(mesh.bitangents + 3 * i));
+    }
+    float area_total = 0.0f;
+    tris->reserve(tris->size() + mesh.num_triangles);
+    for (uint64_t f = 0; f < mesh.num_triangles; ++f) {
+        RawTriangle tri;
+        tri.inst = inst;
+        uint32_t idx[3];
+        for (int j = 0; j < 3; ++j) {
+            idx[j] = mesh.indices[3 * f + j];
+            if (idx[j] >= nv) {
+                *error = "mesh index out of range.";
+                return false;
+            }
+        }
+        if (!mesh.texcoords) {
+            tri.uv[0][0] = 0, tri.uv[0][1] = 0, tri.uv[1][0] = 1, tri.uv[1][1] = 0, tri.uv[2][0] = 1, tri.uv[2][1] = 1;
+        } else {
+            for (int j = 0; j < 3; ++j) tri.uv[j][0] = mesh.texcoords[2 * idx[j]], tri.uv[j][1] = mesh.texcoords[2 * idx[j] + 1];
+        }
+        for (int j = 0; j < 3; ++j) tri.p[j] = pos[idx[j]];
+        const V3 v0v1 = tri.p[1] - tri.p[0], v0v2 = tri.p[2] - tri.p[0];
+        const V3 normal_geom = Cross(v0v1, v0v2);
+        tri.area = Length(normal_geom);
+        area_total += tri.area;
+        if (nrm.empty()) {
+            const V3 n = Normalize(normal_geom);
+            for (int j = 0; j < 3; ++j) tri.n[j] = n;
+        } else {
+            for (int j = 0; j < 3; ++j) tri.n[j] = nrm[idx[j]];
+        }
+        if (tan.empty() && bit.empty()) {
+            const float d01u = tri.uv[1][0] - tri.uv[0][0], d01v = tri.uv[1][1] - tri.uv[0][1];
+            const float d02u = tri.uv[2][0] - tri.uv[0][0], d02v = tri.uv[2][1] - tri.uv[0][1];
+            const float r = 1.0f / (d01v * d02u - d01u * d02v);
+            const V3 tangent = Normalize((d01v * v0v2 - d02v * v0v1) * r);
+            for (int j = 0; j < 3; ++j) {
+                const V3 b = Normalize(Cross(tri.n[j], tangent));
+                tri.t[j] = Normalize(Cross(b, tri.n[j]));
+            }
+        } else if (tan.empty()) {
+            for (int j = 0; j < 3; ++j) tri.t[j] = Normalize(Cross(bit[idx[j]], tri.n[j]));
+        } else {
+            for (int j = 0; j < 3; ++j) {
+                const V3 b = Normalize(Cross(tri.n[j], tan[idx[j]]));
+                tri.t[j] = Normalize(Cross(b, tri.n[j]));
+            }
+        }
+        tris->push_back(tri);
+    }
+    *area_sum = area_total;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BVH: binned SAH, two child boxes per node.
+// ---------------------------------------------------------------------------------------------
+struct Box {
+    V3 lo{kFltMax, kFltMax, kFltMax}, hi{-kFltMax, -kFltMax, -kFltMax};
+    void Grow(V3 p) { lo = Min(lo, p), hi = Max(hi, p); }
+    void Grow(const Box &b) { lo = Min(lo, b.lo), hi = Max(hi, b.hi); }
+    float HalfArea() const {
+        const V3 d = hi - lo;
+        return d.x * d.y + d.y * d.z + d.z * d.x;
+    }
+};
+
+struct BuildNode {
+    Box box;
+    int32_t left = -1, right = -1; // children (BuildNode indices) or -1 for leaf
+    uint32_t first = 0, count = 0; // leaf range in the permuted triangle order
+};
+
+class BvhBuilder {
+public:
+    BvhBuilder(const std::vector<Box> &boxes, const std::vector<V3> &centers, uint32_t max_leaf)
+        : boxes_(boxes), centers_(centers), max_leaf_(max_leaf) {
+        order_.resize(boxes.size());
+        std::iota(order_.begin(), order_.end(), 0u);
+        nodes_.reserve(boxes.size() * 2);
+    }
+
+    int32_t Build() { return Recurse(0, static_cast<uint32_t>(order_.size())); }
+    const std::vector<BuildNode> &nodes() const { return nodes_; }
+    const std::vector<uint32_t> &order() const { return order_; }
+
+private:
+    static constexpr int kBins = 32;
+
+    int32_t Recurse(uint32_t begin, uint32_t end) {
+        const int32_t id = static_cast<int32_t>(nodes_.size());
+        nodes_.emplace_back();
+        Box box, cbox;
+        for (uint32_t i = begin; i < end; ++i) {
+            box.Grow(boxes_[order_[i]]);
+            cbox.Grow(centers_[order_[i]]);
+        }
+        nodes_[id].box = box;
+        const uint32_t n = end - begin;
+        auto make_leaf = [&]() {
+            nodes_[id].first = begin;
+            nodes_[id].count = n;
+            return id;
+        };
+        if (n == 1) return make_leaf();
+
+        const V3 ext = cbox.hi - cbox.lo;
+        float best_cost = kFltMax;
+        int best_axis = -1, best_bin = -1;
+        for (int axis = 0; axis < 3; ++axis) {
+            const float lo = (&cbox.lo.x)[axis], e = (&ext.x)[axis];
+            if (!(e > 0.0f)) continue;
+            Box bin_box[kBins];
+            uint32_t bin_cnt[kBins] = {};
+            const float scale = kBins / e;
+            for (uint32_t i = begin; i < end; ++i) {
+                const uint32_t t = order_[i];
+                int b = static_cast<int>(((&centers_[t].x)[axis] - lo) * scale);
+                b = std::min(std::max(b, 0), kBins - 1);
+                bin_box[b].Grow(boxes_[t]);
+                ++bin_cnt[b];
+            }
+            float right_area[kBins];
+            uint32_t right_cnt[kBins];
+            Box acc;
+            uint32_t cnt = 0;
+            for (int b = kBins - 1; b > 0; --b) {
+                acc.Grow(bin_box[b]);
+                cnt += bin_cnt[b];
+                right_area[b] = cnt ? acc.HalfArea() : 0.0f;
+                right_cnt[b] = cnt;
+            }
+            acc = Box();
+            cnt = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                acc.Grow(bin_box[b]);
+                cnt += bin_cnt[b];
+                if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+                const float cost = acc.HalfArea() * cnt + right_area[b + 1] * right_cnt[b + 1];
+                if (cost < best_cost) best_cost = cost, best_axis = axis, best_bin = b;
+            }
+        }
+        const float leaf_cost = box.HalfArea() * n;
+        // traversal step ~ 1 triangle test
+        if (n <= max_leaf_ && (best_axis < 0 || best_cost + box.HalfArea() >= leaf_cost)) return make_leaf();
+
+        uint32_t mid;
+        if (best_axis < 0) {
+            mid = begin + n / 2; // all centroids coincide: split the list
+        } else {
+            const float lo = (&cbox.lo.x)[best_axis], scale = kBins / (&ext.x)[best_axis];
+            auto it = std::partition(order_.begin() + begin, order_.begin() + end, [&](uint32_t t) {
+                int b = static_cast<int>(((&centers_[t].x)[best_axis] - lo) * scale);
+                b = std::min(std::max(b, 0), kBins - 1);
+                return b <= best_bin;
+            });
+            mid = static_cast<uint32_t>(it - order_.begin());
+            if (mid == begin || mid == end) mid = begin + n / 2;
+        }
+        const int32_t l = Recurse(begin, mid);
+        const int32_t r = Recurse(mid, end);
+        nodes_[id].left = l;
+        nodes_[id].right = r;
+        return id;
+    }
+
+    const std::vector<Box> &boxes_;
+    const std::vector<V3> &centers_;
+    uint32_t max_leaf_;
+    std::vector<uint32_t> order_;
+    std::vector<BuildNode> nodes_;
+};
+
+int32_t EncodeLeaf(uint32_t first, uint32_t count) { return ~static_cast<int32_t>((first << 3) | (count - 1)); }
+
+void SetChildBox(BvhNode *node, int which, const Box &b) {
+    if (which == 0) {
+        node->c0xy = {b.lo.x, b.hi.x, b.lo.y, b.hi.y};
+        node->cz.x = b.lo.z, node->cz.y = b.hi.z;
+    } else {
+        node->c1xy = {b.lo.x, b.hi.x, b.lo.y, b.hi.y};
+        node->cz.z = b.lo.z, node->cz.w = b.hi.z;
+    }
+}
+
+// Leaves with more than 8 triangles cannot be encoded; the builder never makes them for max_leaf <= 8.
+void FlattenBvh(const std::vector<BuildNode> &bn, int32_t root, uint32_t top_nodes, std::vector<BvhNode> *out) {
+    out->clear();
+    if (root < 0) return;
+    const Box empty; // inverted box: never hit
+    if (bn[root].left < 0) { // whole scene is one leaf
+        BvhNode n{};
+        SetChildBox(&n, 0, bn[root].box);
+        SetChildBox(&n, 1, empty);
+        n.child0 = EncodeLeaf(bn[root].first, bn[root].count);
+        n.child1 = EncodeLeaf(0, 1);
+        out->push_back(n);
+        return;
+    }
+    // Output order: breadth-first for the first `top_nodes` inner nodes (the part staged in
+    // shared memory), depth-first below so that subtrees stay contiguous in HBM/L2.
+    std::vector<int32_t> out_index(bn.size(), -1);
+    std::vector<int32_t> order;
+    order.reserve(bn.size());
+    std::vector<int32_t> frontier{root};
+    size_t head = 0;
+    while (head < frontier.size() && order.size() < top_nodes) {
+        const int32_t id = frontier[head++];
+        out_index[id] = static_cast<int32_t>(order.size());
+        order.push_back(id);
+        if (bn[bn[id].left].left >= 0) frontier.push_back(bn[id].left);
+        if (bn[bn[id].right].left >= 0) frontier.push_back(bn[id].right);
+    }
+    std::vector<int32_t> stack;
+    for (size_t i = frontier.size(); i-- > head;) stack.push_back(frontier[i]);
+    while (!stack.empty()) {
+        const int32_t id = stack.back();
+        stack.pop_back();
+        out_index[id] = static_cast<int32_t>(order.size());
+        order.push_back(id);
+        if (bn[bn[id].right].left >= 0) stack.push_back(bn[id].right);
+        if (bn[bn[id].left].left >= 0) stack.push_back(bn[id].left);
+    }
+    out->resize(order.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+        const BuildNode &src = bn[order[i]];
+        BvhNode n{};
+        const BuildNode &l = bn[src.left], &r = bn[src.right];
+        SetChildBox(&n, 0, l.box);
+        SetChildBox(&n, 1, r.box);
+        n.child0 = l.left >= 0 ? out_index[src.left] : EncodeLeaf(l.first, l.count);
+        n.child1 = r.left >= 0 ? out_index[src.right] : EncodeLeaf(r.first, r.count);
+        (*out)[i] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Textures on the host (needed for the env-map tables)
+// ---------------------------------------------------------------------------------------------
+// bitmap.cpp:6-56, identity to_uv assumed by the caller where noted.
+V3 GetColorBitmapHost(const DTexture &t, const float *pixels, float u, float v) {
+    const float *m = t.to_uv.m;
+    const float ux = m[0] * u + m[1] * v + m[2] * 0.0f + m[3], uy = m[4] * u + m[5] * v + m[6] * 0.0f + m[7];
+    float x = ux * t.width, y = uy * t.height;
+    while (x < 0) x += t.width;
+    while (x > t.width - 1) x -= t.width;
+    while (y < 0) y += t.height;
+    while (y > t.height - 1) y -= t.height;
+    const uint32_t x0 = static_cast<uint32_t>(x), y0 = static_cast<uint32_t>(y);
+    const float tx = x - x0, ty = y - y0;
+    const uint32_t x1 = tx > 0.0f ? x0 + 1 : x0, y1 = ty > 0.0f ? y0 + 1 : y0;
+    const float *data = pixels + t.pixel_offset;
+    auto lerp = [](float a, float b, float w) { return (1.0f - w) * a + w * b; };
+    if (t.channels == 1) {
+        const float c00 = data[x0 + t.width * y0], c01 = data[x0 + t.width * y1], c10 = data[x1 + t.width * y0],
+                    c11 = data[x1 + t.width * y1];
+        const float c = lerp(lerp(c00, c01, ty), lerp(c10, c11, ty), tx);
+        return {c, c, c};
+    }
+    auto px = [&](uint32_t xx, uint32_t yy) {
+        const uint32_t o = (xx + t.width * yy) * t.channels;
+        return V3{data[o], data[o + 1], data[o + 2]};
+    };
+    const V3 c00 = px(x0, y0), c01 = px(x0, y1), c10 = px(x1, y0), c11 = px(x1, y1);
+    const V3 c0 = (1.0f - ty) * c00 + ty * c01, c1 = (1.0f - ty) * c10 + ty * c11;
+    return (1.0f - tx) * c0 + tx * c1;
+}
+
+// envmap.cpp:20-68 + packing of renderer.cpp:584-605.
+bool BuildEnvMapTables(const DTexture &tex, const float *pixels, std::vector<float> *packed, float *normalization,
+                       std::string *error) {
+    const int width = tex.width, height = tex.height;
+    const float width_inv = 1.0f / width, height_inv = 1.0f / height;
+    std::vector<float> cdf_rows(height + 1), weight_rows(height), cdf_cols(static_cast<size_t>(width + 1) * height);
+    float sum_row = 0.0f;
+    cdf_rows[0] = 0;
+    for (int y = 0; y < height; ++y) {
+        float sum_col = 0.0f;
+        cdf_cols[0] = 0;
+        for (int x = 0; x < width; ++x) {
+            const V3 rgb = GetColorBitmapHost(tex, pixels, x * width_inv, y * height_inv);
+            sum_col += 0.2126f * rgb.x + 0.7152f * rgb.y + 0.0722f * rgb.z;
+            cdf_cols[static_cast<size_t>(y) * (width + 1) + (x + 1)] = sum_col;
+        }
+        cdf_cols[static_cast<size_t>(y) * (width + 1) + width] = 1.0f;
+        const float normalization_col = 1.0f / sum_col;
+        for (int x = 1; x < width; ++x) cdf_cols[static_cast<size_t>(y) * (width + 1) + width - x] *= normalization_col;
+        const float weight = sinf((y + 0.5f) * kPi / height);
+        weight_rows[y] = weight;
+        sum_row += sum_col * weight;
+        cdf_rows[y + 1] = sum_row;
+    }
+    cdf_rows[height] = 1.0f;
+    const float normalization_row = 1.0f / sum_row;
+    for (int y = 1; y < height; ++y) cdf_rows[height - y] *= normalization_row;
+    if (!std::isfinite(sum_row)) {
+        *error = "The environment map contains an invalid floating point value (nan/inf).";
+        return false;
+    }
+    *normalization = static_cast<float>(1.0 / (sum_row * (k2Pi * width_inv) * (kPi * height_inv)));
+    packed->clear();
+    packed->insert(packed->end(), cdf_rows.begin(), cdf_rows.end());
+    packed->insert(packed->end(), weight_rows.begin(), weight_rows.end());
+    packed->insert(packed->end(), cdf_cols.begin(), cdf_cols.end());
+    return true;
+}
+
+// bsdf.cpp:12-56
+float AverageFresnelDielectric(float eta) {
+    if (eta < 1.0) {
+        return -1.4399f * (eta * eta) + 0.7099f * eta + 0.6681f + 0.0636f / eta;
+    }
+    const float inv_eta = 1.0f / eta, inv_eta_2 = inv_eta * inv_eta, inv_eta_3 = inv_eta_2 * inv_eta,
+                inv_eta_4 = inv_eta_3 * inv_eta, inv_eta_5 = inv_eta_4 * inv_eta;
+    return 0.919317f - 3.4793f * inv_eta + 6.75335f * inv_eta_2 - 7.80989f * inv_eta_3 + 4.98554f * inv_eta_4 -
+           1.36881f * inv_eta_5;
+}
+float AverageFresnelConductor(float r, float e) {
+    return 0.087237f + 0.0230685f * e - 0.0864902f * e * e + 0.0774594f * e * e * e + 0.782654f * r -
+           0.136432f * r * r + 0.278708f * r * r * r + 0.19744f * e * r + 0.0360605f * e * e * r - 0.2586f * e * r * r;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Kulla-Conty tables: kulla_conty.cpp:13-80 (+ microfacet.cpp:8-19, 63-75; ray.cpp:49-52)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+float VanDerCorput2(uint32_t index) { // math.hpp:29-41
+    const float base_inv = 1.0f / 2;
+    float result = 0.0f, frac = base_inv;
+    while (index > 0) {
+        result += frac * (index % 2);
+        index = static_cast<uint32_t>(index * base_inv);
+        frac *= base_inv;
+    }
+    return result;
+}
+
+void SampleGgxIso(float xi_0, float xi_1, float roughness, V3 *h) { // microfacet.cpp:8-19 (direction only)
+    const float alpha_2 = roughness * roughness;
+    const float tan_theta_2 = alpha_2 * xi_0 / (1.0f - xi_0), phi = k2Pi * xi_1;
+    const float cos_theta = 1.0f / sqrtf(1.0f + tan_theta_2), sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    *h = {sin_theta * cosf(phi), sin_theta * sinf(phi), cos_theta};
+}
+
+float SmithG1GgxIso(float roughness, V3 v, V3 h) { // microfacet.cpp:63-75
+    const float n_dot_v = v.z;
+    if (n_dot_v * h.z <= 0) return 0;
+    const float cos_theta_2 = n_dot_v * n_dot_v, tan_theta_2 = (1.0f - cos_theta_2) / cos_theta_2,
+                alpha_2 = roughness * roughness;
+    return 2.0f / (1.0f + sqrtf(static_cast<float>(1.0 + static_cast<double>(alpha_2 * tan_theta_2))));
+}
+
+V3 Reflect(V3 wi, V3 n) { return Normalize(wi - (2.0f * Dot(wi, n)) * n); } // ray.cpp:49-52
+
+float IntegrateBrdf(V3 V, float roughness) {
+    constexpr uint32_t sample_count = 1024;
+    constexpr float step = 1.0f / sample_count;
+    const V3 N = {0, 0, 1};
+    float accum = 0.0f;
+    for (uint32_t i = 0; i < sample_count; ++i) {
+        V3 H;
+        SampleGgxIso(i * step, VanDerCorput2(i), roughness, &H);
+        const V3 L = Reflect(V, H);
+        const V3 mV = {-V.x, -V.y, -V.z};
+        const float G = SmithG1GgxIso(roughness, mV, H) * SmithG1GgxIso(roughness, L, H), n_dot_v = Dot(N, mV),
+                    n_dot_l = Dot(N, L), n_dot_h = Dot(N, H), h_dot_v = Dot(H, mV);
+        if (n_dot_l > 0.0f && n_dot_h > 0.0f && h_dot_v > 0.0f) accum += (h_dot_v * G) / (n_dot_v * n_dot_h);
+    }
+    return fminf(accum * step, 1.0f);
+}
+
+float IntegrateAlbedo(V3 V, float roughness, float brdf) {
+    constexpr uint32_t sample_count = 1024;
+    constexpr float step = 1.0f / sample_count;
+    const V3 N = {0, 0, 1};
+    float accum = 0.0f;
+    for (uint32_t i = 0; i < sample_count; ++i) {
+        V3 H;
+        SampleGgxIso(i * step, VanDerCorput2(i), roughness, &H);
+        const V3 L = Reflect(V, H);
+        const V3 mV = {-V.x, -V.y, -V.z};
+        const float n_dot_l = Dot(N, L), n_dot_h = Dot(N, H), h_dot_v = Dot(mV, H);
+        if (n_dot_l > 0.0f && n_dot_h > 0.0f && h_dot_v > 0.0f) accum += brdf * n_dot_l;
+    }
+    return accum * 2.0f * step;
+}
+
+} // namespace
+
+void ComputeKullaContyTables(float *brdf_avg, float *albedo_avg) {
+    const float step = 1.0f / kLutResolution;
+    auto row = [&](int i) {
+        float albedo_accum = 0.0f;
+        const float roughness = step * (static_cast<float>(i) + 0.5f);
+        for (int j = kLutResolution - 1; j >= 0; --j) {
+            const float n_dot_v = step * (static_cast<float>(j) + 0.5f);
+            const V3 V = {-sqrtf(1.f - n_dot_v * n_dot_v), 0.0f, -n_dot_v};
+            const float b = IntegrateBrdf(V, roughness);
+            brdf_avg[i * kLutResolution + j] = b;
+            albedo_accum += IntegrateAlbedo(V, roughness, b);
+        }
+        albedo_avg[i] = albedo_accum * step;
+    };
+    const unsigned num_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < num_threads; ++t)
+        pool.emplace_back([&, t]() {
+            for (int i = static_cast<int>(t); i < kLutResolution; i += static_cast<int>(num_threads)) row(i);
+        });
+    for (std::thread &th : pool) th.join();
+}
+
+DCamera MakeCamera(const b200pt_camera &cam, uint32_t width, uint32_t height) {
+    const V3 eye = Load3(cam.eye), look_at = Load3(cam.look_at), up_in = Load3(cam.up);
+    const float fov_y = cam.fov_x * static_cast<int>(height) / static_cast<int>(width);
+    const V3 front = Normalize(look_at - eye);
+    const V3 right = Normalize(Cross(front, up_in));
+    const V3 up = Normalize(Cross(right, front));
+    const float to_rad = 0.01745329251994329576923690768489f;
+    DCamera c;
+    c.eye = ToF3(eye);
+    c.front = ToF3(front);
+    c.view_dx = ToF3(right * tanf((0.5f * cam.fov_x) * to_rad));
+    c.view_dy = ToF3(up * tanf((0.5f * fov_y) * to_rad));
+    return c;
+}
+
+bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, HostScene *hs, std::string *error) {
+    if (d.abi_version != B200PT_ABI_VERSION) {
+        *error = "b200pt_scene_desc.abi_version mismatch";
+        return false;
+    }
+    if (max_leaf_size == 0) max_leaf_size = 4;
+    max_leaf_size = std::min(max_leaf_size, 8u);
+    hs->camera = d.camera;
+
+    // ---- textures ----
+    for (uint64_t i = 0; i < d.num_textures; ++i) {
+        const b200pt_texture &t = d.textures[i];
+        DTexture o{};
+        o.type = t.type;
+        o.width = t.width, o.height = t.height, o.channels = t.channels;
+        o.color0 = {t.color0[0], t.color0[1], t.color0[2]};
+        o.color1 = {t.color1[0], t.color1[1], t.color1[2]};
+        memcpy(o.to_uv.m, t.to_uv, sizeof(o.to_uv.m));
+        o.pixel_offset = t.pixel_offset;
+        if (t.type == B200PT_TEX_BITMAP) {
+            const uint64_t n = static_cast<uint64_t>(t.width) * t.height * t.channels;
+            if (t.width <= 0 || t.height <= 0 || t.channels <= 0 || t.pixel_offset + n > d.num_pixels) {
+                *error = "bitmap texture " + std::to_string(i) + " exceeds the pixel pool.";
+                return false;
+            }
+        } else if (t.type != B200PT_TEX_CONSTANT && t.type != B200PT_TEX_CHECKERBOARD) {
+            *error = "unknow texture type."; // renderer.cpp:421
+            return false;
+        }
+        hs->textures.push_back(o);
+    }
+    auto check_texture = [&](uint32_t id, bool allow_invalid) {
+        if (id == kInvalid && allow_invalid) return true;
+        if (id >= d.num_textures) {
+            *error = "cannot find texture (id " + std::to_string(id) + ")."; // renderer.cpp:441-446
+            return false;
+        }
+        return true;
+    };
+
+    // ---- BSDFs (bsdf.cpp:112-186) ----
+    bool need_kulla_conty = false;
+    for (uint64_t i = 0; i < d.num_bsdfs; ++i) {
+        const b200pt_bsdf &b = d.bsdfs[i];
+        DBsdf o{};
+        o.type = b.type;
+        o.twosided = b.twosided;
+        o.id_opacity = b.id_opacity, o.id_bump_map = b.id_bump_map;
+        o.id_radiance = b.id_radiance, o.id_diffuse_reflectance = b.id_diffuse_reflectance;
+        o.id_roughness_u = b.id_roughness_u, o.id_roughness_v = b.id_roughness_v;
+        o.id_specular_reflectance = b.id_specular_reflectance;
+        o.id_specular_transmittance = b.id_specular_transmittance;
+        // The reference never copies RoughDiffuseInfo::use_fast_approx into its BsdfData (bsdf.cpp:136-141):
+        // the field keeps the zero the union was initialised with, i.e. the full Oren-Nayar model is always used.
+        o.use_fast_approx = 0;
+        o.eta = b.eta, o.eta_inv = 1.0f / b.eta;
+        o.F_avg_s = 1.0f, o.F_avg_inv_s = 1.0f, o.reflectivity_s = 1.0f;
+        bool ok = check_texture(b.id_opacity, true) && check_texture(b.id_bump_map, true);
+        switch (b.type) {
+        case B200PT_BSDF_AREA_LIGHT:
+            ok = ok && check_texture(b.id_radiance, false);
+            break;
+        case B200PT_BSDF_DIFFUSE:
+            ok = ok && check_texture(b.id_diffuse_reflectance, false);
+            break;
+        case B200PT_BSDF_ROUGH_DIFFUSE:
+            ok = ok && check_texture(b.id_diffuse_reflectance, false) && check_texture(b.id_roughness_u, false);
+            break;
+        case B200PT_BSDF_CONDUCTOR:
+            ok = ok && check_texture(b.id_roughness_u, false) && check_texture(b.id_roughness_v, false) &&
+                 check_texture(b.id_specular_reflectance, false);
+            o.reflectivity = {b.reflectivity[0], b.reflectivity[1], b.reflectivity[2]};
+            o.edgetint = {b.edgetint[0], b.edgetint[1], b.edgetint[2]};
+            o.F_avg = {AverageFresnelConductor(b.reflectivity[0], b.edgetint[0]),
+                       AverageFresnelConductor(b.reflectivity[1], b.edgetint[1]),
+                       AverageFresnelConductor(b.reflectivity[2], b.edgetint[2])};
+            need_kulla_conty = true;
+            break;
+        case B200PT_BSDF_DIELECTRIC:
+            o.F_avg_s = AverageFresnelDielectric(b.eta);
+            o.F_avg_inv_s = AverageFresnelDielectric(1.0f / b.eta);
+            need_kulla_conty = true;
+            [[fallthrough]]; // bsdf.cpp:157-181
+        case B200PT_BSDF_THIN_DIELECTRIC:
+            ok = ok && check_texture(b.id_roughness_u, false) && check_texture(b.id_roughness_v, false) &&
+                 check_texture(b.id_specular_reflectance, false) && check_texture(b.id_specular_transmittance, false);
+            o.twosided = 1;
+            o.reflectivity_s = ((b.eta - 1.0f) * (b.eta - 1.0f)) / ((b.eta + 1.0f) * (b.eta + 1.0f));
+            break;
+        case B200PT_BSDF_PLASTIC:
+            ok = ok && check_texture(b.id_roughness_u, false) && check_texture(b.id_diffuse_reflectance, false) &&
+                 check_texture(b.id_specular_reflectance, false);
+            o.reflectivity_s = ((b.eta - 1.0f) * (b.eta - 1.0f)) / ((b.eta + 1.0f) * (b.eta + 1.0f));
+            o.F_avg_s = AverageFresnelDielectric(b.eta);
+            break;
+        default:
+            *error = "unknow BSDF type."; // renderer.cpp:484
+            return false;
+        }
+        if (!ok) return false;
+        hs->bsdfs.push_back(o);
+    }
+
+    // ---- media (medium.cpp:6-39) ----
+    for (uint64_t i = 0; i < d.num_media; ++i) {
+        const b200pt_medium &m = d.media[i];
+        DMedium o{};
+        o.sigma_s = {m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]};
+        o.sigma_t = {m.sigma_a[0] + m.sigma_s[0], m.sigma_a[1] + m.sigma_s[1], m.sigma_a[2] + m.sigma_s[2]};
+        o.sampling_weight = 0.0f;
+        for (int dim = 0; dim < 3; ++dim) {
+            const float sigma_t = m.sigma_a[dim] + m.sigma_s[dim];
+            const float albedo = m.sigma_s[dim] * (1.0f / sigma_t);
+            if (albedo > o.sampling_weight && sigma_t > 0) o.sampling_weight = albedo;
+        }
+        if (o.sampling_weight > 0 && o.sampling_weight < 0.5f) o.sampling_weight = 0.5f;
+        o.phase_type = m.phase_type;
+        o.g = {m.g[0], m.g[1], m.g[2]};
+        hs->media.push_back(o);
+    }
+
+    // ---- instances + geometry ----
+    std::vector<RawTriangle> tris;
+    std::vector<float> inst_area(d.num_instances, 0.0f);
+    hs->instances.resize(d.num_instances);
+    Box scene_box;
+    for (uint64_t i = 0; i < d.num_instances; ++i) {
+        const b200pt_instance &in = d.instances[i];
+        DInstance &o = hs->instances[i];
+        o = DInstance{};
+        o.id_bsdf = in.id_bsdf;
+        o.id_medium_int = in.id_medium_int, o.id_medium_ext = in.id_medium_ext;
+        o.area_light = kInvalid, o.analytic = kInvalid;
+        if (in.id_bsdf != kInvalid && in.id_bsdf >= d.num_bsdfs) o.id_bsdf = kInvalid; // renderer.cpp:277
+        if ((in.id_medium_int != kInvalid && in.id_medium_int >= d.num_media) ||
+            (in.id_medium_ext != kInvalid && in.id_medium_ext >= d.num_media)) {
+            *error = "instance " + std::to_string(i) + " refers to a medium that does not exist.";
+            return false;
+        }
+        const M4 to_world = LoadM4(in.to_world);
+        MeshView mesh;
+        bool is_mesh = false;
+        switch (in.type) {
+        case B200PT_INST_RECTANGLE:
+            mesh.positions = kRectPos, mesh.normals = kRectNrm, mesh.texcoords = kRectUv, mesh.indices = kRectIdx;
+            mesh.num_vertices = 4, mesh.num_triangles = 2;
+            is_mesh = true;
+            break;
+        case B200PT_INST_CUBE:
+            mesh.positions = kCubePos, mesh.normals = kCubeNrm, mesh.texcoords = kCubeUv, mesh.indices = kCubeIdx;
+            mesh.num_vertices = 24, mesh.num_triangles = 12;
+            is_mesh = true;
+            break;
+        case B200PT_INST_MESHES: {
+            const uint64_t nv = in.num_vertices;
+            auto in_range = [&](uint64_t off, uint64_t pool) { return off == B200PT_NO_OFFSET || off + nv <= pool; };
+            if (!in_range(in.position_offset, d.num_positions) || !in_range(in.normal_offset, d.num_normals) ||
+                !in_range(in.texcoord_offset, d.num_texcoords) || !in_range(in.tangent_offset, d.num_tangents) ||
+                !in_range(in.bitangent_offset, d.num_bitangents) ||
+                in.index_offset + in.num_triangles > d.num_triangles) {
+                *error = "instance " + std::to_string(i) + ": mesh ranges exceed the attribute pools.";
+                return false;
+            }
+            if (in.position_offset != B200PT_NO_OFFSET) mesh.positions = d.positions + 3 * in.position_offset;
+            if (in.normal_offset != B200PT_NO_OFFSET) mesh.normals = d.normals + 3 * in.normal_offset;
+            if (in.texcoord_offset != B200PT_NO_OFFSET) mesh.texcoords = d.texcoords + 2 * in.texcoord_offset;
+            if (in.tangent_offset != B200PT_NO_OFFSET) mesh.tangents = d.tangents + 3 * in.tangent_offset;
+            if (in.bitangent_offset != B200PT_NO_OFFSET) mesh.bitangents = d.bitangents + 3 * in.bitangent_offset;
+            mesh.indices = d.indices + 3 * in.index_offset;
+            mesh.num_vertices = mesh.positions ? nv : 0;
+            mesh.num_triangles = in.num_triangles;
+            is_mesh = true;
+            break;
+        }
+        case B200PT_INST_SPHERE: { // scene.cpp:326-372, sphere.cpp:9-15
+            AnalyticPrim p{};
+            p.type = kSphere, p.inst = static_cast<uint32_t>(i);
+            p.radius = in.sphere_radius;
+            p.center = {in.sphere_center[0], in.sphere_center[1], in.sphere_center[2]};
+            p.to_world = ToAffine(to_world);
+            p.to_local = ToAffine(Inverse(to_world));
+            p.normal_to_world = ToAffine(Inverse(Transpose(to_world)));
+            const V3 c = Load3(in.sphere_center), r{in.sphere_radius, in.sphere_radius, in.sphere_radius};
+            Box b;
+            b.Grow(TransformPoint(to_world, c + r));
+            b.Grow(TransformPoint(to_world, c - r));
+            memcpy(p.bmin, &b.lo, 12), memcpy(p.bmax, &b.hi, 12);
+            const V3 center_world = TransformPoint(to_world, c),
+                     boundary_world = TransformPoint(to_world, c + V3{in.sphere_radius, 0.0f, 0.0f});
+            const float radius_world = Length(center_world - boundary_world);
+            inst_area[i] = 4.0f * kPi * (radius_world * radius_world);
+            o.analytic = static_cast<uint32_t>(hs->analytic.size());
+            hs->analytic.push_back(p);
+            scene_box.Grow(b);
+            break;
+        }
+        case B200PT_INST_DISK: { // scene.cpp:374-416, disk.cpp:9-15
+            AnalyticPrim p{};
+            p.type = kDisk, p.inst = static_cast<uint32_t>(i);
+            p.to_world = ToAffine(to_world);
+            p.to_local = ToAffine(Inverse(to_world));
+            p.normal_to_world = ToAffine(Inverse(Transpose(to_world)));
+            Box b;
+            b.Grow(TransformPoint(to_world, V3{-0.5f, -0.5f, 0}));
+            b.Grow(TransformPoint(to_world, V3{0.5f, 0.5f, 0}));
+            memcpy(p.bmin, &b.lo, 12), memcpy(p.bmax, &b.hi, 12);
+            const float radius_world = Length(TransformPoint(to_world, V3{0, 0, 0}) - TransformPoint(to_world, V3{0.5f, 0, 0}));
+            inst_area[i] = kPi * (radius_world * radius_world);
+            o.analytic = static_cast<uint32_t>(hs->analytic.size());
+            hs->analytic.push_back(p);
+            scene_box.Grow(b);
+            break;
+        }
+        case B200PT_INST_CYLINDER: { // scene.cpp:418-472, cylinder.cpp:9-19
+            AnalyticPrim p{};
+            p.type = kCylinder, p.inst = static_cast<uint32_t>(i);
+            const V3 p0 = Load3(in.cylinder_p0), p1 = Load3(in.cylinder_p1);
+            M4 m = LocalToWorldMat(Normalize(p1 - p0));
+            m = Mul(Translate(p0), m);
+            m = Mul(to_world, m);
+            p.length = Length(TransformPoint(m, V3{0, 0, Length(p1 - p0)}) - TransformPoint(m, V3{0, 0, 0}));
+            p.radius = Length(TransformPoint(m, V3{in.cylinder_radius, 0, 0}) - TransformPoint(m, V3{0, 0, 0}));
+            p.to_world = ToAffine(m);
+            p.to_local = ToAffine(Inverse(m));
+            p.normal_to_world = ToAffine(Inverse(Transpose(m)));
+            Box b;
+            b.Grow(TransformPoint(m, V3{p.radius, p.radius, 0}));
+            b.Grow(TransformPoint(m, V3{-p.radius, -p.radius, 0}));
+            b.Grow(TransformPoint(m, V3{p.radius, p.radius, p.length}));
+            b.Grow(TransformPoint(m, V3{-p.radius, -p.radius, p.length}));
+            memcpy(p.bmin, &b.lo, 12), memcpy(p.bmax, &b.hi, 12);
+            inst_area[i] = k2Pi * (p.radius * p.radius);
+            o.analytic = static_cast<uint32_t>(hs->analytic.size());
+            hs->analytic.push_back(p);
+            scene_box.Grow(b);
+            break;
+        }
+        default:
+            *error = "unknow instance type."; // scene.cpp:184
+            return false;
+        }
+        if (is_mesh && !AppendMesh(mesh, to_world, static_cast<uint32_t>(i), &tris, &inst_area[i], error)) return false;
+        o.pdf_area = 1.0f / inst_area[i];
+    }
+
+    // ---- area lights (renderer.cpp:271-304) ----
+    hs->cdf_area_light.assign(1, 0.0f);
+    for (uint64_t i = 0; i < d.num_instances; ++i) {
+        const uint32_t id_bsdf = hs->instances[i].id_bsdf;
+        if (id_bsdf != kInvalid && d.bsdfs[id_bsdf].type == B200PT_BSDF_AREA_LIGHT) {
+            hs->instances[i].area_light = static_cast<uint32_t>(hs->map_area_light_instance.size());
+            hs->map_area_light_instance.push_back(static_cast<uint32_t>(i));
+            hs->cdf_area_light.push_back(d.bsdfs[id_bsdf].area_light_weight + hs->cdf_area_light.back());
+        }
+    }
+
+    // ---- BVH over all triangles ----
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t nt = tris.size();
+    std::vector<Box> boxes(nt);
+    std::vector<V3> centers(nt);
+    for (size_t i = 0; i < nt; ++i) {
+        for (int j = 0; j < 3; ++j) boxes[i].Grow(tris[i].p[j]);
+        centers[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
+        scene_box.Grow(boxes[i]);
+    }
+    std::vector<uint32_t> order;
+    if (nt > 0) {
+        if (nt >= (1u << 28)) {
+            *error = "too many triangles for the leaf encoding.";
+            return false;
+        }
+        BvhBuilder builder(boxes, centers, max_leaf_size);
+        const int32_t root = builder.Build();
+        FlattenBvh(builder.nodes(), root, 1024, &hs->nodes);
+        order = builder.order();
+    }
+    hs->tri_verts.resize(nt);
+    hs->tri_shade.resize(nt);
+    for (size_t i = 0; i < nt; ++i) {
+        const RawTriangle &t = tris[order[i]];
+        TriVerts &v = hs->tri_verts[i];
+        float inst_bits;
+        memcpy(&inst_bits, &t.inst, 4);
+        v.v0 = {t.p[0].x, t.p[0].y, t.p[0].z, inst_bits};
+        v.v1 = {t.p[1].x, t.p[1].y, t.p[1].z, 0.0f};
+        v.v2 = {t.p[2].x, t.p[2].y, t.p[2].z, 0.0f};
+        TriShade &s = hs->tri_shade[i];
+        memset(&s, 0, sizeof(s));
+        for (int j = 0; j < 3; ++j) {
+            s.n[j][0] = t.n[j].x, s.n[j][1] = t.n[j].y, s.n[j][2] = t.n[j].z;
+            s.t[j][0] = t.t[j].x, s.t[j][1] = t.t[j].y, s.t[j][2] = t.t[j].z;
+            s.uv[j][0] = t.uv[j][0], s.uv[j][1] = t.uv[j][1];
+        }
+        s.inst = t.inst;
+    }
+    hs->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    memcpy(hs->scene_bmin, &scene_box.lo, 12);
+    memcpy(hs->scene_bmax, &scene_box.hi, 12);
+
+    // ---- triangle CDFs of mesh area lights (replaces the area-weighted BVH descent of blas.cpp:79-98) ----
+    for (uint32_t light = 0; light < hs->map_area_light_instance.size(); ++light) {
+        const uint32_t inst = hs->map_area_light_instance[light];
+        DInstance &o = hs->instances[inst];
+        if (o.analytic != kInvalid) continue;
+        o.light_tri_begin = static_cast<uint32_t>(hs->light_tri_ids.size());
+        double total = 0.0;
+        for (size_t i = 0; i < nt; ++i)
+            if (tris[order[i]].inst == inst) {
+                hs->light_tri_ids.push_back(static_cast<uint32_t>(i));
+                total += tris[order[i]].area;
+                hs->light_tri_cdf.push_back(static_cast<float>(total));
+            }
+        o.light_tri_count = static_cast<uint32_t>(hs->light_tri_ids.size()) - o.light_tri_begin;
+        for (uint32_t k = 0; k < o.light_tri_count; ++k)
+            hs->light_tri_cdf[o.light_tri_begin + k] = static_cast<float>(hs->light_tri_cdf[o.light_tri_begin + k] / total);
+        if (o.light_tri_count) hs->light_tri_cdf[o.light_tri_begin + o.light_tri_count - 1] = 1.0f;
+    }
+
+    // ---- emitters (emitter.cpp:122-175, renderer.cpp:522-620) ----
+    uint32_t id_sun = kInvalid, id_envmap = kInvalid;
+    for (uint64_t i = 0; i < d.num_emitters; ++i) {
+        const b200pt_emitter &e = d.emitters[i];
+        DEmitter o{};
+        o.type = e.type;
+        o.id_texture = e.id_texture;
+        o.position = {e.position[0], e.position[1], e.position[2]};
+        o.direction = {e.direction[0], e.direction[1], e.direction[2]};
+        o.radiance = {e.radiance[0], e.radiance[1], e.radiance[2]};
+        const M4 to_world = LoadM4(e.to_world);
+        o.to_world = ToAffine(to_world);
+        o.to_local = ToAffine(Inverse(to_world));
+        switch (e.type) {
+        case B200PT_EMIT_POINT:
+        case B200PT_EMIT_DIRECTIONAL:
+            break;
+        case B200PT_EMIT_SPOT:
+            o.cutoff_angle = e.cutoff_angle;
+            o.cos_cutoff_angle = cosf(e.cutoff_angle);
+            o.uv_factor = tanf(e.cutoff_angle);
+            o.beam_width = e.beam_width;
+            o.cos_beam_width = cosf(e.beam_width);
+            o.transition_width_rcp = 1.0f / (e.cutoff_angle - e.beam_width);
+            o.position = ToF3(TransformPoint(to_world, V3{0, 0, 0}));
+            if (!check_texture(e.id_texture, true)) return false;
+            break;
+        case B200PT_EMIT_SUN:
+            if (!check_texture(e.id_texture, false)) return false;
+            o.cos_cutoff_angle = e.cos_cutoff_angle;
+            id_sun = static_cast<uint32_t>(i);
+            break;
+        case B200PT_EMIT_ENVMAP: {
+            if (!check_texture(e.id_texture, false)) return false;
+            const DTexture &tex = hs->textures[e.id_texture];
+            if (tex.type != B200PT_TEX_BITMAP) {
+                *error = "radiance texture '" + std::to_string(e.id_texture) + "' for emitter '" + std::to_string(i) +
+                         "' is not a bitmap."; // renderer.cpp:575-580
+                return false;
+            }
+            if (!BuildEnvMapTables(tex, d.pixels, &hs->envmap_tables, &hs->envmap_normalization, error)) return false;
+            o.env_width = tex.width, o.env_height = tex.height;
+            o.env_normalization = hs->envmap_normalization;
+            // InitEnvMap (emitter.cpp:166-175) against the packing [rows | weights | cols] (Q9)
+            o.env_cdf_cols = 0;
+            o.env_cdf_rows = tex.height + 1;
+            o.env_weight_rows = (tex.height + 1) + tex.height;
+            id_envmap = static_cast<uint32_t>(i);
+            break;
+        }
+        case B200PT_EMIT_CONSTANT:
+            id_envmap = static_cast<uint32_t>(i);
+            break;
+        default:
+            *error = "unknow emitter type."; // renderer.cpp:563
+            return false;
+        }
+        hs->emitters.push_back(o);
+    }
+
+    // ---- integrator (renderer.cpp:622-676) ----
+    DIntegrator &ig = hs->integrator;
+    ig.type = d.integrator.type;
+    if (ig.type != B200PT_INTEGRATOR_PATH && ig.type != B200PT_INTEGRATOR_VOLPATH) {
+        *error = "unknow integrator type"; // renderer.cpp:664
+        return false;
+    }
+    ig.hide_emitters = d.integrator.hide_emitters;
+    ig.pdf_rr = d.integrator.pdf_rr;
+    ig.pdf_rr_rcp = d.integrator.pdf_rr; // Q1: renderer.cpp:634 stores pdf_rr, not its reciprocal
+    ig.depth_rr = d.integrator.depth_rr;
+    ig.depth_max = d.integrator.depth_max;
+    ig.num_emitters = static_cast<uint32_t>(d.num_emitters);
+    ig.num_area_lights = static_cast<uint32_t>(hs->map_area_light_instance.size());
+    ig.id_sun = id_sun;
+    ig.id_envmap = id_envmap;
+
+    // ---- Kulla-Conty LUTs (renderer.cpp:311-314); only read by conductor/dielectric BSDFs ----
+    hs->kc_brdf_avg.assign(kLutResolution * kLutResolution, 0.0f);
+    hs->kc_albedo_avg.assign(kLutResolution, 0.0f);
+    if (need_kulla_conty) ComputeKullaContyTables(hs->kc_brdf_avg.data(), hs->kc_albedo_avg.data());
+    return true;
+}
+
+} // namespace b200pt

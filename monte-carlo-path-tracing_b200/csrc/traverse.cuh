@@ -1,0 +1,252 @@
+// traverse.cuh — BVH closest-hit / any-hit traversal and ray-primitive tests.
+//
+// Replaces TLAS::Intersect / IntersectAny (src/rtcore/accel/tlas.cpp:13-76),
+// BLAS::Intersect / IntersectAny (src/rtcore/accel/blas.cpp:18-77), AABB::Intersect
+// (src/rtcore/accel/aabb.cpp:29-48) and the primitive tests of src/rtcore/primitives/*.
+// Geometry is in world space in one BVH2 (the reference's instances carry no transform of
+// their own: to_world is baked into the triangles, scene.cpp:261-281), so the two-level
+// walk collapses into one.
+#pragma once
+#include "vecmath.cuh"
+
+namespace b200pt {
+
+struct Ray {
+    V3 o, d;
+    float tmin, tmax;
+};
+
+struct HitRec {       // 16 B, what the closest-hit kernel writes per ray
+    float t;
+    uint32_t prim;    // triangle index (| kPrimInsideBit) | kPrimAnalyticBit+index | kPrimMiss
+    float u, v;       // triangle: barycentric weights of vertex 0 and 1; .u sign bit unused
+};
+
+// Per-ray constants of Woop's watertight test (ray.cpp:24-46) and of the slab test (ray.cpp:21-22).
+struct RayPre {
+    V3 idir, ood;     // 1/d (with the reference's 1e-4 substitute for zero components), o/d
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+
+__device__ __forceinline__ RayPre Precompute(const Ray &r) {
+    RayPre p;
+    p.idir = {1.0f / (r.d.x != 0 ? r.d.x : kEpsilonDistance), 1.0f / (r.d.y != 0 ? r.d.y : kEpsilonDistance),
+              1.0f / (r.d.z != 0 ? r.d.z : kEpsilonDistance)};
+    p.ood = r.o * p.idir;
+    const float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
+    p.kz = (ax > ay && ax > az) ? 0 : (ay > az ? 1 : 2);
+    p.kx = p.kz + 1;
+    if (p.kx == 3) p.kx = 0;
+    p.ky = p.kx + 1;
+    if (p.ky == 3) p.ky = 0;
+    const float dz = Comp(r.d, p.kz);
+    if (dz < 0.0f) {
+        const int t = p.kx;
+        p.kx = p.ky;
+        p.ky = t;
+    }
+    p.Sx = Comp(r.d, p.kx) / dz;
+    p.Sy = Comp(r.d, p.ky) / dz;
+    p.Sz = 1.0f / dz;
+    return p;
+}
+
+// Woop, Benthin, Wald 2013 — triangle.cpp:23-87.  Products and differences are kept un-fused
+// (__fmul_rn/__fsub_rn) so shared edges evaluate identically from both sides.
+__device__ __forceinline__ bool IntersectTriangleWoop(const Ray &ray, const RayPre &pre, const float4 &p0, const float4 &p1,
+                                                      const float4 &p2, float *t_out, float *u_out, float *v_out,
+                                                      bool *inside) {
+    const V3 A = {p0.x - ray.o.x, p0.y - ray.o.y, p0.z - ray.o.z};
+    const V3 B = {p1.x - ray.o.x, p1.y - ray.o.y, p1.z - ray.o.z};
+    const V3 C = {p2.x - ray.o.x, p2.y - ray.o.y, p2.z - ray.o.z};
+    const float Akz = Comp(A, pre.kz), Bkz = Comp(B, pre.kz), Ckz = Comp(C, pre.kz);
+    const float Ax = __fsub_rn(Comp(A, pre.kx), __fmul_rn(pre.Sx, Akz)), Ay = __fsub_rn(Comp(A, pre.ky), __fmul_rn(pre.Sy, Akz));
+    const float Bx = __fsub_rn(Comp(B, pre.kx), __fmul_rn(pre.Sx, Bkz)), By = __fsub_rn(Comp(B, pre.ky), __fmul_rn(pre.Sy, Bkz));
+    const float Cx = __fsub_rn(Comp(C, pre.kx), __fmul_rn(pre.Sx, Ckz)), Cy = __fsub_rn(Comp(C, pre.ky), __fmul_rn(pre.Sy, Ckz));
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) { // exact edge hits: redo in double (triangle.cpp:50-63)
+        U = static_cast<float>(__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx)));
+        V = static_cast<float>(__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx)));
+        W = static_cast<float>(__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax)));
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    const float Az = pre.Sz * Akz, Bz = pre.Sz * Bkz, Cz = pre.Sz * Ckz;
+    const float T = U * Az + V * Bz + W * Cz;
+    const float det_inv = 1.0f / det;
+    const float t = T * det_inv;
+    if (t > ray.tmax || t < ray.tmin) return false;
+    *t_out = t;
+    *u_out = U * det_inv;
+    *v_out = V * det_inv;
+    *inside = det_inv < 0;
+    return true;
+}
+
+// aabb.cpp:29-48 for a world-space box.
+__device__ __forceinline__ bool IntersectBox(const float *bmin, const float *bmax, const Ray &ray, const RayPre &pre) {
+    const float tx0 = (bmin[0] - ray.o.x) * pre.idir.x, tx1 = (bmax[0] - ray.o.x) * pre.idir.x;
+    const float ty0 = (bmin[1] - ray.o.y) * pre.idir.y, ty1 = (bmax[1] - ray.o.y) * pre.idir.y;
+    const float tz0 = (bmin[2] - ray.o.z) * pre.idir.z, tz1 = (bmax[2] - ray.o.z) * pre.idir.z;
+    const float t_enter = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), ray.tmin));
+    const float t_exit = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), ray.tmax));
+    return t_enter <= t_exit;
+}
+
+// Distance-only halves of sphere.cpp:17-44, disk.cpp:17-40, cylinder.cpp:21-60.
+// The hit attributes (normal, uv, frame) are rebuilt in the shading stage from the hit point.
+__device__ __forceinline__ bool IntersectAnalytic(const AnalyticPrim &p, const Ray &ray, float *t_out) {
+    const V3 o_l = XformPoint(p.to_local, ray.o), d_l = XformVector(p.to_local, ray.d);
+    if (p.type == kSphere) {
+        const V3 ro = o_l - mk3(p.center);
+        const float a = Dot(d_l, d_l), b = 2.0f * Dot(d_l, ro), c = Dot(ro, ro) - Sqr(p.radius);
+        float t_near = 0.0f, t_far = 0.0f;
+        if (!SolveQuadratic(a, b, c, &t_near, &t_far) || t_far < kEpsilonDistance) return false;
+        float t = t_near < kEpsilonDistance ? t_far : t_near;
+        const V3 pos_l = ro + t * d_l, pos = XformPoint(p.to_world, pos_l + mk3(p.center));
+        t = Length(pos - ray.o);
+        if (t > ray.tmax || t < ray.tmin) return false;
+        *t_out = t;
+        return true;
+    } else if (p.type == kDisk) {
+        const float t_z = -o_l.z / d_l.z;
+        if (t_z < kEpsilonFloat) return false;
+        const V3 pos_l = o_l + t_z * d_l;
+        if (Length(pos_l) > 0.5f) return false;
+        const V3 pos = XformPoint(p.to_world, pos_l);
+        const float t = Length(pos - ray.o);
+        if (t > ray.tmax || t < ray.tmin) return false;
+        *t_out = t;
+        return true;
+    } else {
+        const float a = Sqr(d_l.x) + Sqr(d_l.y), b = 2.0f * (d_l.x * o_l.x + d_l.y * o_l.y),
+                    c = Sqr(o_l.x) + Sqr(o_l.y) - Sqr(p.radius);
+        float t_near = 0.0f, t_far = 0.0f;
+        if (!SolveQuadratic(a, b, c, &t_near, &t_far) || t_far < kEpsilonDistance) return false;
+        const float z_near = o_l.z + d_l.z * t_near, z_far = o_l.z + d_l.z * t_far;
+        float t = 0;
+        if (kEpsilonDistance < t_near && 0.0f <= z_near && z_near <= p.length)
+            t = t_near;
+        else if (0.0f <= z_far && z_far <= p.length)
+            t = t_far;
+        else
+            return false;
+        const V3 pos = XformPoint(p.to_world, o_l + t * d_l);
+        t = Length(pos - ray.o);
+        if (t > ray.tmax || t < ray.tmin) return false;
+        *t_out = t;
+        return true;
+    }
+}
+
+struct TraversalCounters {
+    uint32_t nodes = 0, prims = 0;
+};
+
+constexpr int kStackSize = 64;
+constexpr int kSentinel = 0x7FFFFFFF;
+constexpr int kTopNodes = 512;  // nodes staged in shared memory (32 KB)
+
+// One BVH2 node = 4 x 16 B loads; `top` is the shared-memory copy of nodes [0, num_top).
+__device__ __forceinline__ void LoadNode(const BvhNode *__restrict__ nodes, const float4 *top, int num_top, int index,
+                                         float4 *n0, float4 *n1, float4 *nz, int *c0, int *c1) {
+    const float4 *src = (index < num_top) ? top + index * 4 : reinterpret_cast<const float4 *>(nodes + index);
+    if (index < num_top) {
+        *n0 = src[0], *n1 = src[1], *nz = src[2];
+        const float4 links = src[3];
+        *c0 = __float_as_int(links.x), *c1 = __float_as_int(links.y);
+    } else {
+        *n0 = __ldg(src), *n1 = __ldg(src + 1), *nz = __ldg(src + 2);
+        const float4 links = __ldg(src + 3);
+        *c0 = __float_as_int(links.x), *c1 = __float_as_int(links.y);
+    }
+}
+
+// ANY = true: occlusion query (returns on the first hit); false: closest hit.
+template <bool ANY, bool STATS>
+__device__ __forceinline__ bool Traverse(const DeviceScene &scene, const float4 *top, int num_top, Ray ray, HitRec *hit,
+                                         TraversalCounters *counters) {
+    const RayPre pre = Precompute(ray);
+    bool found = false;
+    if (!ANY) {
+        hit->t = ray.tmax;
+        hit->prim = kPrimMiss;
+        hit->u = hit->v = 0.0f;
+    }
+
+    // Analytic primitives (spheres, disks, cylinders) are few: tested linearly.
+    for (uint32_t i = 0; i < scene.num_analytic; ++i) {
+        const AnalyticPrim &p = scene.analytic[i];
+        if (STATS) ++counters->nodes;
+        if (!IntersectBox(p.bmin, p.bmax, ray, pre)) continue;
+        if (STATS) ++counters->prims;
+        float t;
+        if (IntersectAnalytic(p, ray, &t)) {
+            if (ANY) return true;
+            ray.tmax = t;
+            hit->t = t;
+            hit->prim = kPrimAnalyticBit | i;
+            found = true;
+        }
+    }
+    if (scene.num_nodes == 0) return found;
+
+    int stack[kStackSize];
+    int sp = 0;
+    int cur = 0;
+    while (cur != kSentinel) {
+        if (cur >= 0) {
+            float4 n0, n1, nz;
+            int child0, child1;
+            LoadNode(scene.nodes, top, num_top, cur, &n0, &n1, &nz, &child0, &child1);
+            if (STATS) counters->nodes += 2;
+            const float c0lox = fmaf(n0.x, pre.idir.x, -pre.ood.x), c0hix = fmaf(n0.y, pre.idir.x, -pre.ood.x);
+            const float c0loy = fmaf(n0.z, pre.idir.y, -pre.ood.y), c0hiy = fmaf(n0.w, pre.idir.y, -pre.ood.y);
+            const float c0loz = fmaf(nz.x, pre.idir.z, -pre.ood.z), c0hiz = fmaf(nz.y, pre.idir.z, -pre.ood.z);
+            const float c1lox = fmaf(n1.x, pre.idir.x, -pre.ood.x), c1hix = fmaf(n1.y, pre.idir.x, -pre.ood.x);
+            const float c1loy = fmaf(n1.z, pre.idir.y, -pre.ood.y), c1hiy = fmaf(n1.w, pre.idir.y, -pre.ood.y);
+            const float c1loz = fmaf(nz.z, pre.idir.z, -pre.ood.z), c1hiz = fmaf(nz.w, pre.idir.z, -pre.ood.z);
+            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), ray.tmin));
+            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), ray.tmax));
+            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), ray.tmin));
+            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), ray.tmax));
+            const bool hit0 = c0min <= c0max, hit1 = c1min <= c1max;
+            if (!hit0 && !hit1) {
+                cur = sp > 0 ? stack[--sp] : kSentinel;
+            } else if (hit0 && hit1) {
+                const bool swap = c1min < c0min;
+                stack[sp++] = swap ? child0 : child1;
+                cur = swap ? child1 : child0;
+            } else {
+                cur = hit0 ? child0 : child1;
+            }
+        } else {
+            const uint32_t leaf = static_cast<uint32_t>(~cur);
+            const uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
+            const float4 *verts = reinterpret_cast<const float4 *>(scene.tri_verts + first);
+            for (uint32_t j = 0; j < count; ++j) {
+                const float4 p0 = __ldg(verts + 3 * j), p1 = __ldg(verts + 3 * j + 1), p2 = __ldg(verts + 3 * j + 2);
+                if (STATS) ++counters->prims;
+                float t, u, v;
+                bool inside;
+                if (IntersectTriangleWoop(ray, pre, p0, p1, p2, &t, &u, &v, &inside)) {
+                    if (ANY) return true;
+                    ray.tmax = t;
+                    hit->t = t;
+                    hit->prim = (first + j) | (inside ? kPrimInsideBit : 0u);
+                    hit->u = u;
+                    hit->v = v;
+                    found = true;
+                }
+            }
+            cur = sp > 0 ? stack[--sp] : kSentinel;
+        }
+    }
+    return found;
+}
+
+} // namespace b200pt

@@ -1,0 +1,668 @@
+// wavefront.cu — the sm_100a kernels of the wavefront path tracer.
+//
+// Replaces the per-pixel / per-sample loop DrawPixel (src/renderer/renderer.cpp:62-85) and the
+// integrators ShadePath (src/renderer/integrators/path.cpp:8-236) and ShadeVolPath
+// (src/renderer/integrators/volpath.cpp:8-485).  Instead of one thread walking one pixel's
+// paths to completion (the reference's DispathRaysCuda megakernel, renderer.cpp:88-95), paths
+// advance in lock step, one bounce per round, through queues of SoA ray records; survivors of
+// Russian roulette / throughput cut-off are compacted with warp ballots so every traversal
+// launch works on a dense queue.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "shading.cuh"
+#include "wavefront.cuh"
+
+namespace b200pt {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// Stage the top of the BVH (nodes [0, num_top), breadth-first order) into shared memory with one
+// TMA bulk copy (cp.async.bulk, completion signalled on an mbarrier).  Every ray walks these
+// nodes, so they are served at shared-memory latency instead of L2.
+__device__ __forceinline__ int StageTopNodes(const DeviceScene &scene, float4 *top, uint64_t *bar) {
+    const int num_top = min(static_cast<int>(scene.num_nodes), kTopNodes);
+    if (num_top == 0) return 0;
+    const uint32_t bytes = static_cast<uint32_t>(num_top) * sizeof(BvhNode);
+    const uint32_t bar_addr = SmemAddr(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         SmemAddr(top)),
+                     "l"(scene.nodes), "r"(bytes), "r"(bar_addr)
+                     : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar_addr)
+                     : "memory");
+    }
+    return num_top;
+}
+
+// Warp-ballot compaction: every lane of the warp must call this; lanes with flag get a unique
+// slot in the queue whose length is *counter.
+__device__ __forceinline__ uint32_t WarpAppend(bool flag, uint32_t *counter) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+    if (ballot == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(ballot) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(ballot & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounters &tc, uint32_t rays, bool shadow, Counters *c) {
+    if (!stats) return;
+    // one atomic per warp
+    uint32_t nodes = tc.nodes, prims = tc.prims, r = rays;
+    for (int o = 16; o > 0; o >>= 1) {
+        nodes += __shfl_down_sync(0xffffffffu, nodes, o);
+        prims += __shfl_down_sync(0xffffffffu, prims, o);
+        r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&c->node_visits, static_cast<unsigned long long>(nodes));
+        atomicAdd(&c->prim_tests, static_cast<unsigned long long>(prims));
+        atomicAdd(shadow ? &c->shadow_rays : &c->closest_rays, static_cast<unsigned long long>(r));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_primary: camera-ray generation (renderer.cpp:62-75) fused with the first closest hit.
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ DeviceScene scene,
+                                                      const __grid_constant__ BatchParams bp, PathQueue q,
+                                                      float *radiance, uint32_t capacity, Counters *counters) {
+    extern __shared__ float4 top[];
+    __shared__ uint64_t bar;
+    const int num_top = StageTopNodes(scene, top, &bar);
+
+    const uint32_t nslots = bp.pixel_count * bp.sample_count;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    TraversalCounters tc;
+    uint32_t rays = 0;
+    for (uint32_t i0 = tid - lane; i0 < nslots; i0 += stride) {
+        const uint32_t slot = i0 + lane;
+        bool active = slot < nslots;
+        uint32_t px = 0, py = 0, s = 0;
+        if (active) {
+            const uint32_t local_pixel = bp.pixel_begin + slot / bp.sample_count;
+            s = bp.sample_begin + slot % bp.sample_count;
+            active = LocalPixelToImage(bp, local_pixel, &px, &py);
+        }
+        Ray ray;
+        HitRec hit;
+        bool found = false;
+        if (active) {
+            const float u = s * bp.spp_inv, v = VanDerCorput2(s + 1);
+            const float x = 2.0f * (px + u) / static_cast<int>(bp.width) - 1.0f,
+                        y = 1.0f - 2.0f * (py + v) / static_cast<int>(bp.height);
+            ray.o = mk3(bp.camera.eye);
+            ray.d = Normalize(mk3(bp.camera.front) + x * mk3(bp.camera.view_dx) + y * mk3(bp.camera.view_dy));
+            ray.tmin = kEpsilonDistance;
+            ray.tmax = kMaxFloat;
+            found = Traverse<false, STATS>(scene, top, num_top, ray, &hit, &tc);
+            ++rays;
+            if (!found) { // path.cpp:24-35: escaped camera ray sees the environment and the sun disc
+                V3 L = mk3(0.0f);
+                if (scene.integrator.id_envmap != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_envmap], ray.d);
+                if (scene.integrator.id_sun != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_sun], ray.d);
+                if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {
+                    radiance[slot] = L.x;
+                    radiance[capacity + slot] = L.y;
+                    radiance[2 * capacity + slot] = L.z;
+                }
+            }
+        }
+        const uint32_t idx = WarpAppend(found, &counters->queue[0]);
+        if (found) {
+            q.ox[idx] = ray.o.x, q.oy[idx] = ray.o.y, q.oz[idx] = ray.o.z;
+            q.dx[idx] = ray.d.x, q.dy[idx] = ray.d.y, q.dz[idx] = ray.d.z;
+            q.tr[idx] = 1.0f, q.tg[idx] = 1.0f, q.tb[idx] = 1.0f;
+            q.pdf[idx] = 0.0f;
+            q.slot[idx] = slot;
+            if (q.medium != nullptr) {
+                q.medium[idx] = kInvalid;
+                q.wx[idx] = -ray.d.x, q.wy[idx] = -ray.d.y, q.wz[idx] = -ray.d.z;
+            }
+            q.hit[idx] = hit;
+        }
+    }
+    FlushCounters(STATS, tc, rays, false, counters);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_extend: closest hit for a compacted queue (TLAS::Intersect, tlas.cpp:13-43).
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ DeviceScene scene, PathQueue q, int which,
+                                                     Counters *counters) {
+    extern __shared__ float4 top[];
+    __shared__ uint64_t bar;
+    const uint32_t n = counters->queue[which];
+    if (blockIdx.x * blockDim.x >= n) return;
+    const int num_top = StageTopNodes(scene, top, &bar);
+    TraversalCounters tc;
+    uint32_t rays = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Ray ray;
+        ray.o = mk3(q.ox[i], q.oy[i], q.oz[i]);
+        ray.d = mk3(q.dx[i], q.dy[i], q.dz[i]);
+        ray.tmin = kEpsilonDistance;
+        ray.tmax = kMaxFloat;
+        HitRec hit;
+        Traverse<false, STATS>(scene, top, num_top, ray, &hit, &tc);
+        q.hit[i] = hit;
+        ++rays;
+    }
+    if (STATS) {
+        __syncwarp();
+        FlushCounters(true, tc, rays, false, counters);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_shadow: occlusion test of the NEE rays (TLAS::IntersectAny, tlas.cpp:44-76).
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ DeviceScene scene, ShadowQueue sq, float *radiance,
+                                                    uint32_t capacity, Counters *counters) {
+    extern __shared__ float4 top[];
+    __shared__ uint64_t bar;
+    const uint32_t n = counters->shadow;
+    if (blockIdx.x * blockDim.x >= n) return;
+    const int num_top = StageTopNodes(scene, top, &bar);
+    TraversalCounters tc;
+    uint32_t rays = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Ray ray;
+        ray.o = mk3(sq.ox[i], sq.oy[i], sq.oz[i]);
+        ray.d = mk3(sq.dx[i], sq.dy[i], sq.dz[i]);
+        ray.tmin = kEpsilonDistance;
+        ray.tmax = sq.tmax[i];
+        ++rays;
+        if (!Traverse<true, STATS>(scene, top, num_top, ray, nullptr, &tc)) {
+            const uint32_t slot = sq.slot[i];
+            atomicAdd(radiance + slot, sq.cr[i]);
+            atomicAdd(radiance + capacity + slot, sq.cg[i]);
+            atomicAdd(radiance + 2 * capacity + slot, sq.cb[i]);
+        }
+    }
+    if (STATS) {
+        __syncwarp();
+        FlushCounters(true, tc, rays, true, counters);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_shade
+// ---------------------------------------------------------------------------------------------
+struct ShadowCandidate {
+    bool valid = false;
+    V3 o = {0, 0, 0}, d = {0, 0, 0}, c = {0, 0, 0};
+    float tmax = 0;
+};
+
+__device__ __forceinline__ void PushShadow(const ShadowCandidate &sc, uint32_t slot, ShadowQueue sq, Counters *counters) {
+    const bool ok = sc.valid && (sc.c.x != 0.0f || sc.c.y != 0.0f || sc.c.z != 0.0f);
+    const uint32_t idx = WarpAppend(ok, &counters->shadow);
+    if (ok) {
+        sq.ox[idx] = sc.o.x, sq.oy[idx] = sc.o.y, sq.oz[idx] = sc.o.z;
+        sq.dx[idx] = sc.d.x, sq.dy[idx] = sc.d.y, sq.dz[idx] = sc.d.z;
+        sq.tmax[idx] = sc.tmax;
+        sq.cr[idx] = sc.c.x, sq.cg[idx] = sc.c.y, sq.cb[idx] = sc.c.z;
+        sq.slot[idx] = slot;
+    }
+}
+
+// Transmittance/pdf of a shadow segment through the medium at the shading point
+// (volpath.cpp:276-285, 341-350, 397-402, 456-461).
+__device__ __forceinline__ bool ShadowMediumAttenuation(const DMedium *medium, float distance, V3 *att) {
+    *att = mk3(1.0f);
+    if (medium == nullptr) return true;
+    MediumRec mrec;
+    mrec.distance = distance;
+    MediumEvaluate(*medium, &mrec);
+    if (!mrec.valid) return false;
+    *att = mrec.att / mrec.pdf;
+    return true;
+}
+
+template <bool VOL>
+__global__ void __launch_bounds__(kThreads) k_shade(const __grid_constant__ DeviceScene scene,
+                                                    const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue qin,
+                                                    int which_in, PathQueue qout, ShadowQueue sq, float *radiance,
+                                                    Counters *counters, uint32_t capacity) {
+    const uint32_t n = counters->queue[which_in];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const DIntegrator &ig = scene.integrator;
+    for (uint32_t i0 = tid - lane; i0 < n; i0 += stride) {
+        const uint32_t i = i0 + lane;
+        const bool active = i < n;
+        bool alive = active;
+
+        // ---- load the path segment ----
+        Ray ray;
+        ray.o = ray.d = mk3(0.0f);
+        ray.tmin = kEpsilonDistance, ray.tmax = kMaxFloat;
+        V3 att = mk3(0.0f), wo = mk3(0.0f), wo_prev = mk3(0.0f), Ladd = mk3(0.0f);
+        float pdf_sample = 0.0f;
+        uint32_t slot = 0, ray_medium = kInvalid;
+        HitRec hit;
+        hit.prim = kPrimMiss, hit.t = kMaxFloat, hit.u = hit.v = 0.0f;
+        if (active) {
+            ray.o = mk3(qin.ox[i], qin.oy[i], qin.oz[i]);
+            ray.d = mk3(qin.dx[i], qin.dy[i], qin.dz[i]);
+            att = mk3(qin.tr[i], qin.tg[i], qin.tb[i]);
+            pdf_sample = qin.pdf[i];
+            slot = qin.slot[i];
+            hit = qin.hit[i];
+            wo = -ray.d;
+            if (VOL) {
+                ray_medium = qin.medium[i];
+                wo_prev = mk3(qin.wx[i], qin.wy[i], qin.wz[i]);
+            }
+        }
+        const uint32_t local_pixel = bp.pixel_begin + slot / bp.sample_count;
+        const uint32_t sample = bp.sample_begin + slot % bp.sample_count;
+        uint32_t px = 0, py = 0;
+        LocalPixelToImage(bp, local_pixel, &px, &py);
+        Rng rng(py * bp.width + px, sample, depth, bp.key);
+
+        // ---- the vertex this segment arrives at ----
+        const bool has_hit = hit.prim != kPrimMiss;
+        Surf surf;
+        surf.inside = false, surf.inst = 0, surf.uv = {0, 0};
+        surf.pos = surf.n = surf.t = surf.b = mk3(0.0f);
+        const DBsdf *bsdf = nullptr;
+        if (alive && has_hit) {
+            ray.tmax = hit.t;
+            if (hit.prim & kPrimAnalyticBit)
+                surf = SurfAnalytic(scene, hit.prim & ~kPrimAnalyticBit, ray, hit.t);
+            else
+                surf = SurfTriangle(scene, hit.prim & kPrimIndexMask, hit.u, hit.v, (hit.prim & kPrimInsideBit) != 0);
+            const uint32_t id_bsdf = scene.instances[surf.inst].id_bsdf;
+            if (id_bsdf != kInvalid) bsdf = scene.bsdfs + id_bsdf;
+        }
+
+        // ---- participating medium along the segment (volpath.cpp:44-60, 119-137, 163-186) ----
+        bool scattering = false;
+        const DMedium *vertex_medium = nullptr; // medium of a scattering vertex
+        V3 vertex_pos = surf.pos;
+        if (VOL && alive) {
+            uint32_t id_medium = ray_medium;
+            if (id_medium == kInvalid && has_hit) {
+                const bool inside = Dot(-ray.d, surf.n) > 0 ? surf.inside : !surf.inside;
+                id_medium = inside ? scene.instances[surf.inst].id_medium_int : scene.instances[surf.inst].id_medium_ext;
+            }
+            if (id_medium != kInvalid) {
+                MediumRec mrec;
+                MediumSample(scene.media[id_medium], ray.tmax, rng, &mrec);
+                if (mrec.valid) {
+                    att *= mrec.att / mrec.pdf;
+                    if (mrec.scattered) {
+                        scattering = true;
+                        vertex_pos = ray.o + ray.d * mrec.distance;
+                        vertex_medium = scene.media + id_medium;
+                        ray_medium = id_medium;
+                        // volpath.cpp only refreshes `wo` at surface vertices (:233): a medium vertex keeps
+                        // the wo that was used at the previous vertex.
+                        wo = wo_prev;
+                    }
+                }
+            }
+        }
+
+        // ---- arrival at a surface / escape (path.cpp:24-53 for depth 1, :81-132 afterwards) ----
+        if (alive && !scattering) {
+            if (!has_hit) {
+                // depth 1 misses are finished inside k_primary
+                if (depth > 1 && ig.id_envmap != kInvalid) {
+                    const DEmitter &env = scene.emitters[ig.id_envmap];
+                    const V3 Le = EmitterEvaluateDir(scene, env, ray.d);
+                    const float pdf_direct = EmitterPdf(scene, env, ray.d), w = MisWeight(pdf_sample, pdf_direct);
+                    Ladd += w * att * Le;
+                }
+                alive = false;
+            } else if (bsdf != nullptr) {
+                if (surf.inside && !bsdf->twosided) {
+                    alive = false; // back of a one-sided surface absorbs
+                } else if (bsdf->type == B200PT_BSDF_AREA_LIGHT) {
+                    if (depth == 1) {
+                        if (!ig.hide_emitters) Ladd += TexColor(scene, bsdf->id_radiance, surf.uv);
+                    } else {
+                        const float cos_theta_prime = Dot(-ray.d, surf.n);
+                        if (cos_theta_prime >= kEpsilonFloat) {
+                            const uint32_t light = scene.instances[surf.inst].area_light;
+                            const float pdf_area = (__ldg(scene.cdf_area_light + light + 1) - __ldg(scene.cdf_area_light + light)) *
+                                                   scene.instances[surf.inst].pdf_area,
+                                        pdf_direct = pdf_area * Sqr(ray.tmax) / cos_theta_prime,
+                                        w = MisWeight(pdf_sample, pdf_direct);
+                            Ladd += w * att * TexColor(scene, bsdf->id_radiance, surf.uv);
+                        }
+                    }
+                    alive = false;
+                }
+            }
+            if (alive) {
+                wo = -ray.d;
+                if (depth > 1 && depth - 1 >= ig.depth_rr) att *= ig.pdf_rr_rcp; // Q1
+            }
+        }
+
+        // ---- loop condition of iteration `depth` (path.cpp:57-60) ----
+        if (alive) {
+            if (!(depth < ig.depth_rr || (depth < ig.depth_max && rng.Next() < ig.pdf_rr))) alive = false;
+        }
+
+        // ---- next-event estimation (path.cpp:138-236, volpath.cpp:247-485) ----
+        const DMedium *nee_medium = nullptr;
+        if (VOL && alive) {
+            if (scattering) {
+                nee_medium = vertex_medium;
+            } else {
+                const bool inside = Dot(wo, surf.n) > 0 ? surf.inside : !surf.inside;
+                const uint32_t id_medium = inside ? scene.instances[surf.inst].id_medium_int : scene.instances[surf.inst].id_medium_ext;
+                if (id_medium != kInvalid) nee_medium = scene.media + id_medium;
+            }
+        }
+        for (uint32_t e = 0; e < ig.num_emitters; ++e) {
+            ShadowCandidate sc;
+            if (alive) {
+                const DEmitter &em = scene.emitters[e];
+                const float xi_0 = rng.Next(), xi_1 = rng.Next();
+                const EmitterRec erec = EmitterSample(scene, em, vertex_pos, xi_0, xi_1);
+                bool ok = erec.valid;
+                if (ok && !scattering && Dot(-erec.wi, surf.n) < kEpsilonFloat) ok = false;
+                V3 medium_att = mk3(1.0f);
+                if (ok && VOL && !ShadowMediumAttenuation(nee_medium, erec.distance, &medium_att)) ok = false;
+                V3 f = mk3(0.0f);
+                float pdf_f = 0.0f;
+                if (ok) {
+                    if (scattering) {
+                        PhaseRec prec;
+                        prec.wi = erec.wi, prec.wo = wo;
+                        PhaseEvaluate(*vertex_medium, &prec);
+                        ok = prec.valid;
+                        f = prec.att, pdf_f = prec.pdf;
+                    } else {
+                        const BsdfRec brec = EvaluateRayPath(scene, erec.wi, wo, surf, bsdf);
+                        ok = brec.valid;
+                        f = brec.att, pdf_f = brec.pdf;
+                    }
+                }
+                if (ok) {
+                    const V3 Le = EmitterEvaluateRec(scene, em, erec);
+                    if (erec.harsh) {
+                        sc.c = att * (Le * medium_att * f);
+                    } else {
+                        const float pdf_direct = EmitterPdf(scene, em, -erec.wi);
+                        if (pdf_direct > kEpsilonFloat)
+                            sc.c = att * (MisWeight(pdf_direct, pdf_f) * Le * medium_att * f / pdf_direct);
+                        else
+                            ok = false;
+                    }
+                }
+                if (ok) {
+                    sc.valid = true;
+                    sc.o = vertex_pos, sc.d = -erec.wi;
+                    sc.tmax = erec.distance - kEpsilonDistance;
+                }
+            }
+            PushShadow(sc, slot, sq, counters);
+        }
+        if (ig.num_area_lights != 0) {
+            ShadowCandidate sc;
+            if (alive) {
+                const float xi_l = rng.Next();
+                const uint32_t index_area_light = BinarySearch(ig.num_area_lights + 1, scene.cdf_area_light, xi_l) - 1; // Q4
+                const uint32_t light_inst = __ldg(scene.map_area_light_instance + index_area_light);
+                const float xi_0 = rng.Next(), xi_1 = rng.Next(), xi_2 = rng.Next();
+                const LightPoint lp = SampleInstance(scene, light_inst, xi_0, xi_1, xi_2);
+                const V3 d_vec = vertex_pos - lp.pos;
+                const float distance = Length(d_vec);
+                const V3 wi = Normalize(d_vec);
+                const float cos_theta_prime = Dot(wi, lp.n);
+                bool ok = cos_theta_prime >= kEpsilonFloat;
+                if (ok && !scattering && Dot(-wi, surf.n) < kEpsilonFloat) ok = false;
+                V3 medium_att = mk3(1.0f);
+                if (ok && VOL && !ShadowMediumAttenuation(nee_medium, distance, &medium_att)) ok = false;
+                V3 f = mk3(0.0f);
+                float pdf_f = 0.0f;
+                if (ok) {
+                    if (scattering) {
+                        PhaseRec prec;
+                        prec.wi = wi, prec.wo = wo;
+                        PhaseEvaluate(*vertex_medium, &prec);
+                        ok = prec.valid;
+                        f = prec.att, pdf_f = prec.pdf;
+                    } else {
+                        const BsdfRec brec = EvaluateRayPath(scene, wi, wo, surf, bsdf);
+                        ok = brec.valid;
+                        f = brec.att, pdf_f = brec.pdf;
+                    }
+                }
+                if (ok) {
+                    const float pdf_area = (__ldg(scene.cdf_area_light + index_area_light + 1) -
+                                            __ldg(scene.cdf_area_light + index_area_light)) *
+                                           scene.instances[light_inst].pdf_area,
+                                pdf_direct = pdf_area * Sqr(distance) / cos_theta_prime, w = MisWeight(pdf_direct, pdf_f);
+                    const DBsdf &light_bsdf = scene.bsdfs[scene.instances[light_inst].id_bsdf];
+                    const V3 Le = TexColor(scene, light_bsdf.id_radiance, lp.uv);
+                    sc.c = att * (w * (Le * medium_att * f / pdf_direct));
+                    sc.valid = true;
+                    sc.o = lp.pos, sc.d = wi; // traced from the light towards the shading point (path.cpp:201-202)
+                    sc.tmax = distance - kEpsilonDistance;
+                }
+            }
+            PushShadow(sc, slot, sq, counters);
+        }
+
+        // ---- sample the continuation (path.cpp:66-79, volpath.cpp:98-117, 147-161) ----
+        V3 next_d = mk3(0.0f);
+        if (alive) {
+            V3 wi, f;
+            float pdf;
+            bool ok;
+            if (scattering) {
+                PhaseRec prec;
+                prec.wo = wo;
+                PhaseSample(*vertex_medium, rng, &prec);
+                ok = prec.valid;
+                wi = prec.wi, f = prec.att, pdf = prec.pdf;
+            } else {
+                const BsdfRec brec = SampleRayPath(scene, wo, surf, bsdf, rng);
+                ok = brec.valid;
+                wi = brec.wi, f = brec.att, pdf = brec.pdf;
+            }
+            if (!ok) {
+                alive = false;
+            } else {
+                att *= f / pdf;
+                pdf_sample = pdf;
+                if (MaxComp(att) < kEpsilon) alive = false;
+                next_d = -wi;
+            }
+        }
+        const uint32_t out = WarpAppend(alive, &counters->queue[which_in ^ 1]);
+        if (alive) {
+            qout.ox[out] = vertex_pos.x, qout.oy[out] = vertex_pos.y, qout.oz[out] = vertex_pos.z;
+            qout.dx[out] = next_d.x, qout.dy[out] = next_d.y, qout.dz[out] = next_d.z;
+            qout.tr[out] = att.x, qout.tg[out] = att.y, qout.tb[out] = att.z;
+            qout.pdf[out] = pdf_sample;
+            qout.slot[out] = slot;
+            if (VOL) {
+                qout.medium[out] = scattering ? ray_medium : kInvalid;
+                qout.wx[out] = wo.x, qout.wy[out] = wo.y, qout.wz[out] = wo.z;
+            }
+        }
+        if (active && (Ladd.x != 0.0f || Ladd.y != 0.0f || Ladd.z != 0.0f)) {
+            radiance[slot] += Ladd.x;
+            radiance[capacity + slot] += Ladd.y;
+            radiance[2 * capacity + slot] += Ladd.z;
+        }
+        (void)out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_reset(Counters *c, int which_queue, bool reset_shadow) {
+    if (which_queue >= 0) c->queue[which_queue] = 0;
+    if (reset_shadow) c->shadow = 0;
+}
+
+// renderer.cpp:76-84: clamp each SAMPLE to <= 1 per channel (Q2), then sum the pixel's samples.
+// One warp per pixel: lanes stride over the pixel's samples (coalesced), shuffle-reduce.
+__global__ void __launch_bounds__(kThreads) k_resolve(const __grid_constant__ BatchParams bp, const float *radiance,
+                                                      uint32_t capacity, float *accum) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, num_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = warp; p < bp.pixel_count; p += num_warps) {
+        float r = 0.0f, g = 0.0f, b = 0.0f;
+        const uint32_t base = p * bp.sample_count;
+        for (uint32_t s = lane; s < bp.sample_count; s += 32) {
+            r += fminf(radiance[base + s], 1.0f);
+            g += fminf(radiance[capacity + base + s], 1.0f);
+            b += fminf(radiance[2 * capacity + base + s], 1.0f);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            r += __shfl_down_sync(0xffffffffu, r, o);
+            g += __shfl_down_sync(0xffffffffu, g, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+            float *a = accum + 3ull * (bp.pixel_begin + p);
+            a[0] += r, a[1] += g, a[2] += b;
+        }
+    }
+}
+
+// mean over spp (renderer.cpp:82-84) and scatter from tile order to the row-major frame.
+__global__ void k_finalize(const __grid_constant__ BatchParams bp, uint32_t num_local_pixels, const float *accum, float *frame,
+                           float *tiles) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < num_local_pixels; p += gridDim.x * blockDim.x) {
+        const float r = accum[3ull * p] * bp.spp_inv, g = accum[3ull * p + 1] * bp.spp_inv, b = accum[3ull * p + 2] * bp.spp_inv;
+        if (tiles != nullptr) {
+            tiles[3ull * p] = r, tiles[3ull * p + 1] = g, tiles[3ull * p + 2] = b;
+        }
+        uint32_t i, j;
+        if (frame != nullptr && LocalPixelToImage(bp, p, &i, &j)) {
+            float *dst = frame + 3ull * (static_cast<uint64_t>(j) * bp.width + i);
+            dst[0] = r, dst[1] = g, dst[2] = b;
+        }
+    }
+}
+
+// gathered = [tile_world][pixels_per_rank*3]: the all-gathered per-rank tile buffers.
+__global__ void k_assemble(uint32_t width, uint32_t height, uint32_t tile_world, uint32_t pixels_per_rank, const float *gathered,
+                           float *frame) {
+    BatchParams bp{};
+    bp.width = width, bp.height = height;
+    bp.tiles_x = (width + kTileSize - 1) / kTileSize;
+    bp.num_tiles = bp.tiles_x * ((height + kTileSize - 1) / kTileSize);
+    bp.tile_world = tile_world;
+    const uint64_t total = static_cast<uint64_t>(pixels_per_rank) * tile_world;
+    for (uint64_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        bp.tile_rank = static_cast<uint32_t>(k / pixels_per_rank);
+        const uint32_t p = static_cast<uint32_t>(k % pixels_per_rank);
+        uint32_t i, j;
+        if (LocalPixelToImage(bp, p, &i, &j)) {
+            const float *src = gathered + 3ull * k;
+            float *dst = frame + 3ull * (static_cast<uint64_t>(j) * width + i);
+            dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
+        }
+    }
+}
+
+size_t TopSmemBytes() { return static_cast<size_t>(kTopNodes) * sizeof(BvhNode); }
+
+template <typename K>
+void EnableSmem(K kernel) {
+    static bool done = false; // one static per kernel instantiation
+    if (!done) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TopSmemBytes()));
+        done = true;
+    }
+}
+
+} // namespace
+
+void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, float *radiance,
+                   uint32_t capacity, Counters *counters) {
+    if (lc.stats) {
+        EnableSmem(k_primary<true>);
+        k_primary<true><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, bp, q, radiance, capacity, counters);
+    } else {
+        EnableSmem(k_primary<false>);
+        k_primary<false><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, bp, q, radiance, capacity, counters);
+    }
+}
+
+void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, PathQueue q, int which, Counters *counters) {
+    if (lc.stats) {
+        EnableSmem(k_extend<true>);
+        k_extend<true><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, q, which, counters);
+    } else {
+        EnableSmem(k_extend<false>);
+        k_extend<false><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, q, which, counters);
+    }
+}
+
+void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, ShadowQueue sq, float *radiance, uint32_t capacity,
+                  Counters *counters) {
+    if (lc.stats) {
+        EnableSmem(k_shadow<true>);
+        k_shadow<true><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, sq, radiance, capacity, counters);
+    } else {
+        EnableSmem(k_shadow<false>);
+        k_shadow<false><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, sq, radiance, capacity, counters);
+    }
+}
+
+void LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
+                 int which_in, PathQueue qout, ShadowQueue sq, float *radiance, Counters *counters, uint32_t capacity) {
+    if (scene.integrator.type == B200PT_INTEGRATOR_VOLPATH)
+        k_shade<true><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, bp, depth, qin, which_in, qout, sq, radiance, counters, capacity);
+    else
+        k_shade<false><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, bp, depth, qin, which_in, qout, sq, radiance, counters, capacity);
+}
+
+void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow) {
+    k_reset<<<1, 1, 0, lc.stream>>>(counters, which_queue, reset_shadow);
+}
+
+void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum) {
+    k_resolve<<<lc.blocks, kThreads, 0, lc.stream>>>(bp, radiance, capacity, accum);
+}
+
+void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum, float *frame,
+                    float *tiles) {
+    const int blocks = static_cast<int>(std::min<uint64_t>(lc.blocks, (num_local_pixels + kThreads - 1) / kThreads));
+    k_finalize<<<std::max(blocks, 1), kThreads, 0, lc.stream>>>(bp, num_local_pixels, accum, frame, tiles);
+}
+
+void LaunchAssemble(const LaunchConfig &lc, uint32_t width, uint32_t height, uint32_t tile_world, uint32_t pixels_per_rank,
+                    const float *gathered, float *frame) {
+    k_assemble<<<lc.blocks, kThreads, 0, lc.stream>>>(width, height, tile_world, pixels_per_rank, gathered, frame);
+}
+
+} // namespace b200pt

@@ -1,0 +1,94 @@
+// wavefront.cuh — buffers and launch parameters of the wavefront pipeline (shared by
+// wavefront.cu and renderer.cpp-side host code).
+//
+// Pipeline per batch of paths:
+//   k_primary   ray-gen + closest hit for camera rays (fused; misses with no env light die here)
+//   k_shade     hit attributes, emitter hit / env miss MIS, Russian roulette, NEE shadow-ray
+//               generation, BSDF / phase sampling, warp-ballot compaction of survivors
+//   k_shadow    any-hit for the NEE rays, adds the unoccluded contributions
+//   k_extend    closest hit for the compacted survivor queue
+//   k_resolve   per-sample clamp + per-pixel sum (renderer.cpp:77-84)
+// All per-path state is SoA so that a warp's loads/stores are 128-byte transactions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_scene.h"
+#include "traverse.cuh"
+
+namespace b200pt {
+
+constexpr int kTileSize = 8;                  // pixels; tiles are dealt round-robin to ranks
+constexpr int kTilePixels = kTileSize * kTileSize;
+
+// One path segment waiting for its closest hit / shading.  Arrays of `capacity` elements.
+struct PathQueue {
+    float *ox, *oy, *oz;      // ray origin
+    float *dx, *dy, *dz;      // ray direction (unit)
+    float *tr, *tg, *tb;      // path throughput ("attenuation" in path.cpp)
+    float *pdf;               // pdf of the direction sample that produced this ray (MIS at the next vertex)
+    uint32_t *slot;           // sample slot inside the batch
+    uint32_t *medium;         // volpath: medium the ray was scattered in, or kInvalid if it left a surface
+    float *wx, *wy, *wz;      // volpath: `wo` of the last surface vertex (stale-wo behaviour of volpath.cpp)
+    HitRec *hit;              // closest hit, written by k_primary / k_extend
+};
+
+struct ShadowQueue {
+    float *ox, *oy, *oz, *dx, *dy, *dz, *tmax;
+    float *cr, *cg, *cb;      // contribution if unoccluded (already multiplied by throughput)
+    uint32_t *slot;
+};
+
+struct Counters {             // device-resident, zeroed per batch
+    uint32_t queue[2];        // entries in path queue 0 / 1
+    uint32_t shadow;
+    uint32_t pad;
+    unsigned long long closest_rays, shadow_rays, node_visits, prim_tests;
+};
+
+struct BatchParams {
+    DCamera camera;
+    uint32_t width, height, spp;
+    float spp_inv;
+    uint2 key;                // Philox key (seed)
+    uint32_t tiles_x, num_tiles;
+    uint32_t tile_rank, tile_world;
+    uint32_t pixel_begin;     // first local pixel of this batch
+    uint32_t pixel_count;     // local pixels in this batch
+    uint32_t sample_begin;    // first sample index of this batch
+    uint32_t sample_count;    // samples per pixel in this batch (slots = pixel_count * sample_count)
+};
+
+// local pixel -> image coordinates; false for padding pixels of edge tiles / tiles past the end.
+__host__ __device__ inline bool LocalPixelToImage(const BatchParams &p, uint32_t local_pixel, uint32_t *i, uint32_t *j) {
+    const uint32_t tile_local = local_pixel / kTilePixels, in_tile = local_pixel % kTilePixels;
+    const uint32_t tile = tile_local * p.tile_world + p.tile_rank;
+    if (tile >= p.num_tiles) return false;
+    *i = (tile % p.tiles_x) * kTileSize + (in_tile % kTileSize);
+    *j = (tile / p.tiles_x) * kTileSize + (in_tile / kTileSize);
+    return *i < p.width && *j < p.height;
+}
+
+struct LaunchConfig {
+    int blocks;               // persistent grid: SMs x resident CTAs
+    int threads;
+    cudaStream_t stream;
+    bool stats;
+};
+
+// kernel launchers (wavefront.cu)
+void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, float *radiance,
+                   uint32_t capacity, Counters *counters);
+void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, PathQueue q, int which, Counters *counters);
+void LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
+                 int which_in, PathQueue qout, ShadowQueue sq, float *radiance, Counters *counters, uint32_t capacity);
+void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, ShadowQueue sq, float *radiance, uint32_t capacity,
+                  Counters *counters);
+void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow);
+void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum);
+void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,
+                    float *frame, float *tiles);
+void LaunchAssemble(const LaunchConfig &lc, uint32_t width, uint32_t height, uint32_t tile_world, uint32_t pixels_per_rank,
+                    const float *gathered, float *frame);
+
+} // namespace b200pt

@@ -63,3 +63,40 @@ class RefLib:
             return frame, b.value, r.value
         finally:
             self.lib.b200pt_scene_free(scene)
+
+
+_REF_CACHE = {}
+
+
+def ref_lib(variant="woop"):
+    if variant not in _REF_CACHE:
+        _REF_CACHE[variant] = RefLib(variant)
+    return _REF_CACHE[variant]
+
+
+def render_checker(pack_path, width=0, height=0, spp=0):
+    """CPU frame for parity checks: the reference build (Woop triangles, like the CUDA path) when
+    oracle/_ref holds it, else the C restatement.  Returns (frame, kind)."""
+    try:
+        frame, _, _ = ref_lib("woop").render_pack(pack_path, width, height, spp)
+        return frame, "reference"
+    except FileNotFoundError:
+        pass
+    return OracleLib().render_pack(pack_path, width, height, spp), "port"
+
+
+def metrics(a, b, box=8):
+    """Parity metrics of SURVEY.md §8d: per-pixel rel-L2, mean ratio, box-filtered rel-L2 (b = oracle)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    h, w = a.shape[:2]
+    hb, wb = (h // box) * box, (w // box) * box
+    fa = a[:hb, :wb].reshape(hb // box, box, wb // box, box, 3).mean(axis=(1, 3))
+    fb = b[:hb, :wb].reshape(hb // box, box, wb // box, box, 3).mean(axis=(1, 3))
+    return {
+        "rel_l2": float(np.linalg.norm(a - b) / np.linalg.norm(b)),
+        "mean_ratio": float(a.mean() / b.mean()),
+        "box_rel_l2": float(np.linalg.norm(fa - fb) / np.linalg.norm(fb)),
+        "mean_a": float(a.mean()),
+        "mean_b": float(b.mean()),
+    }
