@@ -201,20 +201,33 @@ typedef struct b200pt_render_opts {
     uint64_t seed;              /* Philox key */
     uint32_t tile_rank;         /* this process renders tiles t with t % tile_world == tile_rank */
     uint32_t tile_world;        /* 0 or 1 = whole frame */
-    uint32_t collect_stats;     /* count node visits / primitive tests (slower) */
+    uint32_t collect_stats;     /* B200PT_STATS_* bit mask */
     uint32_t reserved;
 } b200pt_render_opts;
 
+/* Per kernel class of the wavefront pipeline. */
+typedef struct b200pt_kernel_stats {
+    double ms;                   /* summed device time of its launches (B200PT_STATS_TIMING) */
+    uint64_t launches;
+    uint64_t rays;               /* rays traced by it (B200PT_STATS_COUNTERS) */
+    uint64_t node_visits;        /* child-box tests, 2 per 64-byte node fetched */
+    uint64_t prim_tests;         /* ray-triangle / ray-analytic tests */
+} b200pt_kernel_stats;
+
+#define B200PT_STATS_COUNTERS 1u /* count rays / node visits / primitive tests (slows traversal kernels a little) */
+#define B200PT_STATS_TIMING 2u   /* CUDA-event time per kernel class (no effect on the kernels themselves) */
+
 typedef struct b200pt_stats {
-    double render_ms;            /* device time of the last render (CUDA events) */
+    double render_ms;            /* device time of the last render (CUDA events on the render stream) */
     double upload_ms, bvh_build_ms;
     uint64_t samples;            /* width*height*spp rendered by this rank */
-    uint64_t closest_rays, shadow_rays;
-    uint64_t node_visits, prim_tests;   /* only when collect_stats */
     uint64_t kernel_launches;    /* kernels launched by the last render */
     uint64_t num_bvh_nodes, num_triangles, num_prims;
-    double traverse_ms;          /* device time inside closest-hit + any-hit kernels (collect_stats) */
-    uint64_t reserved[4];
+    b200pt_kernel_stats primary; /* k_primary: ray-gen + closest hit of camera rays */
+    b200pt_kernel_stats extend;  /* k_extend : closest hit of bounce rays */
+    b200pt_kernel_stats shadow;  /* k_shadow : any-hit of NEE rays */
+    b200pt_kernel_stats shade;   /* k_shade  : shading, NEE generation, sampling, compaction */
+    b200pt_kernel_stats other;   /* resets, resolve, finalize */
 } b200pt_stats;
 
 /* ---- lifecycle: replaces csrt::Renderer ctor/dtor (renderer.cpp:259-369) ---- */

@@ -38,15 +38,31 @@ class CreateOpts(ctypes.Structure):
                 ("max_paths_in_flight", ctypes.c_uint64)]
 
 
-class Stats(ctypes.Structure):
-    _fields_ = [("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double), ("bvh_build_ms", ctypes.c_double),
-                ("samples", ctypes.c_uint64), ("closest_rays", ctypes.c_uint64), ("shadow_rays", ctypes.c_uint64),
-                ("node_visits", ctypes.c_uint64), ("prim_tests", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
-                ("num_bvh_nodes", ctypes.c_uint64), ("num_triangles", ctypes.c_uint64), ("num_prims", ctypes.c_uint64),
-                ("traverse_ms", ctypes.c_double), ("reserved", ctypes.c_uint64 * 4)]
+class KernelStats(ctypes.Structure):
+    _fields_ = [("ms", ctypes.c_double), ("launches", ctypes.c_uint64), ("rays", ctypes.c_uint64),
+                ("node_visits", ctypes.c_uint64), ("prim_tests", ctypes.c_uint64)]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+STATS_COUNTERS = 1  # B200PT_STATS_COUNTERS
+STATS_TIMING = 2    # B200PT_STATS_TIMING
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double), ("bvh_build_ms", ctypes.c_double),
+                ("samples", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
+                ("num_bvh_nodes", ctypes.c_uint64), ("num_triangles", ctypes.c_uint64), ("num_prims", ctypes.c_uint64),
+                ("primary", KernelStats), ("extend", KernelStats), ("shadow", KernelStats), ("shade", KernelStats),
+                ("other", KernelStats)]
+
+    def as_dict(self):
+        out = {}
+        for name, kind in self._fields_:
+            value = getattr(self, name)
+            out[name] = value.as_dict() if kind is KernelStats else value
+        return out
 
 
 # Every symbol include/b200pt.h declares; tests check the library exports all of them.
@@ -135,10 +151,10 @@ class Renderer:
         opts = CreateOpts(device, max_leaf_size, max_paths_in_flight)
         _check(lib().b200pt_create(scene.desc, ctypes.byref(opts), ctypes.byref(self._h)))
 
-    def _opts(self, width, height, spp, seed, tile_rank=0, tile_world=1, stats=False):
-        return RenderOpts(width or 0, height or 0, spp or 0, seed, tile_rank, tile_world, 1 if stats else 0, 0)
+    def _opts(self, width, height, spp, seed, tile_rank=0, tile_world=1, stats=0):
+        return RenderOpts(width or 0, height or 0, spp or 0, seed, tile_rank, tile_world, int(stats), 0)
 
-    def Draw(self, frame=None, width=0, height=0, spp=0, seed=0, stats=False):
+    def Draw(self, frame=None, width=0, height=0, spp=0, seed=0, stats=0):
         """Host-buffer render (the reference's Draw(float*)): H2D/D2H copies happen inside the call."""
         w, h = width or self.scene.width, height or self.scene.height
         if frame is None:
@@ -149,13 +165,13 @@ class Renderer:
         _check(lib().b200pt_render(self._h, ctypes.byref(opts), frame.ctypes.data), self._h)
         return frame
 
-    def draw_device(self, frame_tensor, width=0, height=0, spp=0, seed=0, stream=None, stats=False):
+    def draw_device(self, frame_tensor, width=0, height=0, spp=0, seed=0, stream=None, stats=0):
         """Frame stays in HBM: `frame_tensor` is a CUDA float32 tensor with width*height*3 elements."""
         opts = self._opts(width, height, spp, seed, stats=stats)
         _check(lib().b200pt_render_device(self._h, ctypes.byref(opts), frame_tensor.data_ptr(), stream), self._h)
 
-    def draw_tiles_device(self, tiles_tensor, tile_rank, tile_world, width=0, height=0, spp=0, seed=0, stream=None):
-        opts = self._opts(width, height, spp, seed, tile_rank, tile_world)
+    def draw_tiles_device(self, tiles_tensor, tile_rank, tile_world, width=0, height=0, spp=0, seed=0, stream=None, stats=0):
+        opts = self._opts(width, height, spp, seed, tile_rank, tile_world, stats)
         _check(lib().b200pt_render_tiles_device(self._h, ctypes.byref(opts), tiles_tensor.data_ptr(), stream), self._h)
 
     def assemble_tiles_device(self, gathered_tensor, frame_tensor, width, height, tile_world, stream=None):

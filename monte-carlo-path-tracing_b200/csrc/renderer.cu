@@ -86,13 +86,31 @@ struct b200pt_context {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     bool timing_pending = false;
     int num_sms = 148;
-    bool kc_ready = false;
+    // B200PT_STATS_TIMING: (class, begin, end) per launch, resolved in b200pt_get_stats
+    struct TimedLaunch {
+        int cls;
+        cudaEvent_t begin, end;
+    };
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    uint64_t class_launches[kNumClasses] = {};
+
+    cudaEvent_t NextEvent() {
+        if (events_used == event_pool.size()) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            event_pool.push_back(e);
+        }
+        return event_pool[events_used++];
+    }
 
     ~b200pt_context() {
         if (pinned_count) cudaFreeHost(pinned_count);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
         if (stream) cudaStreamDestroy(stream);
+        for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
     }
 
     int Fail(int code, const std::string &msg) {
@@ -208,7 +226,7 @@ int AllocWavefront(b200pt_context *c, uint64_t capacity) {
 struct ResolvedOpts {
     uint32_t width, height, spp, tile_rank, tile_world;
     uint64_t seed;
-    bool stats;
+    bool counters, timing;
 };
 
 int ResolveOpts(b200pt_context *c, const b200pt_render_opts *o, ResolvedOpts *r) {
@@ -219,7 +237,8 @@ int ResolveOpts(b200pt_context *c, const b200pt_render_opts *o, ResolvedOpts *r)
     r->seed = o ? o->seed : 0;
     r->tile_world = (o && o->tile_world) ? o->tile_world : 1;
     r->tile_rank = o ? o->tile_rank : 0;
-    r->stats = o && o->collect_stats;
+    r->counters = o && (o->collect_stats & B200PT_STATS_COUNTERS);
+    r->timing = o && (o->collect_stats & B200PT_STATS_TIMING);
     if (r->width == 0 || r->height == 0 || r->spp == 0) return c->Fail(B200PT_EINVAL, "width, height and spp must be positive.");
     if (r->tile_rank >= r->tile_world) return c->Fail(B200PT_EINVAL, "tile_rank must be < tile_world.");
     if (static_cast<uint64_t>(r->width) * r->height > (1ull << 30)) return c->Fail(B200PT_EINVAL, "frame too large.");
@@ -250,9 +269,26 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     lc.blocks = c->num_sms * 4;
     lc.threads = 256;
     lc.stream = stream;
-    lc.stats = ro.stats;
+    lc.stats = ro.counters;
 
     uint64_t launches = 0;
+    c->timed.clear();
+    c->events_used = 0;
+    for (uint64_t &n : c->class_launches) n = 0;
+    // Runs one kernel launch, counted (and, with B200PT_STATS_TIMING, bracketed by events) under its class.
+    auto launch = [&](int cls, auto &&fn) {
+        ++launches;
+        ++c->class_launches[cls];
+        if (ro.timing) {
+            b200pt_context::TimedLaunch t{cls, c->NextEvent(), c->NextEvent()};
+            cudaEventRecord(t.begin, stream);
+            fn();
+            cudaEventRecord(t.end, stream);
+            c->timed.push_back(t);
+        } else {
+            fn();
+        }
+    };
     CU_CHECK(c, cudaEventRecord(c->ev_begin, stream));
     CU_CHECK(c, cudaMemsetAsync(c->accum.ptr, 0, 3ull * local_pixels * sizeof(float), stream));
     CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, sizeof(Counters), stream));
@@ -273,21 +309,16 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
             for (int ch = 0; ch < 3; ++ch)
                 CU_CHECK(c, cudaMemsetAsync(c->radiance + static_cast<uint64_t>(ch) * capacity, 0, nslots * sizeof(float), stream));
             CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, 16, stream)); // queue[0], queue[1], shadow
-            LaunchPrimary(lc, c->scene, bp, c->queue[0], c->radiance, capacity, c->counters.ptr);
-            ++launches;
+            launch(kClassPrimary, [&] { LaunchPrimary(lc, c->scene, bp, c->queue[0], c->radiance, capacity, c->counters.ptr); });
             int which = 0;
             for (uint32_t depth = 1; depth <= max_rounds; ++depth) {
-                if (depth > 1) {
-                    LaunchResetCounters(lc, c->counters.ptr, which ^ 1, true);
-                    ++launches;
-                }
-                LaunchShade(lc, c->scene, bp, depth, c->queue[which], which, c->queue[which ^ 1], c->shadow, c->radiance,
-                            c->counters.ptr, capacity);
-                ++launches;
-                if (c->shadow_per_vertex > 0) {
-                    LaunchShadow(lc, c->scene, c->shadow, c->radiance, capacity, c->counters.ptr);
-                    ++launches;
-                }
+                if (depth > 1) launch(kClassOther, [&] { LaunchResetCounters(lc, c->counters.ptr, which ^ 1, true); });
+                launch(kClassShade, [&] {
+                    LaunchShade(lc, c->scene, bp, depth, c->queue[which], which, c->queue[which ^ 1], c->shadow, c->radiance,
+                                c->counters.ptr, capacity);
+                });
+                if (c->shadow_per_vertex > 0)
+                    launch(kClassShadow, [&] { LaunchShadow(lc, c->scene, c->shadow, c->radiance, capacity, c->counters.ptr); });
                 which ^= 1;
                 if (depth == max_rounds) break;
                 if (depth >= 8 && (depth & 3) == 0) { // poll the survivor count
@@ -296,15 +327,12 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
                     CU_CHECK(c, cudaStreamSynchronize(stream));
                     if (*c->pinned_count == 0) break;
                 }
-                LaunchExtend(lc, c->scene, c->queue[which], which, c->counters.ptr);
-                ++launches;
+                launch(kClassExtend, [&] { LaunchExtend(lc, c->scene, c->queue[which], which, c->counters.ptr); });
             }
-            LaunchResolve(lc, bp, c->radiance, capacity, c->accum.ptr);
-            ++launches;
+            launch(kClassOther, [&] { LaunchResolve(lc, bp, c->radiance, capacity, c->accum.ptr); });
         }
     }
-    LaunchFinalize(lc, bp, local_pixels, c->accum.ptr, frame_dev, tiles_dev);
-    ++launches;
+    launch(kClassOther, [&] { LaunchFinalize(lc, bp, local_pixels, c->accum.ptr, frame_dev, tiles_dev); });
     CU_CHECK(c, cudaEventRecord(c->ev_end, stream));
     CU_CHECK(c, cudaGetLastError());
     c->timing_pending = true;
@@ -430,10 +458,21 @@ int b200pt_get_stats(b200pt_handle h, b200pt_stats *out) {
         h->stats.render_ms = ms;
         Counters host_counters;
         CU_CHECK(h, cudaMemcpy(&host_counters, h->counters.ptr, sizeof(Counters), cudaMemcpyDeviceToHost));
-        h->stats.closest_rays = host_counters.closest_rays;
-        h->stats.shadow_rays = host_counters.shadow_rays;
-        h->stats.node_visits = host_counters.node_visits;
-        h->stats.prim_tests = host_counters.prim_tests;
+        b200pt_kernel_stats *ks[kNumClasses] = {&h->stats.primary, &h->stats.extend, &h->stats.shadow, &h->stats.shade, &h->stats.other};
+        for (int k = 0; k < kNumClasses; ++k) {
+            *ks[k] = b200pt_kernel_stats{};
+            ks[k]->launches = h->class_launches[k];
+            if (k < 3) {
+                ks[k]->rays = host_counters.cls[k].rays;
+                ks[k]->node_visits = host_counters.cls[k].node_visits;
+                ks[k]->prim_tests = host_counters.cls[k].prim_tests;
+            }
+        }
+        for (const b200pt_context::TimedLaunch &t : h->timed) {
+            float t_ms = 0.0f;
+            CU_CHECK(h, cudaEventElapsedTime(&t_ms, t.begin, t.end));
+            ks[t.cls]->ms += t_ms;
+        }
         h->timing_pending = false;
     }
     *out = h->stats;

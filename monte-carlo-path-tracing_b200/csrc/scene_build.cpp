@@ -104,9 +104,10 @@ V3 TransformPoint(const M4 &m, V3 p) {
             m.m[1][0] * p.x + m.m[1][1] * p.y + m.m[1][2] * p.z + m.m[1][3],
             m.m[2][0] * p.x + m.m[2][1] * p.y + m.m[2][2] * p.z + m.m[2][3]};
 }
+// mat4.cpp:270-273: TransformVector returns Vec4::direction() = the NORMALISED vector (vec4.hpp:55).
 V3 TransformVector(const M4 &m, V3 v) {
-    return {m.m[0][0] * v.x + m.m[0][1] * v.y + m.m[0][2] * v.z, m.m[1][0] * v.x + m.m[1][1] * v.y + m.m[1][2] * v.z,
-            m.m[2][0] * v.x + m.m[2][1] * v.y + m.m[2][2] * v.z};
+    return Normalize(V3{m.m[0][0] * v.x + m.m[0][1] * v.y + m.m[0][2] * v.z, m.m[1][0] * v.x + m.m[1][1] * v.y + m.m[1][2] * v.z,
+                        m.m[2][0] * v.x + m.m[2][1] * v.y + m.m[2][2] * v.z});
 }
 Affine ToAffine(const M4 &m) {
     Affine a;

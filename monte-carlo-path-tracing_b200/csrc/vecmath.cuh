@@ -71,13 +71,18 @@ __device__ __forceinline__ float Lerp(float a, float b, float t) { return (1.0f 
 __device__ __forceinline__ V3 Lerp(V3 a, V3 b, float t) { return (1.0f - t) * a + t * b; }
 __device__ __forceinline__ float Comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
+// forward declarations used by the transform helpers
+__device__ __forceinline__ V3 Normalize(V3 a);
+
 __device__ __forceinline__ V3 XformPoint(const Affine &m, V3 p) {
     return {m.m[0] * p.x + m.m[1] * p.y + m.m[2] * p.z + m.m[3], m.m[4] * p.x + m.m[5] * p.y + m.m[6] * p.z + m.m[7],
             m.m[8] * p.x + m.m[9] * p.y + m.m[10] * p.z + m.m[11]};
 }
+// TransformVector (mat4.cpp:270-273) returns Vec4::direction(), i.e. the NORMALISED transformed vector
+// (vec4.hpp:55) — normals, local ray directions and env-map directions all go through this.
 __device__ __forceinline__ V3 XformVector(const Affine &m, V3 v) {
-    return {m.m[0] * v.x + m.m[1] * v.y + m.m[2] * v.z, m.m[4] * v.x + m.m[5] * v.y + m.m[6] * v.z,
-            m.m[8] * v.x + m.m[9] * v.y + m.m[10] * v.z};
+    return Normalize(V3{m.m[0] * v.x + m.m[1] * v.y + m.m[2] * v.z, m.m[4] * v.x + m.m[5] * v.y + m.m[6] * v.z,
+                        m.m[8] * v.x + m.m[9] * v.y + m.m[10] * v.z});
 }
 
 // math.cpp:8-13

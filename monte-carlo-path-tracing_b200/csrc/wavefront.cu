@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t WarpAppend(bool flag, uint32_t *counter) {
     return base + __popc(ballot & ((1u << lane) - 1u));
 }
 
-__device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounters &tc, uint32_t rays, bool shadow, Counters *c) {
+__device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounters &tc, uint32_t rays, int cls, Counters *c) {
     if (!stats) return;
     // one atomic per warp
     uint32_t nodes = tc.nodes, prims = tc.prims, r = rays;
@@ -75,9 +75,9 @@ __device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounter
         r += __shfl_down_sync(0xffffffffu, r, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&c->node_visits, static_cast<unsigned long long>(nodes));
-        atomicAdd(&c->prim_tests, static_cast<unsigned long long>(prims));
-        atomicAdd(shadow ? &c->shadow_rays : &c->closest_rays, static_cast<unsigned long long>(r));
+        atomicAdd(&c->cls[cls].node_visits, static_cast<unsigned long long>(nodes));
+        atomicAdd(&c->cls[cls].prim_tests, static_cast<unsigned long long>(prims));
+        atomicAdd(&c->cls[cls].rays, static_cast<unsigned long long>(r));
     }
 }
 
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ De
             q.hit[idx] = hit;
         }
     }
-    FlushCounters(STATS, tc, rays, false, counters);
+    FlushCounters(STATS, tc, rays, kClassPrimary, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Dev
     }
     if (STATS) {
         __syncwarp();
-        FlushCounters(true, tc, rays, false, counters);
+        FlushCounters(true, tc, rays, kClassExtend, counters);
     }
 }
 
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ Dev
     }
     if (STATS) {
         __syncwarp();
-        FlushCounters(true, tc, rays, true, counters);
+        FlushCounters(true, tc, rays, kClassShadow, counters);
     }
 }
 

@@ -39,11 +39,17 @@ struct ShadowQueue {
     uint32_t *slot;
 };
 
-struct Counters {             // device-resident, zeroed per batch
-    uint32_t queue[2];        // entries in path queue 0 / 1
+enum KernelClass { kClassPrimary = 0, kClassExtend = 1, kClassShadow = 2, kClassShade = 3, kClassOther = 4, kNumClasses = 5 };
+
+struct ClassCounters {
+    unsigned long long rays, node_visits, prim_tests;
+};
+
+struct Counters {             // device-resident
+    uint32_t queue[2];        // entries in path queue 0 / 1 (zeroed per batch)
     uint32_t shadow;
     uint32_t pad;
-    unsigned long long closest_rays, shadow_rays, node_visits, prim_tests;
+    ClassCounters cls[3];     // primary / extend / shadow traversal statistics (zeroed per render)
 };
 
 struct BatchParams {

@@ -120,6 +120,39 @@ int ref_render(const b200pt_scene_desc *desc, int width, int height, int spp, fl
     }
 }
 
+// Persistent variant for timing: build once (scene commit + LBVH + LUTs), Draw many times.
+void *ref_create(const b200pt_scene_desc *desc, int width, int height, int spp, double *build_seconds) {
+    try {
+        csrt::RendererConfig cfg = b200pt_glue::InflateScene(*desc);
+        if (width > 0) cfg.camera.width = width;
+        if (height > 0) cfg.camera.height = height;
+        if (spp > 0) cfg.camera.spp = spp;
+        StderrSilencer quiet;
+        const auto t0 = std::chrono::steady_clock::now();
+        csrt::Renderer *renderer = new csrt::Renderer(cfg);
+        if (build_seconds) *build_seconds = Seconds(t0, std::chrono::steady_clock::now());
+        return renderer;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return nullptr;
+    }
+}
+
+// One csrt::Renderer::Draw (renderer.cpp:678): all hardware threads, returns wall seconds or -1.
+double ref_draw(void *renderer, float *frame) {
+    try {
+        StderrSilencer quiet;
+        const auto t0 = std::chrono::steady_clock::now();
+        static_cast<csrt::Renderer *>(renderer)->Draw(frame);
+        return Seconds(t0, std::chrono::steady_clock::now());
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1.0;
+    }
+}
+
+void ref_destroy(void *renderer) { delete static_cast<csrt::Renderer *>(renderer); }
+
 // ---- known-answer helpers: reference leaf functions, called directly ----
 
 uint32_t ref_tea4(uint32_t v0, uint32_t v1) { return csrt::Tea<4>(v0, v1); }

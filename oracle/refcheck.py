@@ -28,6 +28,12 @@ class RefLib:
         L.b200pt_scene_get_desc.argtypes = [ctypes.c_void_p]
         L.b200pt_scene_get_desc.restype = ctypes.c_void_p
         L.b200pt_scene_free.argtypes = [ctypes.c_void_p]
+        L.ref_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        L.ref_create.restype = ctypes.c_void_p
+        L.ref_draw.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ref_draw.restype = ctypes.c_double
+        L.ref_destroy.argtypes = [ctypes.c_void_p]
+        L.ref_destroy.restype = None
         L.ref_tea4.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
         L.ref_tea4.restype = ctypes.c_uint32
         L.ref_random_float.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
@@ -63,6 +69,104 @@ class RefLib:
             return frame, b.value, r.value
         finally:
             self.lib.b200pt_scene_free(scene)
+
+
+class OracleLib:
+    """The plain-C restatement (oracle/pt_oracle.c -> oracle/_ref/liboracle.so)."""
+
+    def __init__(self):
+        path = os.path.join(REF_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.oracle_render.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_tea4.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+        L.oracle_tea4.restype = ctypes.c_uint32
+        L.oracle_random_float.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
+        L.oracle_random_float.restype = ctypes.c_float
+        L.oracle_van_der_corput2.argtypes = [ctypes.c_uint32]
+        L.oracle_van_der_corput2.restype = ctypes.c_float
+        L.oracle_mis_weight.argtypes = [ctypes.c_float, ctypes.c_float]
+        L.oracle_mis_weight.restype = ctypes.c_float
+        L.oracle_sample_hemis_cos.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        L.oracle_kulla_conty.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_build_bvh.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+        L.oracle_build_bvh.restype = ctypes.c_uint32
+
+    def render_pack(self, pack_path, width=0, height=0, spp=0, watertight=True, threads=None):
+        """Loads the pack with the product's pack reader (data I/O only) and renders it with the C restatement."""
+        loader = _pack_loader()
+        scene = ctypes.c_void_p()
+        if loader.b200pt_scene_load(pack_path.encode(), ctypes.byref(scene)) != 0:
+            raise RuntimeError(f"cannot load {pack_path}")
+        try:
+            desc = loader.b200pt_scene_get_desc(scene)
+            cam = np.ctypeslib.as_array(ctypes.cast(desc + 8, ctypes.POINTER(ctypes.c_int32)), shape=(3,))
+            w, h = width or int(cam[1]), height or int(cam[2])
+            frame = np.zeros((h, w, 3), dtype=np.float32)
+            rc = self.lib.oracle_render(desc, width, height, spp, 1 if watertight else 0, threads or (os.cpu_count() or 1), frame.ctypes.data)
+            if rc != 0:
+                raise RuntimeError("oracle_render failed")
+            return frame
+        finally:
+            loader.b200pt_scene_free(scene)
+
+
+_PACK_LOADER = None
+
+
+def _pack_loader():
+    """Any library that exports the scene-pack reader: the product library, else a reference build."""
+    global _PACK_LOADER
+    if _PACK_LOADER is None:
+        candidates = [os.path.join(os.path.dirname(HERE), "monte-carlo-path-tracing_b200", "libb200pt.so"),
+                      os.path.join(REF_DIR, "libcsrt_ref_woop.so"), os.path.join(REF_DIR, "libcsrt_ref_mt.so")]
+        for path in candidates:
+            if os.path.exists(path):
+                L = ctypes.CDLL(path)
+                L.b200pt_scene_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+                L.b200pt_scene_get_desc.argtypes = [ctypes.c_void_p]
+                L.b200pt_scene_get_desc.restype = ctypes.c_void_p
+                L.b200pt_scene_free.argtypes = [ctypes.c_void_p]
+                _PACK_LOADER = L
+                break
+        else:
+            raise FileNotFoundError("no library with b200pt_scene_load found")
+    return _PACK_LOADER
+
+
+class RefRenderer:
+    """A persistent csrt::Renderer over a scene pack: build once, draw() many times (for timing)."""
+
+    def __init__(self, ref, pack_path, width=0, height=0, spp=0):
+        self.ref = ref
+        self.scene = ctypes.c_void_p()
+        if ref.lib.b200pt_scene_load(pack_path.encode(), ctypes.byref(self.scene)) != 0:
+            raise RuntimeError(f"cannot load {pack_path}")
+        desc = ref.lib.b200pt_scene_get_desc(self.scene)
+        cam = np.ctypeslib.as_array(ctypes.cast(desc + 8, ctypes.POINTER(ctypes.c_int32)), shape=(3,))
+        self.width, self.height, self.spp = width or int(cam[1]), height or int(cam[2]), spp or int(cam[0])
+        b = ctypes.c_double()
+        self.handle = ref.lib.ref_create(desc, width, height, spp, ctypes.byref(b))
+        if not self.handle:
+            raise RuntimeError(ref.error())
+        self.build_seconds = b.value
+        self.frame = np.zeros((self.height, self.width, 3), dtype=np.float32)
+
+    def draw(self):
+        seconds = self.ref.lib.ref_draw(self.handle, self.frame.ctypes.data)
+        if seconds < 0:
+            raise RuntimeError(self.ref.error())
+        return seconds
+
+    def close(self):
+        if self.handle:
+            self.ref.lib.ref_destroy(self.handle)
+            self.handle = None
+        if self.scene:
+            self.ref.lib.b200pt_scene_free(self.scene)
+            self.scene = ctypes.c_void_p()
 
 
 _REF_CACHE = {}
