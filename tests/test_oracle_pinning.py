@@ -1,0 +1,114 @@
+"""Pins the CPU oracle (oracle/pt_oracle.c) to the reference.
+
+The reference ships no tests or golden vectors, so the pins are (a) known answers and frames
+produced by the UNMODIFIED reference build and committed under tests/golden/ (tests/golden/make_golden.py),
+(b) the known answers listed in SURVEY.md §8c, and (c) — where oracle/_ref holds the reference build — live
+frames of the reference itself.  Frames must match BIT FOR BIT: the oracle restates the same LCG stream,
+LBVH, traversal order and float expression order.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, pack
+
+import refcheck
+
+SETTINGS = json.load(open(os.path.join(GOLDEN, "settings.json")))
+KATS = json.load(open(os.path.join(GOLDEN, "kats.json")))
+
+
+def test_tea4_known_answers(oracle):
+    # SURVEY.md §8c
+    assert oracle.lib.oracle_tea4(0, 0) == 1576399551
+    assert oracle.lib.oracle_tea4(3, 0) == 3153161610
+    assert oracle.lib.oracle_tea4(3145725, 0) == 649473995
+    assert oracle.lib.oracle_tea4(12, 7) == 1545002379
+    for a, b, expected in KATS["tea4"]:
+        assert oracle.lib.oracle_tea4(a, b) == expected
+
+
+def test_lcg_known_answers(oracle):
+    seed = ctypes.c_uint32(1576399551)
+    floats = [oracle.lib.oracle_random_float(ctypes.byref(seed)) for _ in range(4)]
+    assert np.allclose(floats, [0.294449925, 0.695515215, 0.897309542, 0.59830302], rtol=0, atol=1e-9)
+    seed = ctypes.c_uint32(1576399551)
+    for value, state in KATS["lcg_from_tea4_0_0"]:
+        assert oracle.lib.oracle_random_float(ctypes.byref(seed)) == np.float32(value)
+        assert seed.value == state
+
+
+def test_van_der_corput_and_mis(oracle):
+    assert [oracle.lib.oracle_van_der_corput2(i) for i in range(1, 6)] == [0.5, 0.25, 0.75, 0.125, 0.625]
+    for index, value in KATS["van_der_corput2"]:
+        assert oracle.lib.oracle_van_der_corput2(index) == np.float32(value)
+    assert oracle.lib.oracle_mis_weight(0.3, 0.1) == np.float32(0.900000036)
+    for a, b, value in KATS["mis_weight"]:
+        got = oracle.lib.oracle_mis_weight(a, b)
+        assert got == np.float32(value) or (np.isnan(got) and np.isnan(value))
+
+
+def test_sample_hemis_cos(oracle):
+    for xi0, xi1, vec, pdf in KATS["sample_hemis_cos"]:
+        v = np.zeros(3, dtype=np.float32)
+        p = ctypes.c_float()
+        oracle.lib.oracle_sample_hemis_cos(xi0, xi1, v.ctypes.data, ctypes.byref(p))
+        assert np.array_equal(v, np.asarray(vec, dtype=np.float32))
+        assert p.value == np.float32(pdf)
+
+
+def test_lbvh_topology(oracle):
+    # 5 unit boxes at x=0..4 -> pre-order [0:(1,4) 1:(2,3) 2:leaf0 3:leaf1 4:(5,8) 5:(6,7) 6:leaf2 7:leaf3 8:leaf4], root area 15
+    for case in KATS["lbvh"]:
+        boxes = np.asarray(case["boxes"], dtype=np.float32)
+        areas = np.asarray(case["areas"], dtype=np.float32)
+        n = len(areas)
+        nodes = np.zeros((2 * n, 4), dtype=np.uint32)
+        node_area = np.zeros(2 * n, dtype=np.float32)
+        count = oracle.lib.oracle_build_bvh(n, boxes.ctypes.data, areas.ctypes.data, nodes.ctypes.data, node_area.ctypes.data, 2 * n)
+        assert count == 2 * n - 1 == len(case["nodes"])
+        assert nodes[:count].tolist() == case["nodes"]
+        assert np.array_equal(node_area[:count], np.asarray(case["node_area"], dtype=np.float32))
+    first = KATS["lbvh"][0]
+    assert first["node_area"][0] == 15.0
+    assert [n[0] for n in first["nodes"]] == [0, 0, 1, 1, 0, 0, 1, 1, 1]
+    assert first["nodes"][0][1:3] == [1, 4] and first["nodes"][4][1:3] == [5, 8]
+
+
+def test_kulla_conty_tables_bit_exact(oracle):
+    golden = np.load(os.path.join(GOLDEN, "kulla_conty.npz"))
+    brdf = np.zeros((128, 128), dtype=np.float32)
+    albedo = np.zeros(128, dtype=np.float32)
+    oracle.lib.oracle_kulla_conty(brdf.ctypes.data, albedo.ctypes.data)
+    assert np.array_equal(brdf, golden["brdf_avg"])
+    assert np.array_equal(albedo, golden["albedo_avg"])
+
+
+@pytest.mark.parametrize("variant", ["woop", "mt"])
+@pytest.mark.parametrize("scene", sorted(SETTINGS["exact"]))
+def test_frames_match_reference_golden_bit_for_bit(oracle, scene, variant):
+    w, h, spp = SETTINGS["exact"][scene]
+    golden = np.load(os.path.join(GOLDEN, f"exact_{scene}_{variant}.npy"))
+    frame = oracle.render_pack(pack(scene), w, h, spp, watertight=(variant == "woop"))
+    assert frame.shape == golden.shape
+    assert np.array_equal(frame, golden), f"max abs diff {np.abs(frame - golden).max()}"
+
+
+def test_frame_independent_of_thread_count(oracle):
+    a = oracle.render_pack(pack("cornell-box"), 16, 16, 2, threads=1)
+    b = oracle.render_pack(pack("cornell-box"), 16, 16, 2, threads=5)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("scene,w,h,spp", [("cornell-box", 20, 12, 3), ("volumetric-caustic", 16, 16, 2)])
+def test_live_reference_build_when_present(oracle, scene, w, h, spp):
+    """Different sizes than the golden set, against the reference built from /root/reference (if it travelled)."""
+    try:
+        ref = refcheck.ref_lib("woop")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref reference build not present")
+    expected, _, _ = ref.render_pack(pack(scene), w, h, spp)
+    assert np.array_equal(oracle.render_pack(pack(scene), w, h, spp), expected)
