@@ -23,7 +23,10 @@ using namespace b200pt;
 
 namespace {
 
-constexpr uint64_t kDefaultPathsInFlight = 1ull << 24; // 16 Mi sample slots per batch
+// Upper bound of sample slots per batch.  Deep bounces keep the GPU full only when a batch carries many
+// paths (Dragon 1024^2 x 256 spp: 16 Mi slots -> 166 ms, 256 Mi slots -> 75 ms), so the default takes what a
+// 180 GB part affords: ~190 B of queue state per slot, at most 40 % of the free HBM.
+constexpr uint64_t kDefaultPathsInFlight = 1ull << 28;
 constexpr uint32_t kMaxRounds = 4096;                  // hard stop for max_depth = -1 scenes (RR ends paths long before)
 
 template <typename T>
@@ -72,7 +75,8 @@ struct b200pt_context {
     DeviceArray<uint32_t> map_area_light_instance, light_tri_ids;
 
     // wavefront state
-    uint64_t capacity = 0;        // sample slots per batch
+    uint64_t capacity = 0;        // sample slots per batch currently allocated
+    uint64_t max_capacity = 0;    // upper bound (create option / default)
     uint32_t shadow_per_vertex = 1;
     DeviceArray<float> wave;      // one allocation carved into the SoA queues
     PathQueue queue[2]{};
@@ -184,13 +188,20 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     return B200PT_OK;
 }
 
-// Carve the SoA queues out of one allocation.
-int AllocWavefront(b200pt_context *c, uint64_t capacity) {
+// Carve the SoA queues out of one allocation sized for `wanted` sample slots (clamped to what fits in HBM).
+int AllocWavefront(b200pt_context *c, uint64_t wanted) {
     const bool vol = c->scene.integrator.type == B200PT_INTEGRATOR_VOLPATH;
     c->shadow_per_vertex = c->scene.integrator.num_emitters + (c->scene.integrator.num_area_lights ? 1u : 0u);
-    const uint64_t shadow_cap = capacity * std::max(1u, c->shadow_per_vertex);
     const uint64_t words_per_queue = 11 + (vol ? 4 : 0) + 4; // 10 floats + slot (+ medium, wo) + HitRec
-    const uint64_t total = 2 * words_per_queue * capacity + 11 * shadow_cap + 3 * capacity;
+    const uint64_t words_per_slot = 2 * words_per_queue + 11 * std::max(1u, c->shadow_per_vertex) + 3;
+    c->wave.Free();
+    c->capacity = 0;
+    size_t free_bytes = 0, total_bytes = 0;
+    CU_CHECK(c, cudaMemGetInfo(&free_bytes, &total_bytes));
+    uint64_t capacity = std::min<uint64_t>(wanted, static_cast<uint64_t>(free_bytes * 0.4) / (words_per_slot * sizeof(float)));
+    capacity = std::max<uint64_t>(capacity & ~1023ull, 1024);
+    const uint64_t shadow_cap = capacity * std::max(1u, c->shadow_per_vertex);
+    const uint64_t total = words_per_slot * capacity;
     CU_CHECK(c, c->wave.Alloc(total));
     float *p = c->wave.ptr;
     auto take = [&](uint64_t n) {
@@ -265,6 +276,15 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     const uint32_t local_pixels = PixelsPerRank(ro.width, ro.height, ro.tile_world);
 
     if (c->accum.count < 3ull * local_pixels) CU_CHECK(c, c->accum.Alloc(3ull * local_pixels));
+    // Wavefront state is sized for the job at hand (grown on demand, never shrunk): all of it in one batch if it fits.
+    {
+        const uint64_t wanted = std::min<uint64_t>(c->max_capacity, std::max<uint64_t>(static_cast<uint64_t>(local_pixels) * ro.spp, 1024));
+        if (c->capacity < wanted) {
+            CU_CHECK(c, cudaDeviceSynchronize());
+            const int rc = AllocWavefront(c, wanted);
+            if (rc != B200PT_OK) return rc;
+        }
+    }
     LaunchConfig lc;
     lc.blocks = c->num_sms * 4;
     lc.threads = 256;
@@ -308,7 +328,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
             const uint64_t nslots = static_cast<uint64_t>(bp.pixel_count) * bp.sample_count;
             for (int ch = 0; ch < 3; ++ch)
                 CU_CHECK(c, cudaMemsetAsync(c->radiance + static_cast<uint64_t>(ch) * capacity, 0, nslots * sizeof(float), stream));
-            CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, 16, stream)); // queue[0], queue[1], shadow
+            CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, kCountersPerBatchBytes, stream)); // queue lengths + work counters
             launch(kClassPrimary, [&] { LaunchPrimary(lc, c->scene, bp, c->queue[0], c->radiance, capacity, c->counters.ptr); });
             int which = 0;
             for (uint32_t depth = 1; depth <= max_rounds; ++depth) {
@@ -378,9 +398,7 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     if (rc != B200PT_OK) return rc;
     uint64_t capacity = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : kDefaultPathsInFlight;
     capacity = std::max<uint64_t>(capacity, 1024);
-    capacity = std::min<uint64_t>(capacity, 1ull << 28);
-    rc = AllocWavefront(c.get(), capacity);
-    if (rc != B200PT_OK) return rc;
+    c->max_capacity = std::min<uint64_t>(capacity, 1ull << 28);
     if ((e = c->counters.Alloc(1)) != cudaSuccess) return c->CudaFail(e, "cudaMalloc counters");
     if ((e = cudaMallocHost(&c->pinned_count, sizeof(uint32_t))) != cudaSuccess) return c->CudaFail(e, "cudaMallocHost");
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return c->CudaFail(e, "cudaStreamCreate");

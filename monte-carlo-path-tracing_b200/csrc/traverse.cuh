@@ -166,87 +166,137 @@ __device__ __forceinline__ void LoadNode(const BvhNode *__restrict__ nodes, cons
     }
 }
 
-// ANY = true: occlusion query (returns on the first hit); false: closest hit.
-template <bool ANY, bool STATS>
-__device__ __forceinline__ bool Traverse(const DeviceScene &scene, const float4 *top, int num_top, Ray ray, HitRec *hit,
-                                         TraversalCounters *counters) {
-    const RayPre pre = Precompute(ray);
-    bool found = false;
-    if (!ANY) {
-        hit->t = ray.tmax;
-        hit->prim = kPrimMiss;
-        hit->u = hit->v = 0.0f;
-    }
+// Warp-aggregated queue append usable from divergent code: the currently active lanes reserve
+// consecutive slots with one atomic.
+__device__ __forceinline__ uint32_t AppendCoalesced(uint32_t *counter) {
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
 
-    // Analytic primitives (spheres, disks, cylinders) are few: tested linearly.
-    for (uint32_t i = 0; i < scene.num_analytic; ++i) {
-        const AnalyticPrim &p = scene.analytic[i];
-        if (STATS) ++counters->nodes;
-        if (!IntersectBox(p.bmin, p.bmax, ray, pre)) continue;
-        if (STATS) ++counters->prims;
-        float t;
-        if (IntersectAnalytic(p, ray, &t)) {
-            if (ANY) return true;
-            ray.tmax = t;
-            hit->t = t;
-            hit->prim = kPrimAnalyticBit | i;
-            found = true;
-        }
-    }
-    if (scene.num_nodes == 0) return found;
-
+// Persistent-threads traversal (Aila & Laine style "while-while" with per-lane ray replacement).
+//
+// Every lane owns at most one ray.  A lane whose ray has terminated immediately fetches the next
+// ray index from a global work counter (one warp-aggregated atomic for all idle lanes), so lanes
+// never idle behind the longest ray of their warp; inside an iteration all lanes first walk inner
+// nodes (inner while), then all lanes that reached a leaf intersect its triangles, which keeps the
+// two divergent phases apart.  Incoherent bounce rays ran at 5.6 active lanes per instruction with
+// one-ray-per-thread launches (profiles/r01_extend_baseline.txt); this loop is the fix.
+//
+//   fetch(index, &ray) -> bool   builds ray `index` (false: nothing to trace for this index)
+//   finish(index, hit, found)    consumes the result (closest hit record, or occlusion flag for ANY)
+template <bool ANY, bool STATS, typename Fetch, typename Finish>
+__device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, const float4 *top, int num_top, uint32_t num_rays,
+                                                   uint32_t *work_counter, Fetch fetch, Finish finish,
+                                                   TraversalCounters *counters, uint32_t *rays_traced) {
     int stack[kStackSize];
-    int sp = 0;
-    int cur = 0;
-    while (cur != kSentinel) {
-        if (cur >= 0) {
-            float4 n0, n1, nz;
-            int child0, child1;
-            LoadNode(scene.nodes, top, num_top, cur, &n0, &n1, &nz, &child0, &child1);
-            if (STATS) counters->nodes += 2;
-            const float c0lox = fmaf(n0.x, pre.idir.x, -pre.ood.x), c0hix = fmaf(n0.y, pre.idir.x, -pre.ood.x);
-            const float c0loy = fmaf(n0.z, pre.idir.y, -pre.ood.y), c0hiy = fmaf(n0.w, pre.idir.y, -pre.ood.y);
-            const float c0loz = fmaf(nz.x, pre.idir.z, -pre.ood.z), c0hiz = fmaf(nz.y, pre.idir.z, -pre.ood.z);
-            const float c1lox = fmaf(n1.x, pre.idir.x, -pre.ood.x), c1hix = fmaf(n1.y, pre.idir.x, -pre.ood.x);
-            const float c1loy = fmaf(n1.z, pre.idir.y, -pre.ood.y), c1hiy = fmaf(n1.w, pre.idir.y, -pre.ood.y);
-            const float c1loz = fmaf(nz.z, pre.idir.z, -pre.ood.z), c1hiz = fmaf(nz.w, pre.idir.z, -pre.ood.z);
-            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), ray.tmin));
-            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), ray.tmax));
-            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), ray.tmin));
-            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), ray.tmax));
-            const bool hit0 = c0min <= c0max, hit1 = c1min <= c1max;
-            if (!hit0 && !hit1) {
-                cur = sp > 0 ? stack[--sp] : kSentinel;
-            } else if (hit0 && hit1) {
-                const bool swap = c1min < c0min;
-                stack[sp++] = swap ? child0 : child1;
-                cur = swap ? child1 : child0;
-            } else {
-                cur = hit0 ? child0 : child1;
-            }
-        } else {
-            const uint32_t leaf = static_cast<uint32_t>(~cur);
-            const uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
-            const float4 *verts = reinterpret_cast<const float4 *>(scene.tri_verts + first);
-            for (uint32_t j = 0; j < count; ++j) {
-                const float4 p0 = __ldg(verts + 3 * j), p1 = __ldg(verts + 3 * j + 1), p2 = __ldg(verts + 3 * j + 2);
-                if (STATS) ++counters->prims;
-                float t, u, v;
-                bool inside;
-                if (IntersectTriangleWoop(ray, pre, p0, p1, p2, &t, &u, &v, &inside)) {
-                    if (ANY) return true;
-                    ray.tmax = t;
-                    hit->t = t;
-                    hit->prim = (first + j) | (inside ? kPrimInsideBit : 0u);
-                    hit->u = u;
-                    hit->v = v;
-                    found = true;
+    int sp = 0, cur = kSentinel;
+    bool has = false, exhausted = false, found = false;
+    uint32_t index = 0;
+    Ray ray;
+    ray.o = ray.d = mk3(0.0f);
+    ray.tmin = ray.tmax = 0.0f;
+    RayPre pre = Precompute(ray);
+    HitRec hit;
+    hit.t = 0.0f, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
+
+    for (;;) {
+        if (!has && !exhausted) {
+            index = AppendCoalesced(work_counter);
+            if (index >= num_rays) {
+                exhausted = true;
+            } else if (fetch(index, &ray)) {
+                pre = Precompute(ray);
+                hit.t = ray.tmax, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
+                found = false;
+                has = true;
+                sp = 0;
+                cur = scene.num_nodes ? 0 : kSentinel;
+                ++(*rays_traced);
+                // Analytic primitives (spheres, disks, cylinders) are few: tested linearly up front.
+                for (uint32_t i = 0; i < scene.num_analytic; ++i) {
+                    const AnalyticPrim &p = scene.analytic[i];
+                    if (STATS) ++counters->nodes;
+                    if (!IntersectBox(p.bmin, p.bmax, ray, pre)) continue;
+                    if (STATS) ++counters->prims;
+                    float t;
+                    if (IntersectAnalytic(p, ray, &t)) {
+                        found = true;
+                        if (ANY) {
+                            cur = kSentinel;
+                            break;
+                        }
+                        ray.tmax = t;
+                        hit.t = t;
+                        hit.prim = kPrimAnalyticBit | i;
+                    }
                 }
             }
-            cur = sp > 0 ? stack[--sp] : kSentinel;
+        }
+        if (__all_sync(0xffffffffu, !has)) break;
+        if (has) {
+            // ---- inner nodes: descend until this lane holds a leaf or runs out of work ----
+            while (static_cast<unsigned>(cur) < static_cast<unsigned>(kSentinel)) {
+                float4 n0, n1, nz;
+                int child0, child1;
+                LoadNode(scene.nodes, top, num_top, cur, &n0, &n1, &nz, &child0, &child1);
+                if (STATS) counters->nodes += 2;
+                const float c0lox = fmaf(n0.x, pre.idir.x, -pre.ood.x), c0hix = fmaf(n0.y, pre.idir.x, -pre.ood.x);
+                const float c0loy = fmaf(n0.z, pre.idir.y, -pre.ood.y), c0hiy = fmaf(n0.w, pre.idir.y, -pre.ood.y);
+                const float c0loz = fmaf(nz.x, pre.idir.z, -pre.ood.z), c0hiz = fmaf(nz.y, pre.idir.z, -pre.ood.z);
+                const float c1lox = fmaf(n1.x, pre.idir.x, -pre.ood.x), c1hix = fmaf(n1.y, pre.idir.x, -pre.ood.x);
+                const float c1loy = fmaf(n1.z, pre.idir.y, -pre.ood.y), c1hiy = fmaf(n1.w, pre.idir.y, -pre.ood.y);
+                const float c1loz = fmaf(nz.z, pre.idir.z, -pre.ood.z), c1hiz = fmaf(nz.w, pre.idir.z, -pre.ood.z);
+                const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), ray.tmin));
+                const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), ray.tmax));
+                const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), ray.tmin));
+                const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), ray.tmax));
+                const bool hit0 = c0min <= c0max, hit1 = c1min <= c1max;
+                if (!hit0 && !hit1) {
+                    cur = sp > 0 ? stack[--sp] : kSentinel;
+                } else if (hit0 && hit1) {
+                    const bool swap = c1min < c0min;
+                    stack[sp++] = swap ? child0 : child1;
+                    cur = swap ? child1 : child0;
+                } else {
+                    cur = hit0 ? child0 : child1;
+                }
+            }
+            // ---- leaf ----
+            if (cur < 0) {
+                const uint32_t leaf = static_cast<uint32_t>(~cur);
+                const uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
+                const float4 *verts = reinterpret_cast<const float4 *>(scene.tri_verts + first);
+                cur = sp > 0 ? stack[--sp] : kSentinel;
+                for (uint32_t j = 0; j < count; ++j) {
+                    const float4 p0 = __ldg(verts + 3 * j), p1 = __ldg(verts + 3 * j + 1), p2 = __ldg(verts + 3 * j + 2);
+                    if (STATS) ++counters->prims;
+                    float t, u, v;
+                    bool inside;
+                    if (IntersectTriangleWoop(ray, pre, p0, p1, p2, &t, &u, &v, &inside)) {
+                        found = true;
+                        if (ANY) {
+                            cur = kSentinel;
+                            break;
+                        }
+                        ray.tmax = t;
+                        hit.t = t;
+                        hit.prim = (first + j) | (inside ? kPrimInsideBit : 0u);
+                        hit.u = u;
+                        hit.v = v;
+                    }
+                }
+            }
+            if (cur == kSentinel) {
+                finish(index, hit, found);
+                has = false;
+            }
         }
     }
-    return found;
 }
 
 } // namespace b200pt

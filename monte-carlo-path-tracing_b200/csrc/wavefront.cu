@@ -91,59 +91,48 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ De
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
     const int num_top = StageTopNodes(scene, top, &bar);
-
     const uint32_t nslots = bp.pixel_count * bp.sample_count;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     TraversalCounters tc;
     uint32_t rays = 0;
-    for (uint32_t i0 = tid - lane; i0 < nslots; i0 += stride) {
-        const uint32_t slot = i0 + lane;
-        bool active = slot < nslots;
-        uint32_t px = 0, py = 0, s = 0;
-        if (active) {
-            const uint32_t local_pixel = bp.pixel_begin + slot / bp.sample_count;
-            s = bp.sample_begin + slot % bp.sample_count;
-            active = LocalPixelToImage(bp, local_pixel, &px, &py);
-        }
-        Ray ray;
-        HitRec hit;
-        bool found = false;
-        if (active) {
-            const float u = s * bp.spp_inv, v = VanDerCorput2(s + 1);
-            const float x = 2.0f * (px + u) / static_cast<int>(bp.width) - 1.0f,
-                        y = 1.0f - 2.0f * (py + v) / static_cast<int>(bp.height);
-            ray.o = mk3(bp.camera.eye);
-            ray.d = Normalize(mk3(bp.camera.front) + x * mk3(bp.camera.view_dx) + y * mk3(bp.camera.view_dy));
-            ray.tmin = kEpsilonDistance;
-            ray.tmax = kMaxFloat;
-            found = Traverse<false, STATS>(scene, top, num_top, ray, &hit, &tc);
-            ++rays;
-            if (!found) { // path.cpp:24-35: escaped camera ray sees the environment and the sun disc
-                V3 L = mk3(0.0f);
-                if (scene.integrator.id_envmap != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_envmap], ray.d);
-                if (scene.integrator.id_sun != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_sun], ray.d);
-                if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {
-                    radiance[slot] = L.x;
-                    radiance[capacity + slot] = L.y;
-                    radiance[2 * capacity + slot] = L.z;
-                }
+    Ray cam; // the camera ray of the slot this lane currently traces (the traversal shortens its own copy)
+    auto fetch = [&](uint32_t slot, Ray *ray) {
+        uint32_t px, py;
+        if (!LocalPixelToImage(bp, bp.pixel_begin + slot / bp.sample_count, &px, &py)) return false;
+        const uint32_t s = bp.sample_begin + slot % bp.sample_count;
+        const float u = s * bp.spp_inv, v = VanDerCorput2(s + 1);
+        const float x = 2.0f * (px + u) / static_cast<int>(bp.width) - 1.0f, y = 1.0f - 2.0f * (py + v) / static_cast<int>(bp.height);
+        ray->o = mk3(bp.camera.eye);
+        ray->d = Normalize(mk3(bp.camera.front) + x * mk3(bp.camera.view_dx) + y * mk3(bp.camera.view_dy));
+        ray->tmin = kEpsilonDistance;
+        ray->tmax = kMaxFloat;
+        cam = *ray;
+        return true;
+    };
+    auto finish = [&](uint32_t slot, const HitRec &hit, bool found) {
+        if (!found) { // path.cpp:24-35: an escaped camera ray sees the environment and the sun disc
+            V3 L = mk3(0.0f);
+            if (scene.integrator.id_envmap != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_envmap], cam.d);
+            if (scene.integrator.id_sun != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_sun], cam.d);
+            if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {
+                radiance[slot] = L.x;
+                radiance[capacity + slot] = L.y;
+                radiance[2 * capacity + slot] = L.z;
             }
+            return;
         }
-        const uint32_t idx = WarpAppend(found, &counters->queue[0]);
-        if (found) {
-            q.ox[idx] = ray.o.x, q.oy[idx] = ray.o.y, q.oz[idx] = ray.o.z;
-            q.dx[idx] = ray.d.x, q.dy[idx] = ray.d.y, q.dz[idx] = ray.d.z;
-            q.tr[idx] = 1.0f, q.tg[idx] = 1.0f, q.tb[idx] = 1.0f;
-            q.pdf[idx] = 0.0f;
-            q.slot[idx] = slot;
-            if (q.medium != nullptr) {
-                q.medium[idx] = kInvalid;
-                q.wx[idx] = -ray.d.x, q.wy[idx] = -ray.d.y, q.wz[idx] = -ray.d.z;
-            }
-            q.hit[idx] = hit;
+        const uint32_t idx = AppendCoalesced(&counters->queue[0]);
+        q.ox[idx] = cam.o.x, q.oy[idx] = cam.o.y, q.oz[idx] = cam.o.z;
+        q.dx[idx] = cam.d.x, q.dy[idx] = cam.d.y, q.dz[idx] = cam.d.z;
+        q.tr[idx] = 1.0f, q.tg[idx] = 1.0f, q.tb[idx] = 1.0f;
+        q.pdf[idx] = 0.0f;
+        q.slot[idx] = slot;
+        if (q.medium != nullptr) {
+            q.medium[idx] = kInvalid;
+            q.wx[idx] = -cam.d.x, q.wy[idx] = -cam.d.y, q.wz[idx] = -cam.d.z;
         }
-    }
+        q.hit[idx] = hit;
+    };
+    TraversePersistent<false, STATS>(scene, top, num_top, nslots, &counters->work_primary, fetch, finish, &tc, &rays);
     FlushCounters(STATS, tc, rays, kClassPrimary, counters);
 }
 
@@ -160,21 +149,16 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Dev
     const int num_top = StageTopNodes(scene, top, &bar);
     TraversalCounters tc;
     uint32_t rays = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Ray ray;
-        ray.o = mk3(q.ox[i], q.oy[i], q.oz[i]);
-        ray.d = mk3(q.dx[i], q.dy[i], q.dz[i]);
-        ray.tmin = kEpsilonDistance;
-        ray.tmax = kMaxFloat;
-        HitRec hit;
-        Traverse<false, STATS>(scene, top, num_top, ray, &hit, &tc);
-        q.hit[i] = hit;
-        ++rays;
-    }
-    if (STATS) {
-        __syncwarp();
-        FlushCounters(true, tc, rays, kClassExtend, counters);
-    }
+    auto fetch = [&](uint32_t i, Ray *ray) {
+        ray->o = mk3(q.ox[i], q.oy[i], q.oz[i]);
+        ray->d = mk3(q.dx[i], q.dy[i], q.dz[i]);
+        ray->tmin = kEpsilonDistance;
+        ray->tmax = kMaxFloat;
+        return true;
+    };
+    auto finish = [&](uint32_t i, const HitRec &hit, bool) { q.hit[i] = hit; };
+    TraversePersistent<false, STATS>(scene, top, num_top, n, &counters->work_extend, fetch, finish, &tc, &rays);
+    FlushCounters(STATS, tc, rays, kClassExtend, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -190,24 +174,22 @@ __global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ Dev
     const int num_top = StageTopNodes(scene, top, &bar);
     TraversalCounters tc;
     uint32_t rays = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Ray ray;
-        ray.o = mk3(sq.ox[i], sq.oy[i], sq.oz[i]);
-        ray.d = mk3(sq.dx[i], sq.dy[i], sq.dz[i]);
-        ray.tmin = kEpsilonDistance;
-        ray.tmax = sq.tmax[i];
-        ++rays;
-        if (!Traverse<true, STATS>(scene, top, num_top, ray, nullptr, &tc)) {
-            const uint32_t slot = sq.slot[i];
-            atomicAdd(radiance + slot, sq.cr[i]);
-            atomicAdd(radiance + capacity + slot, sq.cg[i]);
-            atomicAdd(radiance + 2 * capacity + slot, sq.cb[i]);
-        }
-    }
-    if (STATS) {
-        __syncwarp();
-        FlushCounters(true, tc, rays, kClassShadow, counters);
-    }
+    auto fetch = [&](uint32_t i, Ray *ray) {
+        ray->o = mk3(sq.ox[i], sq.oy[i], sq.oz[i]);
+        ray->d = mk3(sq.dx[i], sq.dy[i], sq.dz[i]);
+        ray->tmin = kEpsilonDistance;
+        ray->tmax = sq.tmax[i];
+        return true;
+    };
+    auto finish = [&](uint32_t i, const HitRec &, bool occluded) {
+        if (occluded) return;
+        const uint32_t slot = sq.slot[i];
+        atomicAdd(radiance + slot, sq.cr[i]);
+        atomicAdd(radiance + capacity + slot, sq.cg[i]);
+        atomicAdd(radiance + 2 * capacity + slot, sq.cb[i]);
+    };
+    TraversePersistent<true, STATS>(scene, top, num_top, n, &counters->work_shadow, fetch, finish, &tc, &rays);
+    FlushCounters(STATS, tc, rays, kClassShadow, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -528,6 +510,8 @@ __global__ void __launch_bounds__(kThreads) k_shade(const __grid_constant__ Devi
 __global__ void k_reset(Counters *c, int which_queue, bool reset_shadow) {
     if (which_queue >= 0) c->queue[which_queue] = 0;
     if (reset_shadow) c->shadow = 0;
+    c->work_extend = 0;
+    c->work_shadow = 0;
 }
 
 // renderer.cpp:76-84: clamp each SAMPLE to <= 1 per channel (Q2), then sum the pixel's samples.

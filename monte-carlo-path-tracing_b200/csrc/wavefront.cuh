@@ -47,10 +47,14 @@ struct ClassCounters {
 
 struct Counters {             // device-resident
     uint32_t queue[2];        // entries in path queue 0 / 1 (zeroed per batch)
-    uint32_t shadow;
-    uint32_t pad;
+    uint32_t shadow;          // entries in the shadow queue
+    uint32_t work_primary;    // next unclaimed ray of the persistent traversal loops
+    uint32_t work_extend;
+    uint32_t work_shadow;
+    uint32_t pad[2];
     ClassCounters cls[3];     // primary / extend / shadow traversal statistics (zeroed per render)
 };
+constexpr size_t kCountersPerBatchBytes = 32; // the part of Counters that is zeroed for every batch
 
 struct BatchParams {
     DCamera camera;
