@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -90,6 +91,8 @@ struct b200pt_context {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     bool timing_pending = false;
     int num_sms = 148;
+    // launch tunables (overridable through the environment for experiments: B200PT_TOP_NODES, B200PT_REFILL, B200PT_CTAS_PER_SM)
+    int top_nodes = 256, refill = 16, ctas_per_sm = 4, min_inner = 8;
     // B200PT_STATS_TIMING: (class, begin, end) per launch, resolved in b200pt_get_stats
     struct TimedLaunch {
         int cls;
@@ -290,6 +293,10 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     lc.threads = 256;
     lc.stream = stream;
     lc.stats = ro.counters;
+    lc.top_nodes = c->top_nodes;
+    lc.refill = c->refill;
+    lc.min_inner = c->min_inner;
+    lc.blocks = c->num_sms * c->ctas_per_sm;
 
     uint64_t launches = 0;
     c->timed.clear();
@@ -387,6 +394,14 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     c->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    auto env_int = [](const char *name, int fallback, int lo, int hi) {
+        const char *v = getenv(name);
+        return v ? std::min(std::max(atoi(v), lo), hi) : fallback;
+    };
+    c->top_nodes = env_int("B200PT_TOP_NODES", c->top_nodes, 1, kTopNodesMax);
+    c->refill = env_int("B200PT_REFILL", c->refill, 1, 32);
+    c->min_inner = env_int("B200PT_MIN_INNER", c->min_inner, 1, 32);
+    c->ctas_per_sm = env_int("B200PT_CTAS_PER_SM", c->ctas_per_sm, 1, 16);
 
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();
@@ -461,6 +476,7 @@ int b200pt_assemble_tiles_device(b200pt_handle h, uint32_t width, uint32_t heigh
     CU_CHECK(h, cudaSetDevice(h->device));
     LaunchConfig lc;
     lc.blocks = h->num_sms * 4, lc.threads = 256, lc.stream = static_cast<cudaStream_t>(stream), lc.stats = false;
+    lc.top_nodes = h->top_nodes, lc.refill = h->refill, lc.min_inner = h->min_inner;
     LaunchAssemble(lc, width, height, tile_world, PixelsPerRank(width, height, tile_world), gathered_dev, frame_dev);
     CU_CHECK(h, cudaGetLastError());
     return B200PT_OK;

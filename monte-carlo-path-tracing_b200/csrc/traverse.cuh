@@ -149,7 +149,8 @@ struct TraversalCounters {
 
 constexpr int kStackSize = 64;
 constexpr int kSentinel = 0x7FFFFFFF;
-constexpr int kTopNodes = 512;  // nodes staged in shared memory (32 KB)
+constexpr int kTopNodes = 512;     // default number of BVH nodes staged in shared memory (32 KB per CTA)
+constexpr int kTopNodesMax = 2048; // upper bound (128 KB)
 
 // One BVH2 node = 4 x 16 B loads; `top` is the shared-memory copy of nodes [0, num_top).
 __device__ __forceinline__ void LoadNode(const BvhNode *__restrict__ nodes, const float4 *top, int num_top, int index,
@@ -191,7 +192,7 @@ __device__ __forceinline__ uint32_t AppendCoalesced(uint32_t *counter) {
 //   finish(index, hit, found)    consumes the result (closest hit record, or occlusion flag for ANY)
 template <bool ANY, bool STATS, typename Fetch, typename Finish>
 __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, const float4 *top, int num_top, uint32_t num_rays,
-                                                   uint32_t *work_counter, Fetch fetch, Finish finish,
+                                                   uint32_t *work_counter, int refill_threshold, int min_inner_lanes, Fetch fetch, Finish finish,
                                                    TraversalCounters *counters, uint32_t *rays_traced) {
     int stack[kStackSize];
     int sp = 0, cur = kSentinel;
@@ -205,7 +206,11 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
     hit.t = 0.0f, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
 
     for (;;) {
-        if (!has && !exhausted) {
+        // Refill idle lanes in groups: the fetch path (ray load, 1/d, shear constants) is long, so it is run
+        // when at least `refill_threshold` lanes are idle (or nothing else is left to do), not lane by lane.
+        const unsigned idle = __ballot_sync(0xffffffffu, !has && !exhausted);
+        const bool refill = __popc(idle) >= refill_threshold || __all_sync(0xffffffffu, !has);
+        if (refill && !has && !exhausted) {
             index = AppendCoalesced(work_counter);
             if (index >= num_rays) {
                 exhausted = true;
@@ -265,6 +270,10 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                 } else {
                     cur = hit0 ? child0 : child1;
                 }
+                // Most lanes of an incoherent warp reach their next leaf within a few steps while a few stragglers
+                // keep descending; once fewer than `min_inner_lanes` lanes are still walking inner nodes the warp
+                // leaves the inner phase so the waiting lanes can intersect their leaves (stragglers resume later).
+                if (__popc(__activemask()) < min_inner_lanes) break;
             }
             // ---- leaf ----
             if (cur < 0) {

@@ -25,8 +25,8 @@ __device__ __forceinline__ uint32_t SmemAddr(const void *p) { return static_cast
 // Stage the top of the BVH (nodes [0, num_top), breadth-first order) into shared memory with one
 // TMA bulk copy (cp.async.bulk, completion signalled on an mbarrier).  Every ray walks these
 // nodes, so they are served at shared-memory latency instead of L2.
-__device__ __forceinline__ int StageTopNodes(const DeviceScene &scene, float4 *top, uint64_t *bar) {
-    const int num_top = min(static_cast<int>(scene.num_nodes), kTopNodes);
+__device__ __forceinline__ int StageTopNodes(const DeviceScene &scene, float4 *top, uint64_t *bar, int max_top) {
+    const int num_top = min(static_cast<int>(scene.num_nodes), max_top);
     if (num_top == 0) return 0;
     const uint32_t bytes = static_cast<uint32_t>(num_top) * sizeof(BvhNode);
     const uint32_t bar_addr = SmemAddr(bar);
@@ -87,10 +87,11 @@ __device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounter
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ DeviceScene scene,
                                                       const __grid_constant__ BatchParams bp, PathQueue q,
-                                                      float *radiance, uint32_t capacity, Counters *counters) {
+                                                      float *radiance, uint32_t capacity, Counters *counters, int max_top,
+                                                      int refill, int min_inner) {
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
-    const int num_top = StageTopNodes(scene, top, &bar);
+    const int num_top = StageTopNodes(scene, top, &bar, max_top);
     const uint32_t nslots = bp.pixel_count * bp.sample_count;
     TraversalCounters tc;
     uint32_t rays = 0;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ De
         }
         q.hit[idx] = hit;
     };
-    TraversePersistent<false, STATS>(scene, top, num_top, nslots, &counters->work_primary, fetch, finish, &tc, &rays);
+    TraversePersistent<false, STATS>(scene, top, num_top, nslots, &counters->work_primary, refill, min_inner, fetch, finish, &tc, &rays);
     FlushCounters(STATS, tc, rays, kClassPrimary, counters);
 }
 
@@ -141,12 +142,12 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ De
 // ---------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ DeviceScene scene, PathQueue q, int which,
-                                                     Counters *counters) {
+                                                     Counters *counters, int max_top, int refill, int min_inner) {
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
     const uint32_t n = counters->queue[which];
     if (blockIdx.x * blockDim.x >= n) return;
-    const int num_top = StageTopNodes(scene, top, &bar);
+    const int num_top = StageTopNodes(scene, top, &bar, max_top);
     TraversalCounters tc;
     uint32_t rays = 0;
     auto fetch = [&](uint32_t i, Ray *ray) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Dev
         return true;
     };
     auto finish = [&](uint32_t i, const HitRec &hit, bool) { q.hit[i] = hit; };
-    TraversePersistent<false, STATS>(scene, top, num_top, n, &counters->work_extend, fetch, finish, &tc, &rays);
+    TraversePersistent<false, STATS>(scene, top, num_top, n, &counters->work_extend, refill, min_inner, fetch, finish, &tc, &rays);
     FlushCounters(STATS, tc, rays, kClassExtend, counters);
 }
 
@@ -166,12 +167,12 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Dev
 // ---------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ DeviceScene scene, ShadowQueue sq, float *radiance,
-                                                    uint32_t capacity, Counters *counters) {
+                                                    uint32_t capacity, Counters *counters, int max_top, int refill, int min_inner) {
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
     const uint32_t n = counters->shadow;
     if (blockIdx.x * blockDim.x >= n) return;
-    const int num_top = StageTopNodes(scene, top, &bar);
+    const int num_top = StageTopNodes(scene, top, &bar, max_top);
     TraversalCounters tc;
     uint32_t rays = 0;
     auto fetch = [&](uint32_t i, Ray *ray) {
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ Dev
         atomicAdd(radiance + capacity + slot, sq.cg[i]);
         atomicAdd(radiance + 2 * capacity + slot, sq.cb[i]);
     };
-    TraversePersistent<true, STATS>(scene, top, num_top, n, &counters->work_shadow, fetch, finish, &tc, &rays);
+    TraversePersistent<true, STATS>(scene, top, num_top, n, &counters->work_shadow, refill, min_inner, fetch, finish, &tc, &rays);
     FlushCounters(STATS, tc, rays, kClassShadow, counters);
 }
 
@@ -577,13 +578,13 @@ __global__ void k_assemble(uint32_t width, uint32_t height, uint32_t tile_world,
     }
 }
 
-size_t TopSmemBytes() { return static_cast<size_t>(kTopNodes) * sizeof(BvhNode); }
+size_t TopSmemBytes(const LaunchConfig &lc) { return static_cast<size_t>(std::max(lc.top_nodes, 1)) * sizeof(BvhNode); }
 
 template <typename K>
 void EnableSmem(K kernel) {
     static bool done = false; // one static per kernel instantiation
     if (!done) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TopSmemBytes()));
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTopNodesMax * sizeof(BvhNode)));
         done = true;
     }
 }
@@ -594,20 +595,20 @@ void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const Batch
                    uint32_t capacity, Counters *counters) {
     if (lc.stats) {
         EnableSmem(k_primary<true>);
-        k_primary<true><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, bp, q, radiance, capacity, counters);
+        k_primary<true><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, bp, q, radiance, capacity, counters, lc.top_nodes, lc.refill, lc.min_inner);
     } else {
         EnableSmem(k_primary<false>);
-        k_primary<false><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, bp, q, radiance, capacity, counters);
+        k_primary<false><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, bp, q, radiance, capacity, counters, lc.top_nodes, lc.refill, lc.min_inner);
     }
 }
 
 void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, PathQueue q, int which, Counters *counters) {
     if (lc.stats) {
         EnableSmem(k_extend<true>);
-        k_extend<true><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, q, which, counters);
+        k_extend<true><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, q, which, counters, lc.top_nodes, lc.refill, lc.min_inner);
     } else {
         EnableSmem(k_extend<false>);
-        k_extend<false><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, q, which, counters);
+        k_extend<false><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, q, which, counters, lc.top_nodes, lc.refill, lc.min_inner);
     }
 }
 
@@ -615,10 +616,10 @@ void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, ShadowQueue 
                   Counters *counters) {
     if (lc.stats) {
         EnableSmem(k_shadow<true>);
-        k_shadow<true><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, sq, radiance, capacity, counters);
+        k_shadow<true><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, sq, radiance, capacity, counters, lc.top_nodes, lc.refill, lc.min_inner);
     } else {
         EnableSmem(k_shadow<false>);
-        k_shadow<false><<<lc.blocks, kThreads, TopSmemBytes(), lc.stream>>>(scene, sq, radiance, capacity, counters);
+        k_shadow<false><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, sq, radiance, capacity, counters, lc.top_nodes, lc.refill, lc.min_inner);
     }
 }
 

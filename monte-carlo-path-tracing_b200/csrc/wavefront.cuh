@@ -84,6 +84,9 @@ struct LaunchConfig {
     int threads;
     cudaStream_t stream;
     bool stats;
+    int top_nodes;            // BVH nodes staged in shared memory per CTA (64 B each)
+    int refill;               // idle lanes per warp that trigger a ray refill in the traversal loops
+    int min_inner;            // lanes still walking inner nodes below which a warp switches to its pending leaves
 };
 
 // kernel launchers (wavefront.cu)
