@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <numeric>
@@ -272,8 +273,8 @@ struct BuildNode {
 
 class BvhBuilder {
 public:
-    BvhBuilder(const std::vector<Box> &boxes, const std::vector<V3> &centers, uint32_t max_leaf)
-        : boxes_(boxes), centers_(centers), max_leaf_(max_leaf) {
+    BvhBuilder(const std::vector<Box> &boxes, const std::vector<V3> &centers, uint32_t max_leaf, float traversal_cost)
+        : boxes_(boxes), centers_(centers), max_leaf_(max_leaf), traversal_cost_(traversal_cost) {
         order_.resize(boxes.size());
         std::iota(order_.begin(), order_.end(), 0u);
         nodes_.reserve(boxes.size() * 2);
@@ -340,8 +341,8 @@ private:
             }
         }
         const float leaf_cost = box.HalfArea() * n;
-        // traversal step ~ 1 triangle test
-        if (n <= max_leaf_ && (best_axis < 0 || best_cost + box.HalfArea() >= leaf_cost)) return make_leaf();
+        // SAH: splitting costs one traversal step (traversal_cost_ triangle tests) on top of the children's expected tests
+        if (n <= max_leaf_ && (best_axis < 0 || best_cost + traversal_cost_ * box.HalfArea() >= leaf_cost)) return make_leaf();
 
         uint32_t mid;
         if (best_axis < 0) {
@@ -366,6 +367,7 @@ private:
     const std::vector<Box> &boxes_;
     const std::vector<V3> &centers_;
     uint32_t max_leaf_;
+    float traversal_cost_;
     std::vector<uint32_t> order_;
     std::vector<BuildNode> nodes_;
 };
@@ -899,7 +901,8 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, HostScen
             *error = "too many triangles for the leaf encoding.";
             return false;
         }
-        BvhBuilder builder(boxes, centers, max_leaf_size);
+        const char *ct_env = getenv("B200PT_SAH_TRAVERSAL_COST"); // tuning knob, default 1 triangle test per node step
+        BvhBuilder builder(boxes, centers, max_leaf_size, ct_env ? static_cast<float>(atof(ct_env)) : 1.0f);
         const int32_t root = builder.Build();
         FlattenBvh(builder.nodes(), root, 1024, &hs->nodes);
         order = builder.order();

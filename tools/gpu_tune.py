@@ -17,7 +17,7 @@ caps = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [24, 2
 scene = pkg.Scene(os.path.join(ROOT, "scenes", name + ".b200scene"))
 frame = torch.zeros(h * w * 3, dtype=torch.float32, device="cuda")
 for cap in caps:
-    r = pkg.Renderer(scene, device=0, max_paths_in_flight=1 << cap)
+    r = pkg.Renderer(scene, device=0, max_paths_in_flight=1 << cap, max_leaf_size=int(os.environ.get("LEAF", "0")))
     for _ in range(2):
         r.draw_device(frame, w, h, spp, seed=1)
     torch.cuda.synchronize()
@@ -29,6 +29,6 @@ for cap in caps:
     r.draw_device(frame, w, h, spp, seed=1, stats=pkg.STATS_TIMING)
     torch.cuda.synchronize()
     st = r.stats()
-    print(json.dumps({"cap_log2": cap, "ms": ms, "Msamples_s": w * h * spp / min(ms) / 1e3, "launches": st["kernel_launches"],
+    print(json.dumps({"cap_log2": cap, "nodes": st["num_bvh_nodes"], "ms": ms, "Msamples_s": w * h * spp / min(ms) / 1e3, "launches": st["kernel_launches"],
                       **{k: round(st[k]["ms"], 2) for k in ("primary", "extend", "shadow", "shade", "other")}}), flush=True)
     r.close()
