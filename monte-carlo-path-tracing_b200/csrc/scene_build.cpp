@@ -13,6 +13,7 @@
 // The acceleration structure is NOT the reference's per-instance LBVH: one binned-SAH
 // BVH2 over all world-space triangles, 2 child boxes per 64-byte node, BFS-ordered top.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -277,19 +278,19 @@ public:
         : boxes_(boxes), centers_(centers), max_leaf_(max_leaf), traversal_cost_(traversal_cost) {
         order_.resize(boxes.size());
         std::iota(order_.begin(), order_.end(), 0u);
-        nodes_.reserve(boxes.size() * 2);
+        nodes_.resize(boxes.size() * 2 + 1); // a binary tree over n leaves has at most 2n-1 nodes
     }
 
-    int32_t Build() { return Recurse(0, static_cast<uint32_t>(order_.size())); }
+    int32_t Build() { return Recurse(0, static_cast<uint32_t>(order_.size()), 0); }
     const std::vector<BuildNode> &nodes() const { return nodes_; }
     const std::vector<uint32_t> &order() const { return order_; }
 
 private:
     static constexpr int kBins = 32;
 
-    int32_t Recurse(uint32_t begin, uint32_t end) {
-        const int32_t id = static_cast<int32_t>(nodes_.size());
-        nodes_.emplace_back();
+    // Sub-ranges of order_ are disjoint, node slots come from an atomic counter: large subtrees build on their own thread.
+    int32_t Recurse(uint32_t begin, uint32_t end, int depth) {
+        const int32_t id = next_node_.fetch_add(1);
         Box box, cbox;
         for (uint32_t i = begin; i < end; ++i) {
             box.Grow(boxes_[order_[i]]);
@@ -357,8 +358,15 @@ private:
             mid = static_cast<uint32_t>(it - order_.begin());
             if (mid == begin || mid == end) mid = begin + n / 2;
         }
-        const int32_t l = Recurse(begin, mid);
-        const int32_t r = Recurse(mid, end);
+        int32_t l, r;
+        if (depth < 5 && n > 32768) {
+            std::thread left([&]() { l = Recurse(begin, mid, depth + 1); });
+            r = Recurse(mid, end, depth + 1);
+            left.join();
+        } else {
+            l = Recurse(begin, mid, depth + 1);
+            r = Recurse(mid, end, depth + 1);
+        }
         nodes_[id].left = l;
         nodes_[id].right = r;
         return id;
@@ -370,6 +378,7 @@ private:
     float traversal_cost_;
     std::vector<uint32_t> order_;
     std::vector<BuildNode> nodes_;
+    std::atomic<int32_t> next_node_{0};
 };
 
 int32_t EncodeLeaf(uint32_t first, uint32_t count) { return ~static_cast<int32_t>((first << 3) | (count - 1)); }
