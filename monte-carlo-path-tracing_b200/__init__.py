@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+LIB_PATH = os.environ.get("B200PT_LIB", os.path.join(_HERE, "libb200pt.so"))  # override only for A/B experiments
 INVALID_ID = 0xFFFFFFFF
 
 
