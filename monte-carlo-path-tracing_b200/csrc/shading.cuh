@@ -357,6 +357,9 @@ __device__ __forceinline__ V3 FresnelSchlick(float cos_theta, V3 r) { return (1.
 // kulla_conty.cpp:82-131
 __device__ __forceinline__ float GetBrdfAvg(const float *buf, float cos_theta, float roughness) {
     constexpr int R = kLutResolution;
+    // EvaluateDielectric's transmission branch passes N_dot_O < 0 (dielectric.cpp:207-212): the reference reads
+    // out of bounds there (arbitrary heap value); clamped here, as in the oracle.
+    cos_theta = fmaxf(cos_theta, 0.0f);
     const float offset1 = roughness * R, offset2 = cos_theta * R;
     const int i1 = static_cast<int>(offset1), i2 = static_cast<int>(offset2);
     if (i1 >= R - 1) {

@@ -536,6 +536,10 @@ static Vec3 FresnelSchlick3(float cos_theta, Vec3 r) { return add(muls(ssub(1.0f
 /* kulla_conty.cpp */
 static float GetBrdfAvg(const float *buf, float cos_theta, float roughness) { /* :82-131 */
     const int R = kLutResolution;
+    /* EvaluateDielectric's transmission branch (dielectric.cpp:207-212) passes N_dot_O < 0 here; the reference then
+     * indexes the table with a negative offset (an out-of-bounds heap read whose value is arbitrary).  Both
+     * restatements clamp instead; frames that take this branch match the reference only to ~1e-5. */
+    if (cos_theta < 0.0f) cos_theta = 0.0f;
     const float offset1 = roughness * R, offset2 = cos_theta * R;
     const int i1 = (int)offset1, i2 = (int)offset2;
     if (i1 >= R - 1) {

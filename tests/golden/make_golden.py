@@ -86,8 +86,26 @@ def main():
         frame, _, seconds = woop.render_pack(pack, w, h, spp)
         np.save(os.path.join(HERE, f"converged_{name}.npy"), frame.astype(np.float32))
         print("converged", name, frame.mean(), f"{seconds:.1f}s")
+    # ---- synthetic scenes (tests/scene_builder.py): the branches the BASELINE scenes never reach ----
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, ROOT)
+    import scene_builder
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    synthetic = {}
+    for name, builder in scene_builder.synthetic_scenes().items():
+        desc = builder.desc()
+        pack = os.path.join(HERE, f"synthetic_{name}.b200scene")
+        assert pkg.lib().b200pt_scene_save(ctypes.byref(desc), pack.encode()) == 0
+        for variant, ref in (("woop", woop), ("mt", mt)):
+            frame, _, _ = ref.render_pack(pack, 32, 32, 4)
+            np.save(os.path.join(HERE, f"exact_synthetic_{name}_{variant}.npy"), frame)
+        frame, _, seconds = woop.render_pack(pack, 64, 64, 512)
+        np.save(os.path.join(HERE, f"converged_synthetic_{name}.npy"), frame.astype(np.float32))
+        synthetic[name] = {"exact": [32, 32, 4], "converged": [64, 64, 512]}
+        print("synthetic", name, frame.mean(), f"{seconds:.1f}s")
     with open(os.path.join(HERE, "settings.json"), "w") as f:
-        json.dump({"exact": EXACT, "converged": CONVERGED}, f, indent=1)
+        json.dump({"exact": EXACT, "converged": CONVERGED, "synthetic": synthetic}, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -26,7 +26,8 @@ _RENDERERS = {}
 
 def renderer(pkg, name):
     if name not in _RENDERERS:
-        _RENDERERS[name] = pkg.Renderer(pkg.Scene(pack(name)), device=0, max_paths_in_flight=1 << 22)
+        path = os.path.join(GOLDEN, name + ".b200scene") if name.startswith("synthetic_") else pack(name)
+        _RENDERERS[name] = pkg.Renderer(pkg.Scene(path), device=0, max_paths_in_flight=1 << 22)
     return _RENDERERS[name]
 
 
@@ -51,6 +52,21 @@ def test_matches_reference_golden_frames(pkg, scene):
     floor_pixel, floor_box = rel_l2(a, b), rel_l2(boxed(a), boxed(b))
     mean_ratio = a.mean() / golden.mean()
     assert abs(mean_ratio - 1.0) < 0.01, f"{scene}: mean ratio {mean_ratio}"
+    assert rel_l2(boxed(a), boxed(golden)) <= 2.0 * floor_box + 0.005, (scene, rel_l2(boxed(a), boxed(golden)), floor_box)
+    assert rel_l2(a, golden) <= 1.5 * floor_pixel + 0.005, (scene, rel_l2(a, golden), floor_pixel)
+
+
+@pytest.mark.parametrize("scene", sorted(SETTINGS["synthetic"]))
+def test_synthetic_scenes_match_reference_golden(pkg, scene):
+    """Every BSDF / emitter / primitive / medium branch the BASELINE scenes never reach (tests/scene_builder.py)."""
+    w, h, spp = SETTINGS["synthetic"][scene]["converged"]
+    golden = np.load(os.path.join(GOLDEN, f"converged_synthetic_{scene}.npy"))
+    r = renderer(pkg, "synthetic_" + scene)
+    a = r.Draw(width=w, height=h, spp=spp, seed=21)
+    b = r.Draw(width=w, height=h, spp=spp, seed=22)
+    assert np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 1.0 + 1e-6
+    floor_pixel, floor_box = rel_l2(a, b), rel_l2(boxed(a), boxed(b))
+    assert abs(a.mean() / golden.mean() - 1.0) < 0.01, (scene, a.mean(), golden.mean())
     assert rel_l2(boxed(a), boxed(golden)) <= 2.0 * floor_box + 0.005, (scene, rel_l2(boxed(a), boxed(golden)), floor_box)
     assert rel_l2(a, golden) <= 1.5 * floor_pixel + 0.005, (scene, rel_l2(a, golden), floor_pixel)
 

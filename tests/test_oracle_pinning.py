@@ -97,6 +97,42 @@ def test_frames_match_reference_golden_bit_for_bit(oracle, scene, variant):
     assert np.array_equal(frame, golden), f"max abs diff {np.abs(frame - golden).max()}"
 
 
+@pytest.mark.parametrize("variant", ["woop", "mt"])
+@pytest.mark.parametrize("scene", sorted(SETTINGS["synthetic"]))
+def test_synthetic_scenes_match_reference_golden(oracle, scene, variant):
+    """Plastic, thin / rough dielectric, rough diffuse, anisotropic conductor, cylinder, disk, bump + bitmap on meshes,
+    spot / point / sun / env-map / constant emitters, one-sided surfaces, isotropic medium behind a BSDF-less surface."""
+    w, h, spp = SETTINGS["synthetic"][scene]["exact"]
+    golden = np.load(os.path.join(GOLDEN, f"exact_synthetic_{scene}_{variant}.npy"))
+    frame = oracle.render_pack(os.path.join(GOLDEN, f"synthetic_{scene}.b200scene"), w, h, spp, watertight=(variant == "woop"))
+    if scene == "dielectrics_conductor_cylinder":
+        # the rough dielectric's transmission evaluate reads the Kulla-Conty table out of bounds in the reference
+        # (undefined value, see GetBrdfAvg in oracle/pt_oracle.c): everything else must still agree
+        assert np.linalg.norm(frame - golden) / np.linalg.norm(golden) < 1e-4
+        assert (np.abs(frame - golden).max(axis=2) > 0).mean() < 0.03
+    else:
+        assert np.array_equal(frame, golden), f"max abs diff {np.abs(frame - golden).max()}"
+
+
+def test_scene_builder_matches_header_layout(tmp_path):
+    """tests/scene_builder.py mirrors include/b200pt.h with ctypes; the C compiler has the last word on the layout."""
+    import ctypes
+    import subprocess
+    import scene_builder as sb
+    from conftest import ROOT
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200pt.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   "sizeof(b200pt_camera),sizeof(b200pt_integrator),sizeof(b200pt_texture),sizeof(b200pt_bsdf),sizeof(b200pt_medium),"
+                   "sizeof(b200pt_instance),sizeof(b200pt_emitter),sizeof(b200pt_scene_desc),offsetof(b200pt_instance,num_vertices),"
+                   "offsetof(b200pt_texture,pixel_offset));return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [ctypes.sizeof(sb.Camera), ctypes.sizeof(sb.Integrator), ctypes.sizeof(sb.Texture), ctypes.sizeof(sb.Bsdf),
+                     ctypes.sizeof(sb.Medium), ctypes.sizeof(sb.Instance), ctypes.sizeof(sb.Emitter), ctypes.sizeof(sb.SceneDesc),
+                     sb.Instance.num_vertices.offset, sb.Texture.pixel_offset.offset]
+
+
 def test_frame_independent_of_thread_count(oracle):
     a = oracle.render_pack(pack("cornell-box"), 16, 16, 2, threads=1)
     b = oracle.render_pack(pack("cornell-box"), 16, 16, 2, threads=5)
