@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round evidence run (one gpurun call): GPU tests, both bench arms, ncu launch list, per-kernel DRAM traffic, one --set full capture.
+set -u
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/gpu.txt 2>&1
+echo "== pytest -m gpu"; (time timeout 1500 python -m pytest tests -m gpu -x -q) > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
+echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
+echo "== bench reference"; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err; cat $O/bench_reference.json
+echo "== bench b200"; timeout 900 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; cat $O/bench_n1.json
+echo "== ncu launch list of bench.py"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
+echo "== ncu DRAM bytes of every kernel of one frame"
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 120 --csv \
+    --log-file $O/dram_one_frame.csv python tools/one_frame.py dragon 1024 1024 256 > $O/one_frame_ncu.log 2>&1
+echo "== ncu --set full of the first launches of each kernel"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_(primary|extend|shadow|shade)' -c 8 -f -o $O/full_first8 \
+    python tools/one_frame.py dragon 1024 1024 256 > $O/full_ncu.log 2>&1
+ls -la $O
