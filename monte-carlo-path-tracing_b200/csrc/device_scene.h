@@ -121,6 +121,8 @@ struct DIntegrator {
     uint32_t depth_rr, depth_max;
     uint32_t num_emitters, num_area_lights;
     uint32_t id_sun, id_envmap;
+    uint32_t has_opacity;        // some instance's BSDF carries an opacity texture: traversal runs its alpha-test variant
+    uint32_t pad;
 };
 
 // Everything the kernels dereference.  Passed by value as a kernel parameter.

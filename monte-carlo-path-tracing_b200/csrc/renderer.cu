@@ -92,7 +92,7 @@ struct b200pt_context {
     bool timing_pending = false;
     int num_sms = 148;
     // launch tunables (overridable through the environment for experiments: B200PT_TOP_NODES, B200PT_REFILL, B200PT_CTAS_PER_SM)
-    int top_nodes = 256, refill = 16, ctas_per_sm = 4, min_inner = 8;
+    int top_nodes = 0, refill = 16, ctas_per_sm = 4, min_inner = 8; // top_nodes = 0: no shared-memory staging (profiles/r01_sweep_sel3_topnodes.log)
     // B200PT_STATS_TIMING: (class, begin, end) per launch, resolved in b200pt_get_stats
     struct TimedLaunch {
         int cls;
@@ -345,7 +345,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
                                 c->counters.ptr, capacity);
                 });
                 if (c->shadow_per_vertex > 0)
-                    launch(kClassShadow, [&] { LaunchShadow(lc, c->scene, c->shadow, c->radiance, capacity, c->counters.ptr); });
+                    launch(kClassShadow, [&] { LaunchShadow(lc, c->scene, bp, depth, c->shadow, c->radiance, capacity, c->counters.ptr); });
                 which ^= 1;
                 if (depth == max_rounds) break;
                 if (depth >= 8 && (depth & 3) == 0) { // poll the survivor count
@@ -354,7 +354,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
                     CU_CHECK(c, cudaStreamSynchronize(stream));
                     if (*c->pinned_count == 0) break;
                 }
-                launch(kClassExtend, [&] { LaunchExtend(lc, c->scene, c->queue[which], which, c->counters.ptr); });
+                launch(kClassExtend, [&] { LaunchExtend(lc, c->scene, bp, depth, c->queue[which], which, c->counters.ptr); });
             }
             launch(kClassOther, [&] { LaunchResolve(lc, bp, c->radiance, capacity, c->accum.ptr); });
         }
@@ -398,7 +398,7 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
         const char *v = getenv(name);
         return v ? std::min(std::max(atoi(v), lo), hi) : fallback;
     };
-    c->top_nodes = env_int("B200PT_TOP_NODES", c->top_nodes, 1, kTopNodesMax);
+    c->top_nodes = env_int("B200PT_TOP_NODES", c->top_nodes, 0, kTopNodesMax);
     c->refill = env_int("B200PT_REFILL", c->refill, 1, 32);
     c->min_inner = env_int("B200PT_MIN_INNER", c->min_inner, 1, 32);
     c->ctas_per_sm = env_int("B200PT_CTAS_PER_SM", c->ctas_per_sm, 1, 16);

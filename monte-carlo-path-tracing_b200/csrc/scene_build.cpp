@@ -1034,6 +1034,9 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, HostScen
     ig.num_area_lights = static_cast<uint32_t>(hs->map_area_light_instance.size());
     ig.id_sun = id_sun;
     ig.id_envmap = id_envmap;
+    ig.has_opacity = 0;
+    for (const DInstance &in : hs->instances)
+        if (in.id_bsdf != kInvalid && hs->bsdfs[in.id_bsdf].id_opacity != kInvalid) ig.has_opacity = 1;
 
     // ---- Kulla-Conty LUTs (renderer.cpp:311-314); only read by conductor/dielectric BSDFs ----
     hs->kc_brdf_avg.assign(kLutResolution * kLutResolution, 0.0f);

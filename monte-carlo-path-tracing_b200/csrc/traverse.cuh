@@ -7,6 +7,7 @@
 // their own: to_world is baked into the triangles, scene.cpp:261-281), so the two-level
 // walk collapses into one.
 #pragma once
+#include "textures.cuh"
 #include "vecmath.cuh"
 
 namespace b200pt {
@@ -52,6 +53,17 @@ __device__ __forceinline__ RayPre Precompute(const Ray &r) {
     return p;
 }
 
+// a[k] for a per-lane k in {0,1,2} as two SEL instructions.  Written in PTX because nvcc turns the C++ conditional
+// into divergent branches (BSSY/BRA/BSYNC per component: profiles/r01_full_first8.txt, 160 instructions per test).
+__device__ __forceinline__ float Sel3(const V3 &a, int k) {
+    float r;
+    asm("{\n\t.reg .pred p0, p1;\n\tsetp.eq.s32 p0, %4, 0;\n\tsetp.eq.s32 p1, %4, 1;\n\tselp.f32 %0, %2, %3, p1;\n\t"
+        "selp.f32 %0, %1, %0, p0;\n\t}"
+        : "=f"(r)
+        : "f"(a.x), "f"(a.y), "f"(a.z), "r"(k));
+    return r;
+}
+
 // Woop, Benthin, Wald 2013 — triangle.cpp:23-87.  Products and differences are kept un-fused
 // (__fmul_rn/__fsub_rn) so shared edges evaluate identically from both sides.
 __device__ __forceinline__ bool IntersectTriangleWoop(const Ray &ray, const RayPre &pre, const float4 &p0, const float4 &p1,
@@ -60,10 +72,10 @@ __device__ __forceinline__ bool IntersectTriangleWoop(const Ray &ray, const RayP
     const V3 A = {p0.x - ray.o.x, p0.y - ray.o.y, p0.z - ray.o.z};
     const V3 B = {p1.x - ray.o.x, p1.y - ray.o.y, p1.z - ray.o.z};
     const V3 C = {p2.x - ray.o.x, p2.y - ray.o.y, p2.z - ray.o.z};
-    const float Akz = Comp(A, pre.kz), Bkz = Comp(B, pre.kz), Ckz = Comp(C, pre.kz);
-    const float Ax = __fsub_rn(Comp(A, pre.kx), __fmul_rn(pre.Sx, Akz)), Ay = __fsub_rn(Comp(A, pre.ky), __fmul_rn(pre.Sy, Akz));
-    const float Bx = __fsub_rn(Comp(B, pre.kx), __fmul_rn(pre.Sx, Bkz)), By = __fsub_rn(Comp(B, pre.ky), __fmul_rn(pre.Sy, Bkz));
-    const float Cx = __fsub_rn(Comp(C, pre.kx), __fmul_rn(pre.Sx, Ckz)), Cy = __fsub_rn(Comp(C, pre.ky), __fmul_rn(pre.Sy, Ckz));
+    const float Akz = Sel3(A, pre.kz), Bkz = Sel3(B, pre.kz), Ckz = Sel3(C, pre.kz);
+    const float Ax = __fsub_rn(Sel3(A, pre.kx), __fmul_rn(pre.Sx, Akz)), Ay = __fsub_rn(Sel3(A, pre.ky), __fmul_rn(pre.Sy, Akz));
+    const float Bx = __fsub_rn(Sel3(B, pre.kx), __fmul_rn(pre.Sx, Bkz)), By = __fsub_rn(Sel3(B, pre.ky), __fmul_rn(pre.Sy, Bkz));
+    const float Cx = __fsub_rn(Sel3(C, pre.kx), __fmul_rn(pre.Sx, Ckz)), Cy = __fsub_rn(Sel3(C, pre.ky), __fmul_rn(pre.Sy, Ckz));
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
     float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
     float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
@@ -99,7 +111,9 @@ __device__ __forceinline__ bool IntersectBox(const float *bmin, const float *bma
 
 // Distance-only halves of sphere.cpp:17-44, disk.cpp:17-40, cylinder.cpp:21-60.
 // The hit attributes (normal, uv, frame) are rebuilt in the shading stage from the hit point.
-__device__ __forceinline__ bool IntersectAnalytic(const AnalyticPrim &p, const Ray &ray, float *t_out) {
+// `uv_out` (optional) receives the texcoord the reference hands to Bsdf::IsTransparent (sphere.cpp:39-41, disk.cpp:38-40,
+// cylinder.cpp:46-49).
+__device__ __forceinline__ bool IntersectAnalytic(const AnalyticPrim &p, const Ray &ray, float *t_out, V2 *uv_out = nullptr) {
     const V3 o_l = XformPoint(p.to_local, ray.o), d_l = XformVector(p.to_local, ray.d);
     if (p.type == kSphere) {
         const V3 ro = o_l - mk3(p.center);
@@ -110,6 +124,11 @@ __device__ __forceinline__ bool IntersectAnalytic(const AnalyticPrim &p, const R
         const V3 pos_l = ro + t * d_l, pos = XformPoint(p.to_world, pos_l + mk3(p.center));
         t = Length(pos - ray.o);
         if (t > ray.tmax || t < ray.tmin) return false;
+        if (uv_out != nullptr) {
+            float theta, phi;
+            CartesianToSpherical(pos_l, &theta, &phi, nullptr);
+            *uv_out = {phi * k1Div2Pi, theta * k1DivPi};
+        }
         *t_out = t;
         return true;
     } else if (p.type == kDisk) {
@@ -120,6 +139,11 @@ __device__ __forceinline__ bool IntersectAnalytic(const AnalyticPrim &p, const R
         const V3 pos = XformPoint(p.to_world, pos_l);
         const float t = Length(pos - ray.o);
         if (t > ray.tmax || t < ray.tmin) return false;
+        if (uv_out != nullptr) {
+            float theta, phi, r;
+            CartesianToSpherical(pos_l, &theta, &phi, &r);
+            *uv_out = {r, phi * k1Div2Pi};
+        }
         *t_out = t;
         return true;
     } else {
@@ -135,13 +159,31 @@ __device__ __forceinline__ bool IntersectAnalytic(const AnalyticPrim &p, const R
             t = t_far;
         else
             return false;
-        const V3 pos = XformPoint(p.to_world, o_l + t * d_l);
+        const V3 pos_l = o_l + t * d_l;
+        const V3 pos = XformPoint(p.to_world, pos_l);
         t = Length(pos - ray.o);
         if (t > ray.tmax || t < ray.tmin) return false;
+        if (uv_out != nullptr) *uv_out = {atan2f(pos_l.y, pos_l.x) * k1Div2Pi, pos_l.z / p.length};
         *t_out = t;
         return true;
     }
 }
+
+// Stochastic alpha test of a candidate hit: Bsdf::IsTransparent (bsdf.cpp:272-276) as the reference calls it from inside
+// every primitive test (triangle.cpp:116-118, sphere.cpp:42, disk.cpp:41, cylinder.cpp:50).  A transparent verdict makes
+// the primitive invisible to THIS ray only; the random number comes from the ray's own Philox stream (the reference
+// advances the per-pixel LCG here).
+__device__ __forceinline__ bool OpacityRejects(const DeviceScene &scene, uint32_t inst, V2 uv, Rng &rng) {
+    const uint32_t id_bsdf = scene.instances[inst].id_bsdf;
+    if (id_bsdf == kInvalid) return false;
+    const uint32_t id_opacity = scene.bsdfs[id_bsdf].id_opacity;
+    if (id_opacity == kInvalid) return false;
+    return TexIsTransparent(scene, id_opacity, uv, rng.Next());
+}
+
+// Random-number domains (4th Philox counter word) of the alpha tests inside closest-hit and any-hit traversal; the
+// shading stage uses Rng's default domain.
+constexpr uint32_t kRngDomainClosest = 0x0a1fa001u, kRngDomainShadow = 0x0a1fa002u;
 
 struct TraversalCounters {
     uint32_t nodes = 0, prims = 0;
@@ -153,10 +195,12 @@ constexpr int kTopNodes = 512;     // default number of BVH nodes staged in shar
 constexpr int kTopNodesMax = 2048; // upper bound (128 KB)
 
 // One BVH2 node = 4 x 16 B loads; `top` is the shared-memory copy of nodes [0, num_top).
+// TOP = false compiles the shared-memory path out (plain read-only loads, all of the SM's unified L1 left to the cache).
+template <bool TOP>
 __device__ __forceinline__ void LoadNode(const BvhNode *__restrict__ nodes, const float4 *top, int num_top, int index,
                                          float4 *n0, float4 *n1, float4 *nz, int *c0, int *c1) {
-    const float4 *src = (index < num_top) ? top + index * 4 : reinterpret_cast<const float4 *>(nodes + index);
-    if (index < num_top) {
+    const float4 *src = (TOP && index < num_top) ? top + index * 4 : reinterpret_cast<const float4 *>(nodes + index);
+    if (TOP && index < num_top) {
         *n0 = src[0], *n1 = src[1], *nz = src[2];
         const float4 links = src[3];
         *c0 = __float_as_int(links.x), *c1 = __float_as_int(links.y);
@@ -188,11 +232,13 @@ __device__ __forceinline__ uint32_t AppendCoalesced(uint32_t *counter) {
 // two divergent phases apart.  Incoherent bounce rays ran at 5.6 active lanes per instruction with
 // one-ray-per-thread launches (profiles/r01_extend_baseline.txt); this loop is the fix.
 //
-//   fetch(index, &ray) -> bool   builds ray `index` (false: nothing to trace for this index)
-//   finish(index, hit, found)    consumes the result (closest hit record, or occlusion flag for ANY)
-template <bool ANY, bool STATS, typename Fetch, typename Finish>
+//   fetch(index, &ray, &ctr) -> bool   builds ray `index` (false: nothing to trace for this index); with OPACITY it also
+//                                      returns the (pixel, sample, depth) counter of the ray's random-number stream
+//   finish(index, hit, found)          consumes the result (closest hit record, or occlusion flag for ANY)
+// OPACITY compiles the stochastic alpha test into the primitive tests (scenes whose BSDFs carry opacity textures).
+template <bool ANY, bool STATS, bool OPACITY, bool TOP, typename Fetch, typename Finish>
 __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, const float4 *top, int num_top, uint32_t num_rays,
-                                                   uint32_t *work_counter, int refill_threshold, int min_inner_lanes, Fetch fetch, Finish finish,
+                                                   uint32_t *work_counter, int refill_threshold, int min_inner_lanes, uint2 key, Fetch fetch, Finish finish,
                                                    TraversalCounters *counters, uint32_t *rays_traced) {
     int stack[kStackSize];
     int sp = 0, cur = kSentinel;
@@ -204,6 +250,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
     RayPre pre = Precompute(ray);
     HitRec hit;
     hit.t = 0.0f, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
+    Rng rng(0, 0, 0, key, ANY ? kRngDomainShadow : kRngDomainClosest);
 
     for (;;) {
         // Refill idle lanes in groups: the fetch path (ray load, 1/d, shear constants) is long, so it is run
@@ -214,7 +261,8 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
             index = AppendCoalesced(work_counter);
             if (index >= num_rays) {
                 exhausted = true;
-            } else if (fetch(index, &ray)) {
+            } else if (uint3 ctr = make_uint3(0, 0, 0); fetch(index, &ray, &ctr)) {
+                if (OPACITY) rng = Rng(ctr.x, ctr.y, ctr.z, key, ANY ? kRngDomainShadow : kRngDomainClosest);
                 pre = Precompute(ray);
                 hit.t = ray.tmax, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
                 found = false;
@@ -229,7 +277,9 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                     if (!IntersectBox(p.bmin, p.bmax, ray, pre)) continue;
                     if (STATS) ++counters->prims;
                     float t;
-                    if (IntersectAnalytic(p, ray, &t)) {
+                    V2 uv = {0.0f, 0.0f};
+                    if (IntersectAnalytic(p, ray, &t, OPACITY ? &uv : nullptr)) {
+                        if (OPACITY && OpacityRejects(scene, p.inst, uv, rng)) continue;
                         found = true;
                         if (ANY) {
                             cur = kSentinel;
@@ -248,7 +298,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
             while (static_cast<unsigned>(cur) < static_cast<unsigned>(kSentinel)) {
                 float4 n0, n1, nz;
                 int child0, child1;
-                LoadNode(scene.nodes, top, num_top, cur, &n0, &n1, &nz, &child0, &child1);
+                LoadNode<TOP>(scene.nodes, top, num_top, cur, &n0, &n1, &nz, &child0, &child1);
                 if (STATS) counters->nodes += 2;
                 const float c0lox = fmaf(n0.x, pre.idir.x, -pre.ood.x), c0hix = fmaf(n0.y, pre.idir.x, -pre.ood.x);
                 const float c0loy = fmaf(n0.z, pre.idir.y, -pre.ood.y), c0hiy = fmaf(n0.w, pre.idir.y, -pre.ood.y);
@@ -287,6 +337,12 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                     float t, u, v;
                     bool inside;
                     if (IntersectTriangleWoop(ray, pre, p0, p1, p2, &t, &u, &v, &inside)) {
+                        if (OPACITY) { // triangle.cpp:115-118: texcoord = Lerp(texcoords, u, v, w)
+                            const float *tc = &scene.tri_shade[first + j].uv[0][0];
+                            const float w = 1.0f - u - v;
+                            const V2 uv = {u * __ldg(tc) + v * __ldg(tc + 2) + w * __ldg(tc + 4), u * __ldg(tc + 1) + v * __ldg(tc + 3) + w * __ldg(tc + 5)};
+                            if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng)) continue;
+                        }
                         found = true;
                         if (ANY) {
                             cur = kSentinel;

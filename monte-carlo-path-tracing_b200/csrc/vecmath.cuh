@@ -224,16 +224,17 @@ __device__ __forceinline__ uint4 Philox4x32_10(uint4 ctr, uint2 key) {
 }
 
 struct Rng {
-    uint32_t c0, c1, c2;
+    uint32_t c0, c1, c2, domain;
     uint2 key;
     uint4 buf;
     int idx;
     // (pixel, sample, depth) identify the path vertex; each vertex owns 2^16 blocks of 4 floats.
-    __device__ __forceinline__ Rng(uint32_t pixel, uint32_t sample, uint32_t depth, uint2 k)
-        : c0(pixel), c1(sample), c2(depth << 16), key(k), buf(make_uint4(0, 0, 0, 0)), idx(4) {}
+    // `dom` separates independent consumers of the same vertex (shading / alpha tests of the closest-hit ray / of the shadow ray).
+    __device__ __forceinline__ Rng(uint32_t pixel, uint32_t sample, uint32_t depth, uint2 k, uint32_t dom = 0x5eedu)
+        : c0(pixel), c1(sample), c2(depth << 16), domain(dom), key(k), buf(make_uint4(0, 0, 0, 0)), idx(4) {}
     __device__ __forceinline__ float Next() {
         if (idx == 4) {
-            buf = Philox4x32_10(make_uint4(c0, c1, c2, 0x5eedu), key);
+            buf = Philox4x32_10(make_uint4(c0, c1, c2, domain), key);
             ++c2;
             idx = 0;
         }

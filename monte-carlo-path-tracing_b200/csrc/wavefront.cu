@@ -84,22 +84,23 @@ __device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounter
 // ---------------------------------------------------------------------------------------------
 // k_primary: camera-ray generation (renderer.cpp:62-75) fused with the first closest hit.
 // ---------------------------------------------------------------------------------------------
-template <bool STATS>
+template <bool STATS, bool OPACITY, bool TOP>
 __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ DeviceScene scene,
                                                       const __grid_constant__ BatchParams bp, PathQueue q,
                                                       float *radiance, uint32_t capacity, Counters *counters, int max_top,
                                                       int refill, int min_inner) {
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
-    const int num_top = StageTopNodes(scene, top, &bar, max_top);
+    const int num_top = TOP ? StageTopNodes(scene, top, &bar, max_top) : 0;
     const uint32_t nslots = bp.pixel_count * bp.sample_count;
     TraversalCounters tc;
     uint32_t rays = 0;
     Ray cam; // the camera ray of the slot this lane currently traces (the traversal shortens its own copy)
-    auto fetch = [&](uint32_t slot, Ray *ray) {
+    auto fetch = [&](uint32_t slot, Ray *ray, uint3 *ctr) {
         uint32_t px, py;
         if (!LocalPixelToImage(bp, bp.pixel_begin + slot / bp.sample_count, &px, &py)) return false;
         const uint32_t s = bp.sample_begin + slot % bp.sample_count;
+        if (OPACITY) *ctr = make_uint3(py * bp.width + px, s, 0u);
         const float u = s * bp.spp_inv, v = VanDerCorput2(s + 1);
         const float x = 2.0f * (px + u) / static_cast<int>(bp.width) - 1.0f, y = 1.0f - 2.0f * (py + v) / static_cast<int>(bp.height);
         ray->o = mk3(bp.camera.eye);
@@ -133,53 +134,65 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ De
         }
         q.hit[idx] = hit;
     };
-    TraversePersistent<false, STATS>(scene, top, num_top, nslots, &counters->work_primary, refill, min_inner, fetch, finish, &tc, &rays);
+    TraversePersistent<false, STATS, OPACITY, TOP>(scene, top, num_top, nslots, &counters->work_primary, refill, min_inner, bp.key, fetch, finish, &tc, &rays);
     FlushCounters(STATS, tc, rays, kClassPrimary, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_extend: closest hit for a compacted queue (TLAS::Intersect, tlas.cpp:13-43).
 // ---------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ DeviceScene scene, PathQueue q, int which,
+// Random-number counter (pixel, sample, depth) of the alpha tests along the ray of sample slot `slot`.
+__device__ __forceinline__ uint3 SlotCounter(const BatchParams &bp, uint32_t slot, uint32_t depth) {
+    uint32_t px = 0, py = 0;
+    LocalPixelToImage(bp, bp.pixel_begin + slot / bp.sample_count, &px, &py);
+    return make_uint3(py * bp.width + px, bp.sample_begin + slot % bp.sample_count, depth);
+}
+
+template <bool STATS, bool OPACITY, bool TOP>
+__global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ DeviceScene scene,
+                                                     const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue q, int which,
                                                      Counters *counters, int max_top, int refill, int min_inner) {
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
     const uint32_t n = counters->queue[which];
     if (blockIdx.x * blockDim.x >= n) return;
-    const int num_top = StageTopNodes(scene, top, &bar, max_top);
+    const int num_top = TOP ? StageTopNodes(scene, top, &bar, max_top) : 0;
     TraversalCounters tc;
     uint32_t rays = 0;
-    auto fetch = [&](uint32_t i, Ray *ray) {
+    auto fetch = [&](uint32_t i, Ray *ray, uint3 *ctr) {
         ray->o = mk3(q.ox[i], q.oy[i], q.oz[i]);
         ray->d = mk3(q.dx[i], q.dy[i], q.dz[i]);
         ray->tmin = kEpsilonDistance;
         ray->tmax = kMaxFloat;
+        if (OPACITY) *ctr = SlotCounter(bp, q.slot[i], depth);
         return true;
     };
     auto finish = [&](uint32_t i, const HitRec &hit, bool) { q.hit[i] = hit; };
-    TraversePersistent<false, STATS>(scene, top, num_top, n, &counters->work_extend, refill, min_inner, fetch, finish, &tc, &rays);
+    TraversePersistent<false, STATS, OPACITY, TOP>(scene, top, num_top, n, &counters->work_extend, refill, min_inner, bp.key, fetch, finish, &tc, &rays);
     FlushCounters(STATS, tc, rays, kClassExtend, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_shadow: occlusion test of the NEE rays (TLAS::IntersectAny, tlas.cpp:44-76).
 // ---------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ DeviceScene scene, ShadowQueue sq, float *radiance,
+template <bool STATS, bool OPACITY, bool TOP>
+__global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ DeviceScene scene,
+                                                    const __grid_constant__ BatchParams bp, uint32_t depth, ShadowQueue sq, float *radiance,
                                                     uint32_t capacity, Counters *counters, int max_top, int refill, int min_inner) {
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
     const uint32_t n = counters->shadow;
     if (blockIdx.x * blockDim.x >= n) return;
-    const int num_top = StageTopNodes(scene, top, &bar, max_top);
+    const int num_top = TOP ? StageTopNodes(scene, top, &bar, max_top) : 0;
     TraversalCounters tc;
     uint32_t rays = 0;
-    auto fetch = [&](uint32_t i, Ray *ray) {
+    auto fetch = [&](uint32_t i, Ray *ray, uint3 *ctr) {
         ray->o = mk3(sq.ox[i], sq.oy[i], sq.oz[i]);
         ray->d = mk3(sq.dx[i], sq.dy[i], sq.dz[i]);
         ray->tmin = kEpsilonDistance;
         ray->tmax = sq.tmax[i];
+        // several NEE rays of one vertex (one per emitter) share (pixel, sample, depth): the queue index separates them
+        if (OPACITY) *ctr = SlotCounter(bp, sq.slot[i], depth), ctr->y ^= i * 0x9e3779b9u;
         return true;
     };
     auto finish = [&](uint32_t i, const HitRec &, bool occluded) {
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ Dev
         atomicAdd(radiance + capacity + slot, sq.cg[i]);
         atomicAdd(radiance + 2 * capacity + slot, sq.cb[i]);
     };
-    TraversePersistent<true, STATS>(scene, top, num_top, n, &counters->work_shadow, refill, min_inner, fetch, finish, &tc, &rays);
+    TraversePersistent<true, STATS, OPACITY, TOP>(scene, top, num_top, n, &counters->work_shadow, refill, min_inner, bp.key, fetch, finish, &tc, &rays);
     FlushCounters(STATS, tc, rays, kClassShadow, counters);
 }
 
@@ -580,47 +593,48 @@ __global__ void k_assemble(uint32_t width, uint32_t height, uint32_t tile_world,
 
 size_t TopSmemBytes(const LaunchConfig &lc) { return static_cast<size_t>(std::max(lc.top_nodes, 1)) * sizeof(BvhNode); }
 
+// Dynamic shared memory above 48 KB needs an opt-in per kernel function (only reached with B200PT_TOP_NODES > 768).
 template <typename K>
-void EnableSmem(K kernel) {
-    static bool done = false; // one static per kernel instantiation
-    if (!done) {
+void EnableSmem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTopNodesMax * sizeof(BvhNode)));
-        done = true;
-    }
 }
 
 } // namespace
 
+// Picks the <STATS, OPACITY, TOP> instantiation of a traversal kernel and launches it on the persistent grid.
+// lc.top_nodes == 0 selects the variants without the shared-memory copy of the top of the tree.
+#define B200PT_LAUNCH_TRAVERSAL(kernel, ...)                                                                          \
+    do {                                                                                                              \
+        const bool opacity = scene.integrator.has_opacity != 0, top = lc.top_nodes > 0;                               \
+        const size_t smem = top ? TopSmemBytes(lc) : 0;                                                               \
+        auto go = [&](auto k) {                                                                                       \
+            EnableSmem(k, smem);                                                                                      \
+            k<<<lc.blocks, kThreads, smem, lc.stream>>>(__VA_ARGS__, lc.top_nodes, lc.refill, lc.min_inner);          \
+        };                                                                                                            \
+        auto pick_top = [&](auto with_top, auto without_top) {                                                        \
+            if (top) go(with_top);                                                                                    \
+            else go(without_top);                                                                                     \
+        };                                                                                                            \
+        if (lc.stats && opacity) pick_top(kernel<true, true, true>, kernel<true, true, false>);                       \
+        else if (lc.stats) pick_top(kernel<true, false, true>, kernel<true, false, false>);                           \
+        else if (opacity) pick_top(kernel<false, true, true>, kernel<false, true, false>);                            \
+        else pick_top(kernel<false, false, true>, kernel<false, false, false>);                                       \
+    } while (0)
+
 void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, float *radiance,
                    uint32_t capacity, Counters *counters) {
-    if (lc.stats) {
-        EnableSmem(k_primary<true>);
-        k_primary<true><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, bp, q, radiance, capacity, counters, lc.top_nodes, lc.refill, lc.min_inner);
-    } else {
-        EnableSmem(k_primary<false>);
-        k_primary<false><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, bp, q, radiance, capacity, counters, lc.top_nodes, lc.refill, lc.min_inner);
-    }
+    B200PT_LAUNCH_TRAVERSAL(k_primary, scene, bp, q, radiance, capacity, counters);
 }
 
-void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, PathQueue q, int which, Counters *counters) {
-    if (lc.stats) {
-        EnableSmem(k_extend<true>);
-        k_extend<true><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, q, which, counters, lc.top_nodes, lc.refill, lc.min_inner);
-    } else {
-        EnableSmem(k_extend<false>);
-        k_extend<false><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, q, which, counters, lc.top_nodes, lc.refill, lc.min_inner);
-    }
-}
-
-void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, ShadowQueue sq, float *radiance, uint32_t capacity,
+void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
                   Counters *counters) {
-    if (lc.stats) {
-        EnableSmem(k_shadow<true>);
-        k_shadow<true><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, sq, radiance, capacity, counters, lc.top_nodes, lc.refill, lc.min_inner);
-    } else {
-        EnableSmem(k_shadow<false>);
-        k_shadow<false><<<lc.blocks, kThreads, TopSmemBytes(lc), lc.stream>>>(scene, sq, radiance, capacity, counters, lc.top_nodes, lc.refill, lc.min_inner);
-    }
+    B200PT_LAUNCH_TRAVERSAL(k_extend, scene, bp, depth, q, which, counters);
+}
+
+void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, ShadowQueue sq,
+                  float *radiance, uint32_t capacity, Counters *counters) {
+    B200PT_LAUNCH_TRAVERSAL(k_shadow, scene, bp, depth, sq, radiance, capacity, counters);
 }
 
 void LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,

@@ -92,11 +92,13 @@ struct LaunchConfig {
 // kernel launchers (wavefront.cu)
 void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, float *radiance,
                    uint32_t capacity, Counters *counters);
-void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, PathQueue q, int which, Counters *counters);
+// `depth` = index of the path vertex the rays leave from: with `bp` it keys the alpha-test random numbers (opacity masks).
+void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
+                  Counters *counters);
 void LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
                  int which_in, PathQueue qout, ShadowQueue sq, float *radiance, Counters *counters, uint32_t capacity);
-void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, ShadowQueue sq, float *radiance, uint32_t capacity,
-                  Counters *counters);
+void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, ShadowQueue sq,
+                  float *radiance, uint32_t capacity, Counters *counters);
 void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow);
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum);
 void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,

@@ -3,7 +3,7 @@
 
 Run once in a container that has /root/reference (after `python -c "import __graft_entry__ as g; g.build()"`):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--synthetic NAME ...]     (--synthetic: only (re)make the named synthetic scenes)
 
 Outputs (all produced by reference code, none by the oracle restatement or the CUDA path):
   kats.json                      known answers of reference leaf functions (Tea<4>, LCG, VdC, MisWeight, cos-hemisphere, LBVH)
@@ -36,6 +36,13 @@ CONVERGED = {  # scene -> (w, h, spp)
 def main():
     woop, mt = refcheck.ref_lib("woop"), refcheck.ref_lib("mt")
     L = woop.lib
+    only_synthetic = sys.argv[2:] if len(sys.argv) > 2 and sys.argv[1] == "--synthetic" else None
+    if only_synthetic is None:
+        make_reference_scene_goldens(woop, mt, L)
+    make_synthetic_goldens(woop, mt, only_synthetic)
+
+
+def make_reference_scene_goldens(woop, mt, L):
     kats = {"tea4": [[a, b, int(L.ref_tea4(a, b))] for a, b in ((0, 0), (3, 0), (3145725, 0), (12, 7), (4294967295, 1))]}
     seed = ctypes.c_uint32(L.ref_tea4(0, 0))
     kats["lcg_from_tea4_0_0"] = [[float(L.ref_random_float(ctypes.byref(seed))), int(seed.value)] for _ in range(8)]
@@ -86,14 +93,20 @@ def main():
         frame, _, seconds = woop.render_pack(pack, w, h, spp)
         np.save(os.path.join(HERE, f"converged_{name}.npy"), frame.astype(np.float32))
         print("converged", name, frame.mean(), f"{seconds:.1f}s")
-    # ---- synthetic scenes (tests/scene_builder.py): the branches the BASELINE scenes never reach ----
+
+
+def make_synthetic_goldens(woop, mt, only):
+    """Synthetic scenes (tests/scene_builder.py): the branches the BASELINE scenes never reach."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, ROOT)
     import scene_builder
     import __graft_entry__ as ge
     pkg = ge.load_package()
-    synthetic = {}
+    settings_path = os.path.join(HERE, "settings.json")
+    synthetic = json.load(open(settings_path)).get("synthetic", {}) if only is not None else {}
     for name, builder in scene_builder.synthetic_scenes().items():
+        if only is not None and name not in only:
+            continue
         desc = builder.desc()
         pack = os.path.join(HERE, f"synthetic_{name}.b200scene")
         assert pkg.lib().b200pt_scene_save(ctypes.byref(desc), pack.encode()) == 0
@@ -104,7 +117,7 @@ def main():
         np.save(os.path.join(HERE, f"converged_synthetic_{name}.npy"), frame.astype(np.float32))
         synthetic[name] = {"exact": [32, 32, 4], "converged": [64, 64, 512]}
         print("synthetic", name, frame.mean(), f"{seconds:.1f}s")
-    with open(os.path.join(HERE, "settings.json"), "w") as f:
+    with open(settings_path, "w") as f:
         json.dump({"exact": EXACT, "converged": CONVERGED, "synthetic": synthetic}, f, indent=1)
 
 

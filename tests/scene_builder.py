@@ -144,8 +144,8 @@ class SceneBuilder:
         self.bsdfs.append(b)
         return b, len(self.bsdfs) - 1
 
-    def diffuse(self, reflectance_tex, twosided=True, bump=INVALID):
-        b, i = self._bsdf(BSDF_DIFFUSE, twosided, bump)
+    def diffuse(self, reflectance_tex, twosided=True, bump=INVALID, opacity=INVALID):
+        b, i = self._bsdf(BSDF_DIFFUSE, twosided, bump, opacity)
         b.id_diffuse_reflectance = reflectance_tex
         return i
 
@@ -393,4 +393,21 @@ def synthetic_scenes():
     b.cube(INVALID, translate(0, 1.0, 0.3) @ scale(1.2, 0.9, 0.9), medium_int=fog)  # a BSDF-less box filled with an isotropic medium
     b.sphere(b.diffuse(b.constant(0.8, 0.8, 0.2)), (0.0, 0.8, 0.3), 0.4, medium_ext=fog)
     scenes["isotropic_medium_null_surface"] = b
+
+    # Opacity masks: Bsdf::IsTransparent inside every primitive test (triangle.cpp:116, sphere.cpp:42, disk.cpp:41,
+    # cylinder.cpp:50) with constant (constant_texture.cpp:18) and 4-channel bitmap (bitmap.cpp:70) alpha.
+    b = SceneBuilder(depth_max=6)
+    stage(b)
+    rgba = np.zeros((8, 8, 4), dtype=np.float32)
+    rgba[..., :3] = 0.5
+    rgba[..., 3] = (np.add.outer(np.arange(8), np.arange(8)) % 2) * 0.8 + 0.1   # alpha 0.1 / 0.9 checker
+    mask = b.bitmap(rgba)
+    pos, idx, nrm, uv = uv_sphere()
+    b.mesh(b.diffuse(b.constant(0.8, 0.3, 0.2), opacity=mask), pos, idx, nrm, uv, to_world=translate(-1.2, 0.8, 0.4) @ scale(0.8, 0.8, 0.8))
+    b.rectangle(b.diffuse(b.constant(0.2, 0.3, 0.8), opacity=b.constant(0.4)), translate(0.2, 1.0, 1.4) @ rotate_y(-15) @ scale(0.7, 0.8, 1))
+    b.sphere(b.diffuse(b.constant(0.3, 0.7, 0.3), opacity=b.constant(0.6)), (1.3, 0.6, 0.2), 0.6)
+    b.disk(b.diffuse(b.constant(0.7, 0.7, 0.2), opacity=mask), translate(0.0, 0.05, 2.2) @ rotate_x(-90) @ scale(1.6, 1.6, 1))
+    b.cylinder(b.diffuse(b.constant(0.6, 0.3, 0.6), opacity=b.constant(0.5)), (0.3, 0.0, -0.8), (0.3, 1.8, -0.8), 0.35)
+    b.point((2.0, 3.0, 3.0), (25, 25, 25))
+    scenes["opacity_masks"] = b
     return scenes
