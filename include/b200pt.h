@@ -202,8 +202,13 @@ typedef struct b200pt_render_opts {
     uint32_t tile_rank;         /* this process renders tiles t with t % tile_world == tile_rank */
     uint32_t tile_world;        /* 0 or 1 = whole frame */
     uint32_t collect_stats;     /* B200PT_STATS_* bit mask */
-    uint32_t reserved;
+    uint32_t flags;             /* B200PT_RENDER_* bit mask */
 } b200pt_render_opts;
+
+/* Trace a camera ray for every sample even in screen tiles that provably see no geometry.  By default such tiles are
+ * dropped by a conservative visibility pre-pass (only in scenes without environment / sun emitters, where an escaped
+ * camera ray carries no radiance); the frame is bit-identical either way. */
+#define B200PT_RENDER_NO_TILE_CULL 1u
 
 /* Per kernel class of the wavefront pipeline. */
 typedef struct b200pt_kernel_stats {
@@ -223,9 +228,11 @@ typedef struct b200pt_stats {
     uint64_t samples;            /* width*height*spp rendered by this rank */
     uint64_t kernel_launches;    /* kernels launched by the last render */
     uint64_t num_bvh_nodes, num_triangles, num_prims;
+    uint64_t local_tiles, active_tiles; /* 8x8 tiles owned by this rank / those that passed the visibility pre-pass */
     b200pt_kernel_stats primary; /* k_primary: ray-gen + closest hit of camera rays */
-    b200pt_kernel_stats extend;  /* k_extend : closest hit of bounce rays */
-    b200pt_kernel_stats shadow;  /* k_shadow : any-hit of NEE rays */
+    b200pt_kernel_stats extend;  /* k_trace  : closest hit of bounce rays + any-hit of NEE rays in ONE launch per bounce;
+                                    ms / launches cover the whole launch, the counters only the bounce rays */
+    b200pt_kernel_stats shadow;  /* counters of the NEE rays traced inside k_trace (ms = 0, launches = 0) */
     b200pt_kernel_stats shade;   /* k_shade  : shading, NEE generation, sampling, compaction */
     b200pt_kernel_stats other;   /* resets, resolve, finalize */
 } b200pt_stats;

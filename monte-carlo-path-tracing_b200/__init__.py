@@ -30,7 +30,7 @@ class MyException(RuntimeError):
 class RenderOpts(ctypes.Structure):
     _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("spp", ctypes.c_uint32),
                 ("seed", ctypes.c_uint64), ("tile_rank", ctypes.c_uint32), ("tile_world", ctypes.c_uint32),
-                ("collect_stats", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("collect_stats", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
 
 
 class CreateOpts(ctypes.Structure):
@@ -48,12 +48,14 @@ class KernelStats(ctypes.Structure):
 
 STATS_COUNTERS = 1  # B200PT_STATS_COUNTERS
 STATS_TIMING = 2    # B200PT_STATS_TIMING
+RENDER_NO_TILE_CULL = 1  # B200PT_RENDER_NO_TILE_CULL
 
 
 class Stats(ctypes.Structure):
     _fields_ = [("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double), ("bvh_build_ms", ctypes.c_double),
                 ("samples", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
                 ("num_bvh_nodes", ctypes.c_uint64), ("num_triangles", ctypes.c_uint64), ("num_prims", ctypes.c_uint64),
+                ("local_tiles", ctypes.c_uint64), ("active_tiles", ctypes.c_uint64),
                 ("primary", KernelStats), ("extend", KernelStats), ("shadow", KernelStats), ("shade", KernelStats),
                 ("other", KernelStats)]
 
@@ -151,27 +153,27 @@ class Renderer:
         opts = CreateOpts(device, max_leaf_size, max_paths_in_flight)
         _check(lib().b200pt_create(scene.desc, ctypes.byref(opts), ctypes.byref(self._h)))
 
-    def _opts(self, width, height, spp, seed, tile_rank=0, tile_world=1, stats=0):
-        return RenderOpts(width or 0, height or 0, spp or 0, seed, tile_rank, tile_world, int(stats), 0)
+    def _opts(self, width, height, spp, seed, tile_rank=0, tile_world=1, stats=0, flags=0):
+        return RenderOpts(width or 0, height or 0, spp or 0, seed, tile_rank, tile_world, int(stats), int(flags))
 
-    def Draw(self, frame=None, width=0, height=0, spp=0, seed=0, stats=0):
+    def Draw(self, frame=None, width=0, height=0, spp=0, seed=0, stats=0, flags=0):
         """Host-buffer render (the reference's Draw(float*)): H2D/D2H copies happen inside the call."""
         w, h = width or self.scene.width, height or self.scene.height
         if frame is None:
             frame = np.zeros((h, w, 3), dtype=np.float32)
         if frame.dtype != np.float32 or frame.size != w * h * 3 or not frame.flags["C_CONTIGUOUS"]:
             raise MyException("frame must be a C-contiguous float32 array of width*height*3 elements.")
-        opts = self._opts(width, height, spp, seed, stats=stats)
+        opts = self._opts(width, height, spp, seed, stats=stats, flags=flags)
         _check(lib().b200pt_render(self._h, ctypes.byref(opts), frame.ctypes.data), self._h)
         return frame
 
-    def draw_device(self, frame_tensor, width=0, height=0, spp=0, seed=0, stream=None, stats=0):
+    def draw_device(self, frame_tensor, width=0, height=0, spp=0, seed=0, stream=None, stats=0, flags=0):
         """Frame stays in HBM: `frame_tensor` is a CUDA float32 tensor with width*height*3 elements."""
-        opts = self._opts(width, height, spp, seed, stats=stats)
+        opts = self._opts(width, height, spp, seed, stats=stats, flags=flags)
         _check(lib().b200pt_render_device(self._h, ctypes.byref(opts), frame_tensor.data_ptr(), stream), self._h)
 
-    def draw_tiles_device(self, tiles_tensor, tile_rank, tile_world, width=0, height=0, spp=0, seed=0, stream=None, stats=0):
-        opts = self._opts(width, height, spp, seed, tile_rank, tile_world, stats)
+    def draw_tiles_device(self, tiles_tensor, tile_rank, tile_world, width=0, height=0, spp=0, seed=0, stream=None, stats=0, flags=0):
+        opts = self._opts(width, height, spp, seed, tile_rank, tile_world, stats, flags)
         _check(lib().b200pt_render_tiles_device(self._h, ctypes.byref(opts), tiles_tensor.data_ptr(), stream), self._h)
 
     def assemble_tiles_device(self, gathered_tensor, frame_tensor, width, height, tile_world, stream=None):

@@ -145,6 +145,9 @@ struct DeviceScene {
     const float *light_tri_cdf;  // per area-light mesh: inclusive prefix sums of triangle areas / total
     const uint32_t *light_tri_ids;
     float scene_bmin[3], scene_bmax[3];
+    // A cut through the top of the BVH (plus the boxes of the analytic primitives): min.xyz max.xyz per box, together
+    // they cover all geometry.  Screen tiles whose pyramid of camera rays misses every box trace nothing (k_cull_tiles).
+    const float *cull_boxes;     uint32_t num_cull_boxes;
     DIntegrator integrator;
 };
 

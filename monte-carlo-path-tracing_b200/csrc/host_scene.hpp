@@ -28,6 +28,7 @@ struct HostScene {
     std::vector<float> light_tri_cdf;
     std::vector<uint32_t> light_tri_ids;
     float scene_bmin[3], scene_bmax[3];
+    std::vector<float> cull_boxes;   // 6 floats per box (DeviceScene::cull_boxes)
     DIntegrator integrator{};
     b200pt_camera camera{};
     double bvh_build_ms = 0.0;

@@ -74,6 +74,9 @@ struct b200pt_context {
     DeviceArray<DEmitter> emitters;
     DeviceArray<float> envmap_tables, kc_brdf, kc_albedo, cdf_area_light, light_tri_cdf;
     DeviceArray<uint32_t> map_area_light_instance, light_tri_ids;
+    DeviceArray<float> cull_boxes;
+    DeviceArray<uint32_t> tile_flags, tile_list; // visibility pre-pass: per local tile flag; ascending active list + count
+    bool tile_cull = true;        // B200PT_TILE_CULL=0 turns the pre-pass off
 
     // wavefront state
     uint64_t capacity = 0;        // sample slots per batch currently allocated
@@ -157,6 +160,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     CU_CHECK(c, c->map_area_light_instance.Upload(h.map_area_light_instance));
     CU_CHECK(c, c->light_tri_cdf.Upload(h.light_tri_cdf));
     CU_CHECK(c, c->light_tri_ids.Upload(h.light_tri_ids));
+    CU_CHECK(c, c->cull_boxes.Upload(h.cull_boxes));
     CU_CHECK(c, c->pixels.Alloc(desc.num_pixels));
     if (desc.num_pixels)
         CU_CHECK(c, cudaMemcpy(c->pixels.ptr, desc.pixels, desc.num_pixels * sizeof(float), cudaMemcpyHostToDevice));
@@ -178,6 +182,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     s.map_area_light_instance = c->map_area_light_instance.ptr;
     s.light_tri_cdf = c->light_tri_cdf.ptr, s.light_tri_ids = c->light_tri_ids.ptr;
     memcpy(s.scene_bmin, h.scene_bmin, 12), memcpy(s.scene_bmax, h.scene_bmax, 12);
+    s.cull_boxes = c->cull_boxes.ptr, s.num_cull_boxes = static_cast<uint32_t>(h.cull_boxes.size() / 6);
     s.integrator = h.integrator;
 
     c->stats.num_bvh_nodes = h.nodes.size();
@@ -240,7 +245,7 @@ int AllocWavefront(b200pt_context *c, uint64_t wanted) {
 struct ResolvedOpts {
     uint32_t width, height, spp, tile_rank, tile_world;
     uint64_t seed;
-    bool counters, timing;
+    bool counters, timing, tile_cull;
 };
 
 int ResolveOpts(b200pt_context *c, const b200pt_render_opts *o, ResolvedOpts *r) {
@@ -253,6 +258,7 @@ int ResolveOpts(b200pt_context *c, const b200pt_render_opts *o, ResolvedOpts *r)
     r->tile_rank = o ? o->tile_rank : 0;
     r->counters = o && (o->collect_stats & B200PT_STATS_COUNTERS);
     r->timing = o && (o->collect_stats & B200PT_STATS_TIMING);
+    r->tile_cull = !(o && (o->flags & B200PT_RENDER_NO_TILE_CULL));
     if (r->width == 0 || r->height == 0 || r->spp == 0) return c->Fail(B200PT_EINVAL, "width, height and spp must be positive.");
     if (r->tile_rank >= r->tile_world) return c->Fail(B200PT_EINVAL, "tile_rank must be < tile_world.");
     if (static_cast<uint64_t>(r->width) * r->height > (1ull << 30)) return c->Fail(B200PT_EINVAL, "frame too large.");
@@ -279,17 +285,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     const uint32_t local_pixels = PixelsPerRank(ro.width, ro.height, ro.tile_world);
 
     if (c->accum.count < 3ull * local_pixels) CU_CHECK(c, c->accum.Alloc(3ull * local_pixels));
-    // Wavefront state is sized for the job at hand (grown on demand, never shrunk): all of it in one batch if it fits.
-    {
-        const uint64_t wanted = std::min<uint64_t>(c->max_capacity, std::max<uint64_t>(static_cast<uint64_t>(local_pixels) * ro.spp, 1024));
-        if (c->capacity < wanted) {
-            CU_CHECK(c, cudaDeviceSynchronize());
-            const int rc = AllocWavefront(c, wanted);
-            if (rc != B200PT_OK) return rc;
-        }
-    }
     LaunchConfig lc;
-    lc.blocks = c->num_sms * 4;
     lc.threads = 256;
     lc.stream = stream;
     lc.stats = ro.counters;
@@ -302,6 +298,39 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     c->timed.clear();
     c->events_used = 0;
     for (uint64_t &n : c->class_launches) n = 0;
+    CU_CHECK(c, cudaEventRecord(c->ev_begin, stream));
+
+    // Visibility pre-pass: which of this rank's tiles can see geometry at all.  Escaped camera rays only carry radiance
+    // when an environment map or a sun disc exists (path.cpp:24-35), so without those the other tiles are exactly black
+    // and none of their samples needs a ray.  The job's pixel list shrinks to the active tiles (part of the timed render).
+    const uint32_t local_tiles = local_pixels / kTilePixels;
+    uint32_t job_pixels = local_pixels;
+    const DIntegrator &ig = c->scene.integrator;
+    if (ro.tile_cull && c->tile_cull && ig.id_envmap == kInvalid && ig.id_sun == kInvalid) {
+        if (c->tile_flags.count < local_tiles) {
+            CU_CHECK(c, c->tile_flags.Alloc(local_tiles));
+            CU_CHECK(c, c->tile_list.Alloc(local_tiles + 1ull));
+        }
+        launches += 2;
+        c->class_launches[kClassOther] += 2;
+        LaunchCullTiles(lc, c->scene, bp, local_tiles, c->tile_flags.ptr, c->tile_list.ptr);
+        CU_CHECK(c, cudaMemcpyAsync(c->pinned_count, c->tile_list.ptr + local_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CU_CHECK(c, cudaStreamSynchronize(stream));
+        job_pixels = *c->pinned_count * kTilePixels;
+        bp.active_tiles = c->tile_list.ptr;
+    }
+    c->stats.active_tiles = job_pixels / kTilePixels;
+    c->stats.local_tiles = local_tiles;
+
+    // Wavefront state is sized for the job at hand (grown on demand, never shrunk): all of it in one batch if it fits.
+    {
+        const uint64_t wanted = std::min<uint64_t>(c->max_capacity, std::max<uint64_t>(static_cast<uint64_t>(job_pixels) * ro.spp, 1024));
+        if (c->capacity < wanted) {
+            CU_CHECK(c, cudaDeviceSynchronize());
+            const int rc = AllocWavefront(c, wanted);
+            if (rc != B200PT_OK) return rc;
+        }
+    }
     // Runs one kernel launch, counted (and, with B200PT_STATS_TIMING, bracketed by events) under its class.
     auto launch = [&](int cls, auto &&fn) {
         ++launches;
@@ -316,19 +345,17 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
             fn();
         }
     };
-    CU_CHECK(c, cudaEventRecord(c->ev_begin, stream));
     CU_CHECK(c, cudaMemsetAsync(c->accum.ptr, 0, 3ull * local_pixels * sizeof(float), stream));
     CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, sizeof(Counters), stream));
 
-    const DIntegrator &ig = c->scene.integrator;
     const uint32_t capacity = static_cast<uint32_t>(c->capacity);
-    const uint32_t pixels_per_chunk = std::min<uint32_t>(local_pixels, capacity);
+    const uint32_t pixels_per_chunk = std::max<uint32_t>(1, std::min<uint32_t>(job_pixels, capacity));
     const uint32_t samples_per_batch = std::max<uint32_t>(1, std::min<uint32_t>(ro.spp, capacity / pixels_per_chunk));
     const uint32_t max_rounds = std::min<uint32_t>(ig.depth_max, kMaxRounds);
 
-    for (uint32_t pixel_begin = 0; pixel_begin < local_pixels; pixel_begin += pixels_per_chunk) {
+    for (uint32_t pixel_begin = 0; pixel_begin < job_pixels; pixel_begin += pixels_per_chunk) {
         bp.pixel_begin = pixel_begin;
-        bp.pixel_count = std::min(pixels_per_chunk, local_pixels - pixel_begin);
+        bp.pixel_count = std::min(pixels_per_chunk, job_pixels - pixel_begin);
         for (uint32_t sample_begin = 0; sample_begin < ro.spp; sample_begin += samples_per_batch) {
             bp.sample_begin = sample_begin;
             bp.sample_count = std::min(samples_per_batch, ro.spp - sample_begin);
@@ -344,17 +371,25 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
                     LaunchShade(lc, c->scene, bp, depth, c->queue[which], which, c->queue[which ^ 1], c->shadow, c->radiance,
                                 c->counters.ptr, capacity);
                 });
-                if (c->shadow_per_vertex > 0)
-                    launch(kClassShadow, [&] { LaunchShadow(lc, c->scene, bp, depth, c->shadow, c->radiance, capacity, c->counters.ptr); });
                 which ^= 1;
-                if (depth == max_rounds) break;
-                if (depth >= 8 && (depth & 3) == 0) { // poll the survivor count
+                // One traversal launch per bounce: closest hits of the survivors (queue `which`) + occlusion of the NEE rays.
+                auto trace = [&](int extend_queue) {
+                    launch(kClassExtend, [&] {
+                        LaunchTrace(lc, c->scene, bp, depth, c->queue[which], extend_queue, c->shadow, c->radiance, capacity, c->counters.ptr);
+                    });
+                };
+                bool survivors = depth < max_rounds;
+                if (survivors && depth >= 8 && (depth & 3) == 0) { // poll the survivor count
                     CU_CHECK(c, cudaMemcpyAsync(c->pinned_count, &c->counters.ptr->queue[which], sizeof(uint32_t),
                                                 cudaMemcpyDeviceToHost, stream));
                     CU_CHECK(c, cudaStreamSynchronize(stream));
-                    if (*c->pinned_count == 0) break;
+                    survivors = *c->pinned_count != 0;
                 }
-                launch(kClassExtend, [&] { LaunchExtend(lc, c->scene, bp, depth, c->queue[which], which, c->counters.ptr); });
+                if (!survivors) {
+                    if (c->shadow_per_vertex > 0) trace(-1); // only the NEE rays of the last vertex are left
+                    break;
+                }
+                trace(which);
             }
             launch(kClassOther, [&] { LaunchResolve(lc, bp, c->radiance, capacity, c->accum.ptr); });
         }
@@ -402,6 +437,7 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     c->refill = env_int("B200PT_REFILL", c->refill, 1, 32);
     c->min_inner = env_int("B200PT_MIN_INNER", c->min_inner, 1, 32);
     c->ctas_per_sm = env_int("B200PT_CTAS_PER_SM", c->ctas_per_sm, 1, 16);
+    c->tile_cull = env_int("B200PT_TILE_CULL", 1, 0, 1) != 0;
 
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();

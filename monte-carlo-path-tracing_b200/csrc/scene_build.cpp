@@ -939,6 +939,46 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, HostScen
     memcpy(hs->scene_bmin, &scene_box.lo, 12);
     memcpy(hs->scene_bmax, &scene_box.hi, 12);
 
+    // ---- cover of the geometry by a few boxes, for the screen-tile visibility pre-pass (wavefront.cu: k_cull_tiles):
+    // best-first cut through the BVH (always open the box with the largest surface area) + the analytic primitives.
+    {
+        constexpr size_t kMaxCullBoxes = 384;
+        struct CutBox {
+            float lo[3], hi[3];
+            int32_t link;
+            float Area() const {
+                const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+                return dx * dy + dy * dz + dz * dx;
+            }
+        };
+        auto children = [&](int32_t node, CutBox *a, CutBox *b) {
+            const BvhNode &n = hs->nodes[node];
+            *a = {{n.c0xy.x, n.c0xy.z, n.cz.x}, {n.c0xy.y, n.c0xy.w, n.cz.y}, n.child0};
+            *b = {{n.c1xy.x, n.c1xy.z, n.cz.z}, {n.c1xy.y, n.c1xy.w, n.cz.w}, n.child1};
+        };
+        std::vector<CutBox> cut;
+        if (!hs->nodes.empty()) {
+            CutBox a, b;
+            children(0, &a, &b);
+            cut.push_back(a);
+            cut.push_back(b);
+            while (cut.size() < kMaxCullBoxes) {
+                int best = -1;
+                for (size_t i = 0; i < cut.size(); ++i)
+                    if (cut[i].link >= 0 && (best < 0 || cut[i].Area() > cut[best].Area())) best = static_cast<int>(i);
+                if (best < 0) break;
+                children(cut[best].link, &a, &b);
+                cut[best] = a;
+                cut.push_back(b);
+            }
+        }
+        for (const CutBox &c : cut)
+            if (c.hi[0] >= c.lo[0] && c.hi[1] >= c.lo[1] && c.hi[2] >= c.lo[2]) // skip the empty box of a one-leaf tree
+                hs->cull_boxes.insert(hs->cull_boxes.end(), {c.lo[0], c.lo[1], c.lo[2], c.hi[0], c.hi[1], c.hi[2]});
+        for (const AnalyticPrim &p : hs->analytic)
+            hs->cull_boxes.insert(hs->cull_boxes.end(), {p.bmin[0], p.bmin[1], p.bmin[2], p.bmax[0], p.bmax[1], p.bmax[2]});
+    }
+
     // ---- triangle CDFs of mesh area lights (replaces the area-weighted BVH descent of blas.cpp:79-98) ----
     for (uint32_t light = 0; light < hs->map_area_light_instance.size(); ++light) {
         const uint32_t inst = hs->map_area_light_instance[light];

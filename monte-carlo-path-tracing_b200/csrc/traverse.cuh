@@ -232,17 +232,21 @@ __device__ __forceinline__ uint32_t AppendCoalesced(uint32_t *counter) {
 // two divergent phases apart.  Incoherent bounce rays ran at 5.6 active lanes per instruction with
 // one-ray-per-thread launches (profiles/r01_extend_baseline.txt); this loop is the fix.
 //
-//   fetch(index, &ray, &ctr) -> bool   builds ray `index` (false: nothing to trace for this index); with OPACITY it also
-//                                      returns the (pixel, sample, depth) counter of the ray's random-number stream
-//   finish(index, hit, found)          consumes the result (closest hit record, or occlusion flag for ANY)
+//   fetch(index, &ray, &ctr, &any) -> bool   builds ray `index` (false: nothing to trace for this index) and says whether it
+//                                            is an occlusion ray (`any`: the first hit ends it) or a closest-hit ray; with
+//                                            OPACITY it also returns the (pixel, sample, depth) counter of the ray's
+//                                            random-number stream
+//   finish(index, hit, found, any)           consumes the result (closest hit record, or occlusion flag)
 // OPACITY compiles the stochastic alpha test into the primitive tests (scenes whose BSDFs carry opacity textures).
-template <bool ANY, bool STATS, bool OPACITY, bool TOP, typename Fetch, typename Finish>
+// MIXED = false promises that no ray is an occlusion ray (camera rays) and compiles the per-lane flag out.
+// `counters` / `rays_traced` have two entries: [0] closest-hit rays, [1] occlusion rays.
+template <bool MIXED, bool STATS, bool OPACITY, bool TOP, typename Fetch, typename Finish>
 __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, const float4 *top, int num_top, uint32_t num_rays,
                                                    uint32_t *work_counter, int refill_threshold, int min_inner_lanes, uint2 key, Fetch fetch, Finish finish,
                                                    TraversalCounters *counters, uint32_t *rays_traced) {
     int stack[kStackSize];
     int sp = 0, cur = kSentinel;
-    bool has = false, exhausted = false, found = false;
+    bool has = false, exhausted = false, found = false, any = false;
     uint32_t index = 0;
     Ray ray;
     ray.o = ray.d = mk3(0.0f);
@@ -250,7 +254,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
     RayPre pre = Precompute(ray);
     HitRec hit;
     hit.t = 0.0f, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
-    Rng rng(0, 0, 0, key, ANY ? kRngDomainShadow : kRngDomainClosest);
+    Rng rng(0, 0, 0, key, kRngDomainClosest);
 
     for (;;) {
         // Refill idle lanes in groups: the fetch path (ray load, 1/d, shear constants) is long, so it is run
@@ -261,27 +265,28 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
             index = AppendCoalesced(work_counter);
             if (index >= num_rays) {
                 exhausted = true;
-            } else if (uint3 ctr = make_uint3(0, 0, 0); fetch(index, &ray, &ctr)) {
-                if (OPACITY) rng = Rng(ctr.x, ctr.y, ctr.z, key, ANY ? kRngDomainShadow : kRngDomainClosest);
+            } else if (uint3 ctr = make_uint3(0, 0, 0); fetch(index, &ray, &ctr, &any)) {
+                if (!MIXED) any = false;
+                if (OPACITY) rng = Rng(ctr.x, ctr.y, ctr.z, key, any ? kRngDomainShadow : kRngDomainClosest);
                 pre = Precompute(ray);
                 hit.t = ray.tmax, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
                 found = false;
                 has = true;
                 sp = 0;
                 cur = scene.num_nodes ? 0 : kSentinel;
-                ++(*rays_traced);
+                ++rays_traced[any];
                 // Analytic primitives (spheres, disks, cylinders) are few: tested linearly up front.
                 for (uint32_t i = 0; i < scene.num_analytic; ++i) {
                     const AnalyticPrim &p = scene.analytic[i];
-                    if (STATS) ++counters->nodes;
+                    if (STATS) ++counters[any].nodes;
                     if (!IntersectBox(p.bmin, p.bmax, ray, pre)) continue;
-                    if (STATS) ++counters->prims;
+                    if (STATS) ++counters[any].prims;
                     float t;
                     V2 uv = {0.0f, 0.0f};
                     if (IntersectAnalytic(p, ray, &t, OPACITY ? &uv : nullptr)) {
                         if (OPACITY && OpacityRejects(scene, p.inst, uv, rng)) continue;
                         found = true;
-                        if (ANY) {
+                        if (any) {
                             cur = kSentinel;
                             break;
                         }
@@ -299,7 +304,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                 float4 n0, n1, nz;
                 int child0, child1;
                 LoadNode<TOP>(scene.nodes, top, num_top, cur, &n0, &n1, &nz, &child0, &child1);
-                if (STATS) counters->nodes += 2;
+                if (STATS) counters[any].nodes += 2;
                 const float c0lox = fmaf(n0.x, pre.idir.x, -pre.ood.x), c0hix = fmaf(n0.y, pre.idir.x, -pre.ood.x);
                 const float c0loy = fmaf(n0.z, pre.idir.y, -pre.ood.y), c0hiy = fmaf(n0.w, pre.idir.y, -pre.ood.y);
                 const float c0loz = fmaf(nz.x, pre.idir.z, -pre.ood.z), c0hiz = fmaf(nz.y, pre.idir.z, -pre.ood.z);
@@ -333,7 +338,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                 cur = sp > 0 ? stack[--sp] : kSentinel;
                 for (uint32_t j = 0; j < count; ++j) {
                     const float4 p0 = __ldg(verts + 3 * j), p1 = __ldg(verts + 3 * j + 1), p2 = __ldg(verts + 3 * j + 2);
-                    if (STATS) ++counters->prims;
+                    if (STATS) ++counters[any].prims;
                     float t, u, v;
                     bool inside;
                     if (IntersectTriangleWoop(ray, pre, p0, p1, p2, &t, &u, &v, &inside)) {
@@ -344,7 +349,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                             if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng)) continue;
                         }
                         found = true;
-                        if (ANY) {
+                        if (any) {
                             cur = kSentinel;
                             break;
                         }
@@ -357,7 +362,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                 }
             }
             if (cur == kSentinel) {
-                finish(index, hit, found);
+                finish(index, hit, found, any);
                 has = false;
             }
         }

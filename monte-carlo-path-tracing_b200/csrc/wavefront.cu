@@ -93,12 +93,12 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ De
     __shared__ uint64_t bar;
     const int num_top = TOP ? StageTopNodes(scene, top, &bar, max_top) : 0;
     const uint32_t nslots = bp.pixel_count * bp.sample_count;
-    TraversalCounters tc;
-    uint32_t rays = 0;
+    TraversalCounters tc[2];
+    uint32_t rays[2] = {0, 0};
     Ray cam; // the camera ray of the slot this lane currently traces (the traversal shortens its own copy)
-    auto fetch = [&](uint32_t slot, Ray *ray, uint3 *ctr) {
+    auto fetch = [&](uint32_t slot, Ray *ray, uint3 *ctr, bool *) {
         uint32_t px, py;
-        if (!LocalPixelToImage(bp, bp.pixel_begin + slot / bp.sample_count, &px, &py)) return false;
+        if (!LocalPixelToImage(bp, JobPixelToLocal(bp, bp.pixel_begin + slot / bp.sample_count), &px, &py)) return false;
         const uint32_t s = bp.sample_begin + slot % bp.sample_count;
         if (OPACITY) *ctr = make_uint3(py * bp.width + px, s, 0u);
         const float u = s * bp.spp_inv, v = VanDerCorput2(s + 1);
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ De
         cam = *ray;
         return true;
     };
-    auto finish = [&](uint32_t slot, const HitRec &hit, bool found) {
+    auto finish = [&](uint32_t slot, const HitRec &hit, bool found, bool) {
         if (!found) { // path.cpp:24-35: an escaped camera ray sees the environment and the sun disc
             V3 L = mk3(0.0f);
             if (scene.integrator.id_envmap != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_envmap], cam.d);
@@ -134,76 +134,70 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ De
         }
         q.hit[idx] = hit;
     };
-    TraversePersistent<false, STATS, OPACITY, TOP>(scene, top, num_top, nslots, &counters->work_primary, refill, min_inner, bp.key, fetch, finish, &tc, &rays);
-    FlushCounters(STATS, tc, rays, kClassPrimary, counters);
+    TraversePersistent<false, STATS, OPACITY, TOP>(scene, top, num_top, nslots, &counters->work_primary, refill, min_inner, bp.key, fetch, finish, tc, rays);
+    FlushCounters(STATS, tc[0], rays[0], kClassPrimary, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_extend: closest hit for a compacted queue (TLAS::Intersect, tlas.cpp:13-43).
+// k_trace: ONE persistent launch per bounce for both ray kinds that leave a path vertex — the closest hit of the
+// compacted survivor queue (TLAS::Intersect, tlas.cpp:13-43) and the occlusion test of the NEE rays
+// (TLAS::IntersectAny, tlas.cpp:44-76).  The two kinds are independent, so tracing them from one work counter
+// halves the number of launch tails (a launch cannot end before its slowest ray: ~0.2 ms on Dragon, which dominated
+// the deep bounces when they were two launches: profiles/r01_dram_traffic.json per-launch times).
+// Ray index space: [0, n_extend) closest-hit rays of queue `which`, then [n_extend, n_extend + n_shadow) NEE rays.
 // ---------------------------------------------------------------------------------------------
 // Random-number counter (pixel, sample, depth) of the alpha tests along the ray of sample slot `slot`.
 __device__ __forceinline__ uint3 SlotCounter(const BatchParams &bp, uint32_t slot, uint32_t depth) {
     uint32_t px = 0, py = 0;
-    LocalPixelToImage(bp, bp.pixel_begin + slot / bp.sample_count, &px, &py);
+    LocalPixelToImage(bp, JobPixelToLocal(bp, bp.pixel_begin + slot / bp.sample_count), &px, &py);
     return make_uint3(py * bp.width + px, bp.sample_begin + slot % bp.sample_count, depth);
 }
 
 template <bool STATS, bool OPACITY, bool TOP>
-__global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ DeviceScene scene,
-                                                     const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue q, int which,
-                                                     Counters *counters, int max_top, int refill, int min_inner) {
+__global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ DeviceScene scene,
+                                                    const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue q, int which,
+                                                    ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters,
+                                                    int max_top, int refill, int min_inner) {
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
-    const uint32_t n = counters->queue[which];
+    const uint32_t n_extend = which >= 0 ? counters->queue[which] : 0u, n_shadow = counters->shadow;
+    const uint32_t n = n_extend + n_shadow;
     if (blockIdx.x * blockDim.x >= n) return;
     const int num_top = TOP ? StageTopNodes(scene, top, &bar, max_top) : 0;
-    TraversalCounters tc;
-    uint32_t rays = 0;
-    auto fetch = [&](uint32_t i, Ray *ray, uint3 *ctr) {
-        ray->o = mk3(q.ox[i], q.oy[i], q.oz[i]);
-        ray->d = mk3(q.dx[i], q.dy[i], q.dz[i]);
+    TraversalCounters tc[2];
+    uint32_t rays[2] = {0, 0};
+    auto fetch = [&](uint32_t i, Ray *ray, uint3 *ctr, bool *any) {
         ray->tmin = kEpsilonDistance;
-        ray->tmax = kMaxFloat;
-        if (OPACITY) *ctr = SlotCounter(bp, q.slot[i], depth);
+        if (i < n_extend) {
+            ray->o = mk3(q.ox[i], q.oy[i], q.oz[i]);
+            ray->d = mk3(q.dx[i], q.dy[i], q.dz[i]);
+            ray->tmax = kMaxFloat;
+            *any = false;
+            if (OPACITY) *ctr = SlotCounter(bp, q.slot[i], depth);
+        } else {
+            const uint32_t j = i - n_extend;
+            ray->o = mk3(sq.ox[j], sq.oy[j], sq.oz[j]);
+            ray->d = mk3(sq.dx[j], sq.dy[j], sq.dz[j]);
+            ray->tmax = sq.tmax[j];
+            *any = true;
+            // several NEE rays of one vertex (one per emitter) share (pixel, sample, depth): the queue index separates them
+            if (OPACITY) *ctr = SlotCounter(bp, sq.slot[j], depth), ctr->y ^= j * 0x9e3779b9u;
+        }
         return true;
     };
-    auto finish = [&](uint32_t i, const HitRec &hit, bool) { q.hit[i] = hit; };
-    TraversePersistent<false, STATS, OPACITY, TOP>(scene, top, num_top, n, &counters->work_extend, refill, min_inner, bp.key, fetch, finish, &tc, &rays);
-    FlushCounters(STATS, tc, rays, kClassExtend, counters);
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_shadow: occlusion test of the NEE rays (TLAS::IntersectAny, tlas.cpp:44-76).
-// ---------------------------------------------------------------------------------------------
-template <bool STATS, bool OPACITY, bool TOP>
-__global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ DeviceScene scene,
-                                                    const __grid_constant__ BatchParams bp, uint32_t depth, ShadowQueue sq, float *radiance,
-                                                    uint32_t capacity, Counters *counters, int max_top, int refill, int min_inner) {
-    extern __shared__ float4 top[];
-    __shared__ uint64_t bar;
-    const uint32_t n = counters->shadow;
-    if (blockIdx.x * blockDim.x >= n) return;
-    const int num_top = TOP ? StageTopNodes(scene, top, &bar, max_top) : 0;
-    TraversalCounters tc;
-    uint32_t rays = 0;
-    auto fetch = [&](uint32_t i, Ray *ray, uint3 *ctr) {
-        ray->o = mk3(sq.ox[i], sq.oy[i], sq.oz[i]);
-        ray->d = mk3(sq.dx[i], sq.dy[i], sq.dz[i]);
-        ray->tmin = kEpsilonDistance;
-        ray->tmax = sq.tmax[i];
-        // several NEE rays of one vertex (one per emitter) share (pixel, sample, depth): the queue index separates them
-        if (OPACITY) *ctr = SlotCounter(bp, sq.slot[i], depth), ctr->y ^= i * 0x9e3779b9u;
-        return true;
+    auto finish = [&](uint32_t i, const HitRec &hit, bool found, bool any) {
+        if (!any) {
+            q.hit[i] = hit;
+        } else if (!found) { // unoccluded: the light sample counts
+            const uint32_t j = i - n_extend, slot = sq.slot[j];
+            atomicAdd(radiance + slot, sq.cr[j]);
+            atomicAdd(radiance + capacity + slot, sq.cg[j]);
+            atomicAdd(radiance + 2 * capacity + slot, sq.cb[j]);
+        }
     };
-    auto finish = [&](uint32_t i, const HitRec &, bool occluded) {
-        if (occluded) return;
-        const uint32_t slot = sq.slot[i];
-        atomicAdd(radiance + slot, sq.cr[i]);
-        atomicAdd(radiance + capacity + slot, sq.cg[i]);
-        atomicAdd(radiance + 2 * capacity + slot, sq.cb[i]);
-    };
-    TraversePersistent<true, STATS, OPACITY, TOP>(scene, top, num_top, n, &counters->work_shadow, refill, min_inner, bp.key, fetch, finish, &tc, &rays);
-    FlushCounters(STATS, tc, rays, kClassShadow, counters);
+    TraversePersistent<true, STATS, OPACITY, TOP>(scene, top, num_top, n, &counters->work_trace, refill, min_inner, bp.key, fetch, finish, tc, rays);
+    FlushCounters(STATS, tc[0], rays[0], kClassExtend, counters);
+    FlushCounters(STATS, tc[1], rays[1], kClassShadow, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,19 +258,24 @@ __global__ void __launch_bounds__(kThreads) k_shade(const __grid_constant__ Devi
         HitRec hit;
         hit.prim = kPrimMiss, hit.t = kMaxFloat, hit.u = hit.v = 0.0f;
         if (active) {
+            hit = qin.hit[i];
+            // A ray that left the scene contributes only through an environment map (path.cpp:81-93); without one
+            // (and outside volpath, where the segment may still scatter) its queue entry is dead: skip the other 52 bytes.
+            if (!VOL && hit.prim == kPrimMiss && ig.id_envmap == kInvalid) alive = false;
+        }
+        if (alive) {
             ray.o = mk3(qin.ox[i], qin.oy[i], qin.oz[i]);
             ray.d = mk3(qin.dx[i], qin.dy[i], qin.dz[i]);
             att = mk3(qin.tr[i], qin.tg[i], qin.tb[i]);
             pdf_sample = qin.pdf[i];
             slot = qin.slot[i];
-            hit = qin.hit[i];
             wo = -ray.d;
             if (VOL) {
                 ray_medium = qin.medium[i];
                 wo_prev = mk3(qin.wx[i], qin.wy[i], qin.wz[i]);
             }
         }
-        const uint32_t local_pixel = bp.pixel_begin + slot / bp.sample_count;
+        const uint32_t local_pixel = JobPixelToLocal(bp, bp.pixel_begin + slot / bp.sample_count);
         const uint32_t sample = bp.sample_begin + slot % bp.sample_count;
         uint32_t px = 0, py = 0;
         LocalPixelToImage(bp, local_pixel, &px, &py);
@@ -524,8 +523,86 @@ __global__ void __launch_bounds__(kThreads) k_shade(const __grid_constant__ Devi
 __global__ void k_reset(Counters *c, int which_queue, bool reset_shadow) {
     if (which_queue >= 0) c->queue[which_queue] = 0;
     if (reset_shadow) c->shadow = 0;
-    c->work_extend = 0;
-    c->work_shadow = 0;
+    c->work_trace = 0;
+}
+
+// Visibility pre-pass for camera rays.  Every camera ray of a tile starts at the eye and runs inside the pyramid spanned
+// by the tile's four corner directions (widened by half a pixel); a box that lies entirely outside one of the pyramid's
+// side planes, or behind the eye, cannot be hit by any of them.  A tile that sees none of the scene's cull boxes (which
+// cover all geometry) produces only escaped rays, i.e. exactly zero radiance when there is no environment / sun emitter,
+// so its samples need no ray at all.  Conservative by construction: a tile is dropped only on a proof of emptiness.
+// One warp per local tile, lanes over boxes.
+__global__ void __launch_bounds__(kThreads) k_cull_tiles(const __grid_constant__ BatchParams bp, const float *__restrict__ boxes,
+                                                         uint32_t num_boxes, uint32_t num_local_tiles, uint32_t *flags) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, num_warps = (gridDim.x * blockDim.x) >> 5;
+    const V3 eye = mk3(bp.camera.eye), front = mk3(bp.camera.front), dx = mk3(bp.camera.view_dx), dy = mk3(bp.camera.view_dy);
+    for (uint32_t t = warp; t < num_local_tiles; t += num_warps) {
+        const uint32_t tile = t * bp.tile_world + bp.tile_rank;
+        bool visible = false;
+        if (tile < bp.num_tiles) {
+            const float i0 = static_cast<float>((tile % bp.tiles_x) * kTileSize), j0 = static_cast<float>((tile / bp.tiles_x) * kTileSize);
+            const float i1 = fminf(i0 + kTileSize, static_cast<float>(bp.width)), j1 = fminf(j0 + kTileSize, static_cast<float>(bp.height));
+            constexpr float kMargin = 0.5f; // pixels
+            const float x0 = 2.0f * (i0 - kMargin) / static_cast<float>(bp.width) - 1.0f, x1 = 2.0f * (i1 + kMargin) / static_cast<float>(bp.width) - 1.0f;
+            const float y0 = 1.0f - 2.0f * (j0 - kMargin) / static_cast<float>(bp.height), y1 = 1.0f - 2.0f * (j1 + kMargin) / static_cast<float>(bp.height);
+            const V3 corner[4] = {front + x0 * dx + y0 * dy, front + x1 * dx + y0 * dy, front + x1 * dx + y1 * dy, front + x0 * dx + y1 * dy};
+            const V3 centre = corner[0] + corner[2];
+            V3 plane[5];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                V3 n = Cross(corner[k], corner[(k + 1) & 3]);
+                if (Dot(n, centre) < 0.0f) n = -n; // inward
+                plane[k] = n;
+            }
+            plane[4] = front;
+            for (uint32_t b = lane; b < num_boxes; b += 32) {
+                const float *bx = boxes + 6 * b;
+                const V3 lo = mk3(bx[0], bx[1], bx[2]), hi = mk3(bx[3], bx[4], bx[5]);
+                const V3 c = 0.5f * (lo + hi) - eye, h = 0.5f * (hi - lo);
+                bool outside = false;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const V3 n = plane[k];
+                    const float s = Dot(n, c), r = fabsf(n.x) * h.x + fabsf(n.y) * h.y + fabsf(n.z) * h.z;
+                    if (s + r < -1e-5f * (fabsf(s) + r)) outside = true; // the whole box is on the outer side
+                }
+                if (!outside) visible = true;
+            }
+        }
+        visible = __any_sync(0xffffffffu, visible);
+        if (lane == 0) flags[t] = visible ? 1u : 0u;
+    }
+}
+
+// Deterministic stream compaction of the tile flags by ONE CTA (at most a few 10^5 tiles): list[0..count) = ascending
+// indices of the set flags, list[n] = count.
+__global__ void __launch_bounds__(1024) k_compact_tiles(const uint32_t *flags, uint32_t n, uint32_t *list) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t chunk = (n + blockDim.x - 1) / blockDim.x, begin = min(n, tid * chunk), end = min(n, begin + chunk);
+    uint32_t mine = 0;
+    for (uint32_t i = begin; i < end; ++i) mine += flags[i];
+    uint32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= static_cast<uint32_t>(o)) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= static_cast<uint32_t>(o)) wi += v;
+        }
+        warp_sums[lane] = wi - w; // exclusive
+        if (lane == 31) list[n] = wi;
+    }
+    __syncthreads();
+    uint32_t out = warp_sums[warp] + incl - mine;
+    for (uint32_t i = begin; i < end; ++i)
+        if (flags[i]) list[out++] = i;
 }
 
 // renderer.cpp:76-84: clamp each SAMPLE to <= 1 per channel (Q2), then sum the pixel's samples.
@@ -548,7 +625,7 @@ __global__ void __launch_bounds__(kThreads) k_resolve(const __grid_constant__ Ba
             b += __shfl_down_sync(0xffffffffu, b, o);
         }
         if (lane == 0) {
-            float *a = accum + 3ull * (bp.pixel_begin + p);
+            float *a = accum + 3ull * JobPixelToLocal(bp, bp.pixel_begin + p);
             a[0] += r, a[1] += g, a[2] += b;
         }
     }
@@ -627,14 +704,9 @@ void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const Batch
     B200PT_LAUNCH_TRAVERSAL(k_primary, scene, bp, q, radiance, capacity, counters);
 }
 
-void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
-                  Counters *counters) {
-    B200PT_LAUNCH_TRAVERSAL(k_extend, scene, bp, depth, q, which, counters);
-}
-
-void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, ShadowQueue sq,
-                  float *radiance, uint32_t capacity, Counters *counters) {
-    B200PT_LAUNCH_TRAVERSAL(k_shadow, scene, bp, depth, sq, radiance, capacity, counters);
+void LaunchTrace(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
+                 ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters) {
+    B200PT_LAUNCH_TRAVERSAL(k_trace, scene, bp, depth, q, which, sq, radiance, capacity, counters);
 }
 
 void LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
@@ -643,6 +715,14 @@ void LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchPa
         k_shade<true><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, bp, depth, qin, which_in, qout, sq, radiance, counters, capacity);
     else
         k_shade<false><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, bp, depth, qin, which_in, qout, sq, radiance, counters, capacity);
+}
+
+void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
+                     uint32_t *flags, uint32_t *list) {
+    const int warps_per_cta = kThreads / 32;
+    const int blocks = static_cast<int>(std::min<uint32_t>(lc.blocks, (num_local_tiles + warps_per_cta - 1) / warps_per_cta));
+    k_cull_tiles<<<std::max(blocks, 1), kThreads, 0, lc.stream>>>(bp, scene.cull_boxes, scene.num_cull_boxes, num_local_tiles, flags);
+    k_compact_tiles<<<1, 1024, 0, lc.stream>>>(flags, num_local_tiles, list);
 }
 
 void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow) {

@@ -5,8 +5,8 @@
 //   k_primary   ray-gen + closest hit for camera rays (fused; misses with no env light die here)
 //   k_shade     hit attributes, emitter hit / env miss MIS, Russian roulette, NEE shadow-ray
 //               generation, BSDF / phase sampling, warp-ballot compaction of survivors
-//   k_shadow    any-hit for the NEE rays, adds the unoccluded contributions
-//   k_extend    closest hit for the compacted survivor queue
+//   k_trace     one launch per bounce: closest hit for the compacted survivor queue + any-hit for the NEE rays
+//               (adds the unoccluded contributions)
 //   k_resolve   per-sample clamp + per-pixel sum (renderer.cpp:77-84)
 // All per-path state is SoA so that a warp's loads/stores are 128-byte transactions.
 #pragma once
@@ -49,9 +49,8 @@ struct Counters {             // device-resident
     uint32_t queue[2];        // entries in path queue 0 / 1 (zeroed per batch)
     uint32_t shadow;          // entries in the shadow queue
     uint32_t work_primary;    // next unclaimed ray of the persistent traversal loops
-    uint32_t work_extend;
-    uint32_t work_shadow;
-    uint32_t pad[2];
+    uint32_t work_trace;
+    uint32_t pad[3];
     ClassCounters cls[3];     // primary / extend / shadow traversal statistics (zeroed per render)
 };
 constexpr size_t kCountersPerBatchBytes = 32; // the part of Counters that is zeroed for every batch
@@ -67,7 +66,16 @@ struct BatchParams {
     uint32_t pixel_count;     // local pixels in this batch
     uint32_t sample_begin;    // first sample index of this batch
     uint32_t sample_count;    // samples per pixel in this batch (slots = pixel_count * sample_count)
+    // Tile visibility pre-pass (k_cull_tiles): the local tiles whose camera rays can reach geometry, in ascending order;
+    // the job's pixel list is then [active tile 0's 64 pixels, active tile 1's, ...].  nullptr = every local tile.
+    const uint32_t *active_tiles;
 };
+
+// index in the job's pixel list -> local pixel (position in this rank's tile-ordered pixel buffer)
+__host__ __device__ inline uint32_t JobPixelToLocal(const BatchParams &p, uint32_t job_pixel) {
+    if (p.active_tiles == nullptr) return job_pixel;
+    return p.active_tiles[job_pixel / kTilePixels] * kTilePixels + job_pixel % kTilePixels;
+}
 
 // local pixel -> image coordinates; false for padding pixels of edge tiles / tiles past the end.
 __host__ __device__ inline bool LocalPixelToImage(const BatchParams &p, uint32_t local_pixel, uint32_t *i, uint32_t *j) {
@@ -93,12 +101,15 @@ struct LaunchConfig {
 void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, float *radiance,
                    uint32_t capacity, Counters *counters);
 // `depth` = index of the path vertex the rays leave from: with `bp` it keys the alpha-test random numbers (opacity masks).
-void LaunchExtend(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
-                  Counters *counters);
+// which < 0: no closest-hit rays this round (last bounce), only the NEE rays.
+void LaunchTrace(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
+                 ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters);
 void LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
                  int which_in, PathQueue qout, ShadowQueue sq, float *radiance, Counters *counters, uint32_t capacity);
-void LaunchShadow(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, ShadowQueue sq,
-                  float *radiance, uint32_t capacity, Counters *counters);
+// Visibility pre-pass: flags[t] = 1 if local tile t can see one of the scene's cull boxes, then the ascending list of
+// such tiles in list[0 .. count) with count stored at list[num_local_tiles].
+void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
+                     uint32_t *flags, uint32_t *list);
 void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow);
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum);
 void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,

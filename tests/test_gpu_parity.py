@@ -134,10 +134,11 @@ def test_edge_cases(pkg):
 def test_full_size_dragon_properties(pkg):
     """BASELINE configs[1] size (1024x1024, 256 spp) through size-independent properties."""
     r = pkg.Renderer(pkg.Scene(pack("dragon")), device=0)
-    frame = r.Draw(width=1024, height=1024, spp=256, seed=1, stats=pkg.STATS_COUNTERS)
+    frame = r.Draw(width=1024, height=1024, spp=256, seed=1, stats=pkg.STATS_COUNTERS, flags=pkg.RENDER_NO_TILE_CULL)
     st = r.stats()
     assert st["samples"] == 1024 * 1024 * 256
     assert st["primary"]["rays"] == 1024 * 1024 * 256            # one camera ray per sample
+    assert st["active_tiles"] == st["local_tiles"] == 128 * 128
     assert np.isfinite(frame).all() and frame.min() >= 0.0 and frame.max() <= 1.0 + 1e-6
     # coverage: most of the frame is background (SURVEY.md §8d: ~92 % of camera rays miss at 1024^2)
     coverage = float((frame.sum(axis=2) > 0).mean())
@@ -148,9 +149,61 @@ def test_full_size_dragon_properties(pkg):
     assert abs(down.mean() / golden.mean() - 1.0) < 0.01
     assert rel_l2(boxed(down, 4), boxed(golden, 4)) < 0.05
     # idempotence: the same call again gives the same bits
-    again = r.Draw(width=1024, height=1024, spp=256, seed=1)
+    again = r.Draw(width=1024, height=1024, spp=256, seed=1, flags=pkg.RENDER_NO_TILE_CULL)
     assert np.array_equal(frame, again)
+    # the default path drops the tiles that provably see no geometry: same bits, far fewer camera rays
+    culled = r.Draw(width=1024, height=1024, spp=256, seed=1, stats=pkg.STATS_COUNTERS)
+    st = r.stats()
+    assert np.array_equal(frame, culled)
+    assert st["samples"] == 1024 * 1024 * 256
+    assert st["primary"]["rays"] == st["active_tiles"] * 64 * 256
+    assert coverage * 128 * 128 <= st["active_tiles"] < 0.35 * 128 * 128, st["active_tiles"]
     r.close()
+
+
+@pytest.mark.parametrize("scene,w,h", [("dragon", 200, 120), ("cornell-box", 64, 64), ("volumetric-caustic", 40, 56),
+                                       ("synthetic_opacity_masks", 64, 48), ("synthetic_dielectrics_conductor_cylinder", 48, 64)])
+def test_tile_visibility_prepass_is_exact(pkg, scene, w, h):
+    """Dropping tiles that cannot see geometry never changes a bit of the frame (whole frame and tile-partitioned)."""
+    import torch
+    r = renderer(pkg, scene)
+    full = r.Draw(width=w, height=h, spp=8, seed=13, flags=pkg.RENDER_NO_TILE_CULL)
+    culled = r.Draw(width=w, height=h, spp=8, seed=13)
+    st = r.stats()
+    assert np.array_equal(full, culled)
+    assert st["active_tiles"] <= st["local_tiles"] == ((w + 7) // 8) * ((h + 7) // 8)
+    # every tile with a lit pixel survived the pre-pass
+    lit_tiles = (np.add.reduceat(np.add.reduceat(full.sum(axis=2), np.arange(0, h, 8), axis=0), np.arange(0, w, 8), axis=1) > 0).sum()
+    assert st["active_tiles"] >= lit_tiles
+    world = 3
+    n = pkg.tile_buffer_floats(w, h, world)
+    gathered = torch.zeros(world * n, dtype=torch.float32, device="cuda")
+    for rank in range(world):
+        r.draw_tiles_device(gathered[rank * n:(rank + 1) * n], rank, world, w, h, 8, seed=13)
+    frame = torch.zeros(h * w * 3, dtype=torch.float32, device="cuda")
+    r.assemble_tiles_device(gathered, frame, w, h, world)
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy().reshape(h, w, 3), full)
+
+
+def test_dragon_prepass_drops_most_of_the_background(pkg):
+    r = renderer(pkg, "dragon")
+    r.Draw(width=512, height=512, spp=1, seed=1)
+    st = r.stats()
+    assert 0 < st["active_tiles"] < 0.35 * st["local_tiles"], st
+
+
+def test_shared_memory_top_of_tree_is_bit_exact(pkg, monkeypatch):
+    """The TMA-staged copy of the top BVH nodes (B200PT_TOP_NODES > 0) only changes where node bytes come from."""
+    scene = pkg.Scene(pack("dragon"))
+    plain = pkg.Renderer(scene, device=0, max_paths_in_flight=1 << 22)
+    a = plain.Draw(width=160, height=160, spp=8, seed=3)
+    plain.close()
+    monkeypatch.setenv("B200PT_TOP_NODES", "256")
+    staged = pkg.Renderer(scene, device=0, max_paths_in_flight=1 << 22)
+    b = staged.Draw(width=160, height=160, spp=8, seed=3)
+    staged.close()
+    assert np.array_equal(a, b)
 
 
 def test_kulla_conty_tables_match_reference(pkg):
