@@ -55,6 +55,25 @@ struct DeviceArray {
 
 } // namespace
 
+namespace {
+constexpr int kMaxArenas = 8;
+constexpr int kPollRing = 8;         // survivor-count polls in flight per arena
+constexpr uint32_t kPollLag = 4;     // a poll is read this many rounds after it was enqueued, so the host never drains the GPU
+constexpr uint32_t kFirstPollDepth = 8;
+
+// One batch of paths in flight.
+struct Arena {
+    PathQueue queue[2]{};
+    ShadowQueue shadow{};
+    float *radiance = nullptr;       // 3 planes of `capacity` floats
+    Counters *counters = nullptr;
+    cudaStream_t stream = nullptr;   // owned side stream (a single-arena render runs on the caller's stream instead)
+    cudaEvent_t done = nullptr;
+    cudaEvent_t poll_event[kPollRing]{};
+    uint32_t *poll_count = nullptr;  // pinned, kPollRing entries
+};
+} // namespace
+
 struct b200pt_context {
     int device = 0;
     std::string error;
@@ -78,20 +97,20 @@ struct b200pt_context {
     DeviceArray<uint32_t> tile_flags, tile_list; // visibility pre-pass: per local tile flag; ascending active list + count
     bool tile_cull = true;        // B200PT_TILE_CULL=0 turns the pre-pass off
 
-    // wavefront state
-    uint64_t capacity = 0;        // sample slots per batch currently allocated
-    uint64_t max_capacity = 0;    // upper bound (create option / default)
+    // wavefront state: up to kMaxArenas independent batches in flight, each with private queues, counters and stream,
+    // so that the latency-bound tail of one batch's launches is filled by another batch's work
+    uint64_t capacity = 0;        // sample slots per arena as currently carved
+    uint64_t max_capacity = 0;    // upper bound on slots over all arenas (create option / default)
     uint32_t shadow_per_vertex = 1;
-    DeviceArray<float> wave;      // one allocation carved into the SoA queues
-    PathQueue queue[2]{};
-    ShadowQueue shadow{};
-    float *radiance = nullptr;
-    DeviceArray<Counters> counters;
+    DeviceArray<float> wave;      // one allocation carved into the arenas' SoA queues
+    Arena arenas[kMaxArenas];
+    int num_arenas = 2;           // B200PT_ARENAS (profiles/r01_sweep_arenas_occupancy.log: 2 is best on Dragon, 4 on matpreview)
+    DeviceArray<Counters> counters; // one per arena
     DeviceArray<float> accum;     // per local pixel RGB sums
     DeviceArray<float> frame;     // staging for b200pt_render (host frame)
     uint32_t *pinned_count = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_fork = nullptr;
     bool timing_pending = false;
     int num_sms = 148;
     // launch tunables (overridable through the environment for experiments: B200PT_TOP_NODES, B200PT_REFILL, B200PT_CTAS_PER_SM)
@@ -116,6 +135,14 @@ struct b200pt_context {
     }
 
     ~b200pt_context() {
+        for (Arena &a : arenas) {
+            if (a.poll_count) cudaFreeHost(a.poll_count);
+            if (a.done) cudaEventDestroy(a.done);
+            for (cudaEvent_t e : a.poll_event)
+                if (e) cudaEventDestroy(e);
+            if (a.stream) cudaStreamDestroy(a.stream);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
         if (pinned_count) cudaFreeHost(pinned_count);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
@@ -196,48 +223,62 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     return B200PT_OK;
 }
 
-// Carve the SoA queues out of one allocation sized for `wanted` sample slots (clamped to what fits in HBM).
-int AllocWavefront(b200pt_context *c, uint64_t wanted) {
+// Words of wavefront state per sample slot.
+uint64_t WordsPerSlot(const b200pt_context *c) {
+    const bool vol = c->scene.integrator.type == B200PT_INTEGRATOR_VOLPATH;
+    const uint32_t shadow_per_vertex = c->scene.integrator.num_emitters + (c->scene.integrator.num_area_lights ? 1u : 0u);
+    const uint64_t words_per_queue = 11 + (vol ? 4 : 0) + 4; // 10 floats + slot (+ medium, wo) + HitRec
+    return 2 * words_per_queue + 11 * std::max(1u, shadow_per_vertex) + 3;
+}
+
+// Carve the SoA queues of `arenas` arenas out of one allocation; each arena gets `wanted_per_arena` sample slots, or
+// what fits in 40 % of the free HBM.  The allocation only ever grows; carving itself is pointer arithmetic.
+int CarveWavefront(b200pt_context *c, uint64_t wanted_per_arena, int arenas) {
     const bool vol = c->scene.integrator.type == B200PT_INTEGRATOR_VOLPATH;
     c->shadow_per_vertex = c->scene.integrator.num_emitters + (c->scene.integrator.num_area_lights ? 1u : 0u);
-    const uint64_t words_per_queue = 11 + (vol ? 4 : 0) + 4; // 10 floats + slot (+ medium, wo) + HitRec
-    const uint64_t words_per_slot = 2 * words_per_queue + 11 * std::max(1u, c->shadow_per_vertex) + 3;
-    c->wave.Free();
-    c->capacity = 0;
-    size_t free_bytes = 0, total_bytes = 0;
-    CU_CHECK(c, cudaMemGetInfo(&free_bytes, &total_bytes));
-    uint64_t capacity = std::min<uint64_t>(wanted, static_cast<uint64_t>(free_bytes * 0.4) / (words_per_slot * sizeof(float)));
-    capacity = std::max<uint64_t>(capacity & ~1023ull, 1024);
+    const uint64_t words_per_slot = WordsPerSlot(c);
+    uint64_t capacity = std::max<uint64_t>((wanted_per_arena + 1023ull) & ~1023ull, 1024);
+    if (c->wave.count < words_per_slot * capacity * arenas) {
+        CU_CHECK(c, cudaDeviceSynchronize());
+        c->wave.Free();
+        size_t free_bytes = 0, total_bytes = 0;
+        CU_CHECK(c, cudaMemGetInfo(&free_bytes, &total_bytes));
+        const uint64_t fits = static_cast<uint64_t>(free_bytes * 0.4) / (words_per_slot * sizeof(float) * arenas);
+        capacity = std::max<uint64_t>(std::min(capacity, fits) & ~1023ull, 1024);
+        CU_CHECK(c, c->wave.Alloc(words_per_slot * capacity * arenas));
+    }
     const uint64_t shadow_cap = capacity * std::max(1u, c->shadow_per_vertex);
-    const uint64_t total = words_per_slot * capacity;
-    CU_CHECK(c, c->wave.Alloc(total));
     float *p = c->wave.ptr;
     auto take = [&](uint64_t n) {
         float *r = p;
         p += n;
         return r;
     };
-    for (int k = 0; k < 2; ++k) {
-        PathQueue &q = c->queue[k];
-        q.hit = reinterpret_cast<HitRec *>(take(4 * capacity)); // first: keeps 16-byte alignment
-        q.ox = take(capacity), q.oy = take(capacity), q.oz = take(capacity);
-        q.dx = take(capacity), q.dy = take(capacity), q.dz = take(capacity);
-        q.tr = take(capacity), q.tg = take(capacity), q.tb = take(capacity);
-        q.pdf = take(capacity);
-        q.slot = reinterpret_cast<uint32_t *>(take(capacity));
-        q.medium = nullptr, q.wx = q.wy = q.wz = nullptr;
-        if (vol) {
-            q.medium = reinterpret_cast<uint32_t *>(take(capacity));
-            q.wx = take(capacity), q.wy = take(capacity), q.wz = take(capacity);
+    for (int a = 0; a < arenas; ++a) {
+        Arena &ar = c->arenas[a];
+        for (int k = 0; k < 2; ++k) {
+            PathQueue &q = ar.queue[k];
+            q.hit = reinterpret_cast<HitRec *>(take(4 * capacity)); // first: keeps 16-byte alignment
+            q.ox = take(capacity), q.oy = take(capacity), q.oz = take(capacity);
+            q.dx = take(capacity), q.dy = take(capacity), q.dz = take(capacity);
+            q.tr = take(capacity), q.tg = take(capacity), q.tb = take(capacity);
+            q.pdf = take(capacity);
+            q.slot = reinterpret_cast<uint32_t *>(take(capacity));
+            q.medium = nullptr, q.wx = q.wy = q.wz = nullptr;
+            if (vol) {
+                q.medium = reinterpret_cast<uint32_t *>(take(capacity));
+                q.wx = take(capacity), q.wy = take(capacity), q.wz = take(capacity);
+            }
         }
+        ShadowQueue &sq = ar.shadow;
+        sq.ox = take(shadow_cap), sq.oy = take(shadow_cap), sq.oz = take(shadow_cap);
+        sq.dx = take(shadow_cap), sq.dy = take(shadow_cap), sq.dz = take(shadow_cap);
+        sq.tmax = take(shadow_cap);
+        sq.cr = take(shadow_cap), sq.cg = take(shadow_cap), sq.cb = take(shadow_cap);
+        sq.slot = reinterpret_cast<uint32_t *>(take(shadow_cap));
+        ar.radiance = take(3 * capacity);
+        ar.counters = c->counters.ptr + a;
     }
-    ShadowQueue &sq = c->shadow;
-    sq.ox = take(shadow_cap), sq.oy = take(shadow_cap), sq.oz = take(shadow_cap);
-    sq.dx = take(shadow_cap), sq.dy = take(shadow_cap), sq.dz = take(shadow_cap);
-    sq.tmax = take(shadow_cap);
-    sq.cr = take(shadow_cap), sq.cg = take(shadow_cap), sq.cb = take(shadow_cap);
-    sq.slot = reinterpret_cast<uint32_t *>(take(shadow_cap));
-    c->radiance = take(3 * capacity);
     c->capacity = capacity;
     return B200PT_OK;
 }
@@ -322,78 +363,146 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     c->stats.active_tiles = job_pixels / kTilePixels;
     c->stats.local_tiles = local_tiles;
 
-    // Wavefront state is sized for the job at hand (grown on demand, never shrunk): all of it in one batch if it fits.
+    // Batches.  The job's pixels are cut into chunks, one arena works on one chunk at a time (all its sample batches in
+    // order, so no two arenas ever add into the same pixel), chunks are dealt round-robin to the arenas.  Several arenas
+    // in flight hide the tail of every launch — a traversal launch cannot end before its slowest ray (~0.2 ms on Dragon,
+    // at every bounce) — behind another batch's work.  Per-class event timing needs serial launches: one arena then.
+    const uint64_t job_slots = static_cast<uint64_t>(job_pixels) * ro.spp;
+    const int S = (ro.timing || job_slots < (1ull << 21)) ? 1 : std::max(1, std::min(c->num_arenas, kMaxArenas));
     {
-        const uint64_t wanted = std::min<uint64_t>(c->max_capacity, std::max<uint64_t>(static_cast<uint64_t>(job_pixels) * ro.spp, 1024));
-        if (c->capacity < wanted) {
-            CU_CHECK(c, cudaDeviceSynchronize());
-            const int rc = AllocWavefront(c, wanted);
-            if (rc != B200PT_OK) return rc;
-        }
+        const uint64_t total = std::min<uint64_t>(c->max_capacity, std::max<uint64_t>(job_slots, 1024));
+        const int rc = CarveWavefront(c, (total + S - 1) / S, S);
+        if (rc != B200PT_OK) return rc;
     }
-    // Runs one kernel launch, counted (and, with B200PT_STATS_TIMING, bracketed by events) under its class.
-    auto launch = [&](int cls, auto &&fn) {
-        ++launches;
-        ++c->class_launches[cls];
-        if (ro.timing) {
-            b200pt_context::TimedLaunch t{cls, c->NextEvent(), c->NextEvent()};
-            cudaEventRecord(t.begin, stream);
-            fn();
-            cudaEventRecord(t.end, stream);
-            c->timed.push_back(t);
-        } else {
-            fn();
-        }
-    };
-    CU_CHECK(c, cudaMemsetAsync(c->accum.ptr, 0, 3ull * local_pixels * sizeof(float), stream));
-    CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, sizeof(Counters), stream));
-
-    const uint32_t capacity = static_cast<uint32_t>(c->capacity);
-    const uint32_t pixels_per_chunk = std::max<uint32_t>(1, std::min<uint32_t>(job_pixels, capacity));
+    const uint32_t capacity = static_cast<uint32_t>(c->capacity); // per arena
+    const uint32_t chunks_per_arena = std::max<uint32_t>(1, static_cast<uint32_t>((job_pixels + static_cast<uint64_t>(S) * capacity - 1) / (static_cast<uint64_t>(S) * capacity)));
+    const uint32_t num_chunks = chunks_per_arena * S;
+    const uint32_t pixels_per_chunk = std::max<uint32_t>(1, (job_pixels + num_chunks - 1) / num_chunks);
     const uint32_t samples_per_batch = std::max<uint32_t>(1, std::min<uint32_t>(ro.spp, capacity / pixels_per_chunk));
     const uint32_t max_rounds = std::min<uint32_t>(ig.depth_max, kMaxRounds);
 
-    for (uint32_t pixel_begin = 0; pixel_begin < job_pixels; pixel_begin += pixels_per_chunk) {
-        bp.pixel_begin = pixel_begin;
-        bp.pixel_count = std::min(pixels_per_chunk, job_pixels - pixel_begin);
-        for (uint32_t sample_begin = 0; sample_begin < ro.spp; sample_begin += samples_per_batch) {
-            bp.sample_begin = sample_begin;
-            bp.sample_count = std::min(samples_per_batch, ro.spp - sample_begin);
-            const uint64_t nslots = static_cast<uint64_t>(bp.pixel_count) * bp.sample_count;
-            for (int ch = 0; ch < 3; ++ch)
-                CU_CHECK(c, cudaMemsetAsync(c->radiance + static_cast<uint64_t>(ch) * capacity, 0, nslots * sizeof(float), stream));
-            CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, kCountersPerBatchBytes, stream)); // queue lengths + work counters
-            launch(kClassPrimary, [&] { LaunchPrimary(lc, c->scene, bp, c->queue[0], c->radiance, capacity, c->counters.ptr); });
-            int which = 0;
-            for (uint32_t depth = 1; depth <= max_rounds; ++depth) {
-                if (depth > 1) launch(kClassOther, [&] { LaunchResetCounters(lc, c->counters.ptr, which ^ 1, true); });
-                launch(kClassShade, [&] {
-                    LaunchShade(lc, c->scene, bp, depth, c->queue[which], which, c->queue[which ^ 1], c->shadow, c->radiance,
-                                c->counters.ptr, capacity);
-                });
-                which ^= 1;
-                // One traversal launch per bounce: closest hits of the survivors (queue `which`) + occlusion of the NEE rays.
-                auto trace = [&](int extend_queue) {
-                    launch(kClassExtend, [&] {
-                        LaunchTrace(lc, c->scene, bp, depth, c->queue[which], extend_queue, c->shadow, c->radiance, capacity, c->counters.ptr);
-                    });
-                };
-                bool survivors = depth < max_rounds;
-                if (survivors && depth >= 8 && (depth & 3) == 0) { // poll the survivor count
-                    CU_CHECK(c, cudaMemcpyAsync(c->pinned_count, &c->counters.ptr->queue[which], sizeof(uint32_t),
-                                                cudaMemcpyDeviceToHost, stream));
-                    CU_CHECK(c, cudaStreamSynchronize(stream));
-                    survivors = *c->pinned_count != 0;
-                }
-                if (!survivors) {
-                    if (c->shadow_per_vertex > 0) trace(-1); // only the NEE rays of the last vertex are left
-                    break;
-                }
-                trace(which);
-            }
-            launch(kClassOther, [&] { LaunchResolve(lc, bp, c->radiance, capacity, c->accum.ptr); });
-        }
+    CU_CHECK(c, cudaMemsetAsync(c->accum.ptr, 0, 3ull * local_pixels * sizeof(float), stream));
+    CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, sizeof(Counters) * kMaxArenas, stream));
+    if (S > 1) CU_CHECK(c, cudaEventRecord(c->ev_fork, stream));
+
+    struct Run {              // progress of one arena through its chunks
+        cudaStream_t stream = nullptr;
+        uint32_t chunk = 0;   // next chunk of this arena (chunk index = chunk * S + arena)
+        uint32_t sample_begin = 0;
+        bool in_batch = false;
+        uint32_t depth = 0;
+        int which = 0;
+        BatchParams bp{};
+    };
+    Run runs[kMaxArenas];
+    for (int a = 0; a < S; ++a) {
+        runs[a].stream = S > 1 ? c->arenas[a].stream : stream;
+        runs[a].bp = bp;
+        if (S > 1) CU_CHECK(c, cudaStreamWaitEvent(runs[a].stream, c->ev_fork, 0));
     }
+    cudaError_t issue_error = cudaSuccess;
+    // Issues the next piece of work of arena `a` (the start of a batch, or one bounce of the batch in flight);
+    // false when the arena has nothing left.
+    auto advance = [&](int a) -> bool {
+        Arena &ar = c->arenas[a];
+        Run &run = runs[a];
+        LaunchConfig la = lc;
+        la.stream = run.stream;
+        auto launch = [&](int cls, auto &&fn) { // one kernel launch, counted (and, with B200PT_STATS_TIMING, event-timed) under its class
+            ++launches;
+            ++c->class_launches[cls];
+            if (ro.timing) {
+                b200pt_context::TimedLaunch t{cls, c->NextEvent(), c->NextEvent()};
+                cudaEventRecord(t.begin, la.stream);
+                fn();
+                cudaEventRecord(t.end, la.stream);
+                c->timed.push_back(t);
+            } else {
+                fn();
+            }
+        };
+        auto check = [&](cudaError_t e) {
+            if (e != cudaSuccess && issue_error == cudaSuccess) issue_error = e;
+        };
+        if (!run.in_batch) {
+            const uint64_t pixel_begin = (static_cast<uint64_t>(run.chunk) * S + a) * pixels_per_chunk;
+            if (pixel_begin >= job_pixels) return false;
+            run.bp.pixel_begin = static_cast<uint32_t>(pixel_begin);
+            run.bp.pixel_count = std::min<uint32_t>(pixels_per_chunk, job_pixels - run.bp.pixel_begin);
+            run.bp.sample_begin = run.sample_begin;
+            run.bp.sample_count = std::min(samples_per_batch, ro.spp - run.sample_begin);
+            const uint64_t nslots = static_cast<uint64_t>(run.bp.pixel_count) * run.bp.sample_count;
+            for (int ch = 0; ch < 3; ++ch)
+                check(cudaMemsetAsync(ar.radiance + static_cast<uint64_t>(ch) * capacity, 0, nslots * sizeof(float), la.stream));
+            check(cudaMemsetAsync(ar.counters, 0, kCountersPerBatchBytes, la.stream)); // queue lengths + work counters
+            launch(kClassPrimary, [&] { LaunchPrimary(la, c->scene, run.bp, ar.queue[0], ar.radiance, capacity, ar.counters); });
+            run.in_batch = true;
+            run.depth = 1;
+            run.which = 0;
+            return true;
+        }
+        const uint32_t depth = run.depth;
+        auto finish_batch = [&] {
+            launch(kClassOther, [&] { LaunchResolve(la, run.bp, ar.radiance, capacity, c->accum.ptr); });
+            run.in_batch = false;
+            run.sample_begin += run.bp.sample_count;
+            if (run.sample_begin >= ro.spp) {
+                run.sample_begin = 0;
+                ++run.chunk;
+            }
+        };
+        if (depth > 1) launch(kClassOther, [&] { LaunchResetCounters(la, ar.counters, run.which ^ 1, true); });
+        launch(kClassShade, [&] {
+            LaunchShade(la, c->scene, run.bp, depth, ar.queue[run.which], run.which, ar.queue[run.which ^ 1], ar.shadow, ar.radiance,
+                        ar.counters, capacity);
+        });
+        run.which ^= 1;
+        // One traversal launch per bounce: closest hits of the survivors (queue `which`) + occlusion of the NEE rays.
+        auto trace = [&](int extend_queue) {
+            launch(kClassExtend, [&] {
+                LaunchTrace(la, c->scene, run.bp, depth, ar.queue[run.which], extend_queue, ar.shadow, ar.radiance, capacity, ar.counters);
+            });
+        };
+        if (depth >= max_rounds) {
+            if (c->shadow_per_vertex > 0) trace(-1); // only the NEE rays of the last vertex are left
+            finish_batch();
+            return true;
+        }
+        if (depth >= kFirstPollDepth) {
+            // Survivor count, polled with a lag: the count written by the shade kernel of round d is read while issuing
+            // round d + kPollLag, when the copy has long completed, so the host never waits for the GPU to drain.  The
+            // rounds issued in between on an empty queue are no-op launches.
+            if (depth >= kFirstPollDepth + kPollLag) {
+                const uint32_t old = (depth - kPollLag) % kPollRing;
+                check(cudaEventSynchronize(ar.poll_event[old]));
+                if (ar.poll_count[old] == 0) { // every ray of the rounds since then has been traced already
+                    finish_batch();
+                    return true;
+                }
+            }
+            const uint32_t cur = depth % kPollRing;
+            check(cudaMemcpyAsync(ar.poll_count + cur, &ar.counters->queue[run.which], sizeof(uint32_t), cudaMemcpyDeviceToHost, la.stream));
+            check(cudaEventRecord(ar.poll_event[cur], la.stream));
+        }
+        trace(run.which);
+        ++run.depth;
+        return true;
+    };
+    for (bool any = true; any;) {
+        any = false;
+        for (int a = 0; a < S; ++a) any = advance(a) || any;
+    }
+    if (issue_error != cudaSuccess) return c->CudaFail(issue_error, "wavefront issue");
+    if (S > 1)
+        for (int a = 0; a < S; ++a) {
+            CU_CHECK(c, cudaEventRecord(c->arenas[a].done, runs[a].stream));
+            CU_CHECK(c, cudaStreamWaitEvent(stream, c->arenas[a].done, 0));
+        }
+    auto launch = [&](int cls, auto &&fn) {
+        ++launches;
+        ++c->class_launches[cls];
+        fn();
+    };
     launch(kClassOther, [&] { LaunchFinalize(lc, bp, local_pixels, c->accum.ptr, frame_dev, tiles_dev); });
     CU_CHECK(c, cudaEventRecord(c->ev_end, stream));
     CU_CHECK(c, cudaGetLastError());
@@ -450,7 +559,16 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     uint64_t capacity = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : kDefaultPathsInFlight;
     capacity = std::max<uint64_t>(capacity, 1024);
     c->max_capacity = std::min<uint64_t>(capacity, 1ull << 28);
-    if ((e = c->counters.Alloc(1)) != cudaSuccess) return c->CudaFail(e, "cudaMalloc counters");
+    c->num_arenas = env_int("B200PT_ARENAS", c->num_arenas, 1, kMaxArenas);
+    if ((e = c->counters.Alloc(kMaxArenas)) != cudaSuccess) return c->CudaFail(e, "cudaMalloc counters");
+    for (Arena &a : c->arenas) {
+        if ((e = cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking)) != cudaSuccess) return c->CudaFail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");
+        for (cudaEvent_t &pe : a.poll_event)
+            if ((e = cudaEventCreateWithFlags(&pe, cudaEventDisableTiming)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");
+        if ((e = cudaMallocHost(&a.poll_count, sizeof(uint32_t) * kPollRing)) != cudaSuccess) return c->CudaFail(e, "cudaMallocHost");
+    }
+    if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");
     if ((e = cudaMallocHost(&c->pinned_count, sizeof(uint32_t))) != cudaSuccess) return c->CudaFail(e, "cudaMallocHost");
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return c->CudaFail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");
@@ -526,8 +644,15 @@ int b200pt_get_stats(b200pt_handle h, b200pt_stats *out) {
         float ms = 0.0f;
         CU_CHECK(h, cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end));
         h->stats.render_ms = ms;
-        Counters host_counters;
-        CU_CHECK(h, cudaMemcpy(&host_counters, h->counters.ptr, sizeof(Counters), cudaMemcpyDeviceToHost));
+        Counters per_arena[kMaxArenas];
+        CU_CHECK(h, cudaMemcpy(per_arena, h->counters.ptr, sizeof(per_arena), cudaMemcpyDeviceToHost));
+        Counters host_counters = per_arena[0];
+        for (int a = 1; a < kMaxArenas; ++a)
+            for (int k = 0; k < 3; ++k) {
+                host_counters.cls[k].rays += per_arena[a].cls[k].rays;
+                host_counters.cls[k].node_visits += per_arena[a].cls[k].node_visits;
+                host_counters.cls[k].prim_tests += per_arena[a].cls[k].prim_tests;
+            }
         b200pt_kernel_stats *ks[kNumClasses] = {&h->stats.primary, &h->stats.extend, &h->stats.shadow, &h->stats.shade, &h->stats.other};
         for (int k = 0; k < kNumClasses; ++k) {
             *ks[k] = b200pt_kernel_stats{};

@@ -19,6 +19,9 @@ namespace b200pt {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef B200PT_TRACE_MIN_CTAS
+#define B200PT_TRACE_MIN_CTAS 4   // resident CTAs per SM the traversal kernels are compiled for (register cap = 65536 / 256 / this)
+#endif
 
 __device__ __forceinline__ uint32_t SmemAddr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -85,7 +88,7 @@ __device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounter
 // k_primary: camera-ray generation (renderer.cpp:62-75) fused with the first closest hit.
 // ---------------------------------------------------------------------------------------------
 template <bool STATS, bool OPACITY, bool TOP>
-__global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ DeviceScene scene,
+__global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(const __grid_constant__ DeviceScene scene,
                                                       const __grid_constant__ BatchParams bp, PathQueue q,
                                                       float *radiance, uint32_t capacity, Counters *counters, int max_top,
                                                       int refill, int min_inner) {
@@ -154,7 +157,7 @@ __device__ __forceinline__ uint3 SlotCounter(const BatchParams &bp, uint32_t slo
 }
 
 template <bool STATS, bool OPACITY, bool TOP>
-__global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ DeviceScene scene,
+__global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const __grid_constant__ DeviceScene scene,
                                                     const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue q, int which,
                                                     ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters,
                                                     int max_top, int refill, int min_inner) {
@@ -180,8 +183,9 @@ __global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ Devi
             ray->d = mk3(sq.dx[j], sq.dy[j], sq.dz[j]);
             ray->tmax = sq.tmax[j];
             *any = true;
-            // several NEE rays of one vertex (one per emitter) share (pixel, sample, depth): the queue index separates them
-            if (OPACITY) *ctr = SlotCounter(bp, sq.slot[j], depth), ctr->y ^= j * 0x9e3779b9u;
+            // several NEE rays of one vertex (one per emitter) share (pixel, sample, depth): the bits of the ray itself
+            // separate them (the queue position would not be reproducible from run to run)
+            if (OPACITY) *ctr = SlotCounter(bp, sq.slot[j], depth), ctr->y ^= (__float_as_uint(ray->tmax) ^ __float_as_uint(ray->d.x) * 0x85ebca6bu) * 0x9e3779b9u;
         }
         return true;
     };
