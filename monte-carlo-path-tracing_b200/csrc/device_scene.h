@@ -122,7 +122,7 @@ struct DIntegrator {
     uint32_t num_emitters, num_area_lights;
     uint32_t id_sun, id_envmap;
     uint32_t has_opacity;        // some instance's BSDF carries an opacity texture: traversal runs its alpha-test variant
-    uint32_t pad;
+    uint32_t shade_bins;         // bit b set: shading bin b (= b200pt_bsdf_type) is in use; 0 = the scene is not binned
 };
 
 // Everything the kernels dereference.  Passed by value as a kernel parameter.
@@ -130,6 +130,7 @@ struct DeviceScene {
     const BvhNode *nodes;        uint32_t num_nodes;
     const TriVerts *tri_verts;   uint32_t num_tris;
     const TriShade *tri_shade;
+    const uint8_t *tri_bsdf_type; // per triangle: b200pt_bsdf_type of its instance's BSDF (0 = none), the shading bin of a hit
     const AnalyticPrim *analytic; uint32_t num_analytic;
     const DInstance *instances;  uint32_t num_instances;
     const DBsdf *bsdfs;          uint32_t num_bsdfs;

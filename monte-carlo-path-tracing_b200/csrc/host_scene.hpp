@@ -14,6 +14,7 @@ struct HostScene {
     std::vector<BvhNode> nodes;
     std::vector<TriVerts> tri_verts;
     std::vector<TriShade> tri_shade;
+    std::vector<uint8_t> tri_bsdf_type;
     std::vector<AnalyticPrim> analytic;
     std::vector<DInstance> instances;
     std::vector<DBsdf> bsdfs;

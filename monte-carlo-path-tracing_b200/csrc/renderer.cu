@@ -66,6 +66,7 @@ struct Arena {
     PathQueue queue[2]{};
     ShadowQueue shadow{};
     float *radiance = nullptr;       // 3 planes of `capacity` floats
+    uint32_t *bin_lists = nullptr;   // shading bins (scenes with several BSDF models): `capacity` entries per bin in use
     Counters *counters = nullptr;
     cudaStream_t stream = nullptr;   // owned side stream (a single-arena render runs on the caller's stream instead)
     cudaEvent_t done = nullptr;
@@ -84,6 +85,7 @@ struct b200pt_context {
     DeviceArray<BvhNode> nodes;
     DeviceArray<TriVerts> tri_verts;
     DeviceArray<TriShade> tri_shade;
+    DeviceArray<uint8_t> tri_bsdf_type;
     DeviceArray<AnalyticPrim> analytic;
     DeviceArray<DInstance> instances;
     DeviceArray<DBsdf> bsdfs;
@@ -96,6 +98,7 @@ struct b200pt_context {
     DeviceArray<float> cull_boxes;
     DeviceArray<uint32_t> tile_flags, tile_list; // visibility pre-pass: per local tile flag; ascending active list + count
     bool tile_cull = true;        // B200PT_TILE_CULL=0 turns the pre-pass off
+    int shade_only = -1;          // see LaunchConfig::shade_only
 
     // wavefront state: up to kMaxArenas independent batches in flight, each with private queues, counters and stream,
     // so that the latency-bound tail of one batch's launches is filled by another batch's work
@@ -104,7 +107,7 @@ struct b200pt_context {
     uint32_t shadow_per_vertex = 1;
     DeviceArray<float> wave;      // one allocation carved into the arenas' SoA queues
     Arena arenas[kMaxArenas];
-    int num_arenas = 2;           // B200PT_ARENAS (profiles/r01_sweep_arenas_occupancy.log: 2 is best on Dragon, 4 on matpreview)
+    int num_arenas = 0;           // B200PT_ARENAS; 0 = automatic (profiles/r01_sweep_arenas_occupancy.log: 2 is best on Dragon, 4 on matpreview)
     DeviceArray<Counters> counters; // one per arena
     DeviceArray<float> accum;     // per local pixel RGB sums
     DeviceArray<float> frame;     // staging for b200pt_render (host frame)
@@ -174,6 +177,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     CU_CHECK(c, c->nodes.Upload(h.nodes));
     CU_CHECK(c, c->tri_verts.Upload(h.tri_verts));
     CU_CHECK(c, c->tri_shade.Upload(h.tri_shade));
+    CU_CHECK(c, c->tri_bsdf_type.Upload(h.tri_bsdf_type));
     CU_CHECK(c, c->analytic.Upload(h.analytic));
     CU_CHECK(c, c->instances.Upload(h.instances));
     CU_CHECK(c, c->bsdfs.Upload(h.bsdfs));
@@ -196,6 +200,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     s.nodes = c->nodes.ptr, s.num_nodes = static_cast<uint32_t>(h.nodes.size());
     s.tri_verts = c->tri_verts.ptr, s.num_tris = static_cast<uint32_t>(h.tri_verts.size());
     s.tri_shade = c->tri_shade.ptr;
+    s.tri_bsdf_type = c->tri_bsdf_type.ptr;
     s.analytic = c->analytic.ptr, s.num_analytic = static_cast<uint32_t>(h.analytic.size());
     s.instances = c->instances.ptr, s.num_instances = static_cast<uint32_t>(h.instances.size());
     s.bsdfs = c->bsdfs.ptr, s.num_bsdfs = static_cast<uint32_t>(h.bsdfs.size());
@@ -212,6 +217,20 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     s.cull_boxes = c->cull_boxes.ptr, s.num_cull_boxes = static_cast<uint32_t>(h.cull_boxes.size() / 6);
     s.integrator = h.integrator;
 
+    // One BSDF type on every scattering surface (area lights and BSDF-less surfaces aside)?  Then the shading kernel
+    // specialised to it runs.
+    {
+        int only = -1;
+        bool mixed = false;
+        for (const DInstance &in : h.instances) {
+            if (in.id_bsdf == kInvalid) continue;
+            const int type = static_cast<int>(h.bsdfs[in.id_bsdf].type);
+            if (type == B200PT_BSDF_AREA_LIGHT) continue;
+            if (only >= 0 && only != type) mixed = true;
+            only = type;
+        }
+        c->shade_only = (mixed || getenv("B200PT_GENERIC_SHADE")) ? -1 : only;
+    }
     c->stats.num_bvh_nodes = h.nodes.size();
     c->stats.num_triangles = h.tri_verts.size();
     c->stats.num_prims = h.tri_verts.size() + h.analytic.size();
@@ -228,7 +247,7 @@ uint64_t WordsPerSlot(const b200pt_context *c) {
     const bool vol = c->scene.integrator.type == B200PT_INTEGRATOR_VOLPATH;
     const uint32_t shadow_per_vertex = c->scene.integrator.num_emitters + (c->scene.integrator.num_area_lights ? 1u : 0u);
     const uint64_t words_per_queue = 11 + (vol ? 4 : 0) + 4; // 10 floats + slot (+ medium, wo) + HitRec
-    return 2 * words_per_queue + 11 * std::max(1u, shadow_per_vertex) + 3;
+    return 2 * words_per_queue + 11 * std::max(1u, shadow_per_vertex) + 3 + __builtin_popcount(c->scene.integrator.shade_bins);
 }
 
 // Carve the SoA queues of `arenas` arenas out of one allocation; each arena gets `wanted_per_arena` sample slots, or
@@ -277,6 +296,8 @@ int CarveWavefront(b200pt_context *c, uint64_t wanted_per_arena, int arenas) {
         sq.cr = take(shadow_cap), sq.cg = take(shadow_cap), sq.cb = take(shadow_cap);
         sq.slot = reinterpret_cast<uint32_t *>(take(shadow_cap));
         ar.radiance = take(3 * capacity);
+        const int bins_in_use = __builtin_popcount(c->scene.integrator.shade_bins);
+        ar.bin_lists = bins_in_use ? reinterpret_cast<uint32_t *>(take(static_cast<uint64_t>(bins_in_use) * capacity)) : nullptr;
         ar.counters = c->counters.ptr + a;
     }
     c->capacity = capacity;
@@ -334,6 +355,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     lc.refill = c->refill;
     lc.min_inner = c->min_inner;
     lc.blocks = c->num_sms * c->ctas_per_sm;
+    lc.shade_only = c->shade_only;
 
     uint64_t launches = 0;
     c->timed.clear();
@@ -368,7 +390,9 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     // in flight hide the tail of every launch — a traversal launch cannot end before its slowest ray (~0.2 ms on Dragon,
     // at every bounce) — behind another batch's work.  Per-class event timing needs serial launches: one arena then.
     const uint64_t job_slots = static_cast<uint64_t>(job_pixels) * ro.spp;
-    const int S = (ro.timing || job_slots < (1ull << 21)) ? 1 : std::max(1, std::min(c->num_arenas, kMaxArenas));
+    // Binned scenes launch one (often small) shading kernel per BSDF model and bounce: more batches in flight pay off there.
+    const int arenas_wanted = c->num_arenas > 0 ? c->num_arenas : (ig.shade_bins ? 4 : 2);
+    const int S = (ro.timing || job_slots < (1ull << 21)) ? 1 : std::max(1, std::min(arenas_wanted, kMaxArenas));
     {
         const uint64_t total = std::min<uint64_t>(c->max_capacity, std::max<uint64_t>(job_slots, 1024));
         const int rc = CarveWavefront(c, (total + S - 1) / S, S);
@@ -408,6 +432,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         Run &run = runs[a];
         LaunchConfig la = lc;
         la.stream = run.stream;
+        const ShadeBins bins{ar.bin_lists, capacity};
         auto launch = [&](int cls, auto &&fn) { // one kernel launch, counted (and, with B200PT_STATS_TIMING, event-timed) under its class
             ++launches;
             ++c->class_launches[cls];
@@ -435,7 +460,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
             for (int ch = 0; ch < 3; ++ch)
                 check(cudaMemsetAsync(ar.radiance + static_cast<uint64_t>(ch) * capacity, 0, nslots * sizeof(float), la.stream));
             check(cudaMemsetAsync(ar.counters, 0, kCountersPerBatchBytes, la.stream)); // queue lengths + work counters
-            launch(kClassPrimary, [&] { LaunchPrimary(la, c->scene, run.bp, ar.queue[0], ar.radiance, capacity, ar.counters); });
+            launch(kClassPrimary, [&] { LaunchPrimary(la, c->scene, run.bp, ar.queue[0], bins, ar.radiance, capacity, ar.counters); });
             run.in_batch = true;
             run.depth = 1;
             run.which = 0;
@@ -453,14 +478,16 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         };
         if (depth > 1) launch(kClassOther, [&] { LaunchResetCounters(la, ar.counters, run.which ^ 1, true); });
         launch(kClassShade, [&] {
-            LaunchShade(la, c->scene, run.bp, depth, ar.queue[run.which], run.which, ar.queue[run.which ^ 1], ar.shadow, ar.radiance,
-                        ar.counters, capacity);
+            const int n = LaunchShade(la, c->scene, run.bp, depth, ar.queue[run.which], run.which, ar.queue[run.which ^ 1], bins, ar.shadow,
+                                      ar.radiance, ar.counters, capacity);
+            launches += n - 1;
+            c->class_launches[kClassShade] += n - 1;
         });
         run.which ^= 1;
         // One traversal launch per bounce: closest hits of the survivors (queue `which`) + occlusion of the NEE rays.
         auto trace = [&](int extend_queue) {
             launch(kClassExtend, [&] {
-                LaunchTrace(la, c->scene, run.bp, depth, ar.queue[run.which], extend_queue, ar.shadow, ar.radiance, capacity, ar.counters);
+                LaunchTrace(la, c->scene, run.bp, depth, ar.queue[run.which], extend_queue, bins, ar.shadow, ar.radiance, capacity, ar.counters);
             });
         };
         if (depth >= max_rounds) {
@@ -559,7 +586,7 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     uint64_t capacity = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : kDefaultPathsInFlight;
     capacity = std::max<uint64_t>(capacity, 1024);
     c->max_capacity = std::min<uint64_t>(capacity, 1ull << 28);
-    c->num_arenas = env_int("B200PT_ARENAS", c->num_arenas, 1, kMaxArenas);
+    c->num_arenas = env_int("B200PT_ARENAS", c->num_arenas, 0, kMaxArenas);
     if ((e = c->counters.Alloc(kMaxArenas)) != cudaSuccess) return c->CudaFail(e, "cudaMalloc counters");
     for (Arena &a : c->arenas) {
         if ((e = cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking)) != cudaSuccess) return c->CudaFail(e, "cudaStreamCreate");

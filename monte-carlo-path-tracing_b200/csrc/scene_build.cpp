@@ -1074,6 +1074,20 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, HostScen
     ig.num_area_lights = static_cast<uint32_t>(hs->map_area_light_instance.size());
     ig.id_sun = id_sun;
     ig.id_envmap = id_envmap;
+    // Shading bins: with two or more BSDF models in the scene, hits are filed by model and shaded model by model.
+    {
+        uint32_t bins = 0, models = 0;
+        for (const DInstance &in : hs->instances) bins |= 1u << (in.id_bsdf == kInvalid ? 0u : hs->bsdfs[in.id_bsdf].type);
+        for (uint32_t t = B200PT_BSDF_DIFFUSE; t <= B200PT_BSDF_PLASTIC; ++t) models += (bins >> t) & 1u;
+        // escaped rays still need shading when an environment map lights them or a medium may scatter them first
+        if (id_envmap != kInvalid || ig.type == B200PT_INTEGRATOR_VOLPATH) bins |= 1u;
+        ig.shade_bins = models >= 2 ? bins : 0u;
+        hs->tri_bsdf_type.resize(hs->tri_shade.size());
+        for (size_t i = 0; i < hs->tri_shade.size(); ++i) {
+            const uint32_t id_bsdf = hs->instances[hs->tri_shade[i].inst].id_bsdf;
+            hs->tri_bsdf_type[i] = static_cast<uint8_t>(id_bsdf == kInvalid ? 0u : hs->bsdfs[id_bsdf].type);
+        }
+    }
     ig.has_opacity = 0;
     for (const DInstance &in : hs->instances)
         if (in.id_bsdf != kInvalid && hs->bsdfs[in.id_bsdf].id_opacity != kInvalid) ig.has_opacity = 1;

@@ -712,8 +712,14 @@ __device__ __forceinline__ void EvaluatePlastic(const DeviceScene &s, const DBsd
 }
 
 // bsdf.cpp:188-236 — kAreaLight has no case: the record stays invalid.
+// ONLY >= 0 specialises a shading kernel to ONE BSDF type (the queue entries it is given are binned by the type of the
+// surface they hit, wavefront.cu): the other models are not compiled in, which keeps the code a warp runs through short
+// and contiguous (the generic kernel is 0.7 MB of code and stalls on instruction fetch when lanes scatter over it).
+constexpr int kAnyBsdf = -1;
+
+template <int ONLY>
 __device__ __forceinline__ void BsdfSample(const DeviceScene &s, const DBsdf &d, Rng &rng, BsdfRec *rec) {
-    switch (d.type) {
+    switch (ONLY == kAnyBsdf ? d.type : static_cast<uint32_t>(ONLY)) {
     case B200PT_BSDF_DIFFUSE: SampleDiffuse(s, d, rng, rec); break;
     case B200PT_BSDF_ROUGH_DIFFUSE: SampleRoughDiffuse(s, d, rng, rec); break;
     case B200PT_BSDF_CONDUCTOR: SampleConductor(s, d, rng, rec); break;
@@ -722,8 +728,9 @@ __device__ __forceinline__ void BsdfSample(const DeviceScene &s, const DBsdf &d,
     case B200PT_BSDF_PLASTIC: SamplePlastic(s, d, rng, rec); break;
     }
 }
+template <int ONLY>
 __device__ __forceinline__ void BsdfEvaluate(const DeviceScene &s, const DBsdf &d, BsdfRec *rec) {
-    switch (d.type) {
+    switch (ONLY == kAnyBsdf ? d.type : static_cast<uint32_t>(ONLY)) {
     case B200PT_BSDF_DIFFUSE: EvaluateDiffuse(s, d, rec); break;
     case B200PT_BSDF_ROUGH_DIFFUSE: EvaluateRoughDiffuse(s, d, rec); break;
     case B200PT_BSDF_CONDUCTOR: EvaluateConductor(s, d, rec); break;
@@ -734,6 +741,7 @@ __device__ __forceinline__ void BsdfEvaluate(const DeviceScene &s, const DBsdf &
 }
 
 // path.cpp:238-266
+template <int ONLY>
 __device__ __forceinline__ BsdfRec EvaluateRayPath(const DeviceScene &s, V3 wi, V3 wo, const Surf &hit, const DBsdf *bsdf) {
     BsdfRec rec;
     rec.wi = wi, rec.wo = wo, rec.uv = hit.uv, rec.pos = hit.pos;
@@ -744,7 +752,7 @@ __device__ __forceinline__ BsdfRec EvaluateRayPath(const DeviceScene &s, V3 wi, 
             rec.inside = !rec.inside;
             rec.n = -rec.n;
         }
-        BsdfEvaluate(s, *bsdf, &rec);
+        BsdfEvaluate<ONLY>(s, *bsdf, &rec);
     } else {
         rec.pdf = 1;
         rec.att = mk3(1.0f);
@@ -753,6 +761,7 @@ __device__ __forceinline__ BsdfRec EvaluateRayPath(const DeviceScene &s, V3 wi, 
     return rec;
 }
 // path.cpp:268-296
+template <int ONLY>
 __device__ __forceinline__ BsdfRec SampleRayPath(const DeviceScene &s, V3 wo, const Surf &hit, const DBsdf *bsdf, Rng &rng) {
     BsdfRec rec;
     rec.wo = wo, rec.uv = hit.uv, rec.pos = hit.pos;
@@ -763,7 +772,7 @@ __device__ __forceinline__ BsdfRec SampleRayPath(const DeviceScene &s, V3 wo, co
             rec.inside = !rec.inside;
             rec.n = -rec.n;
         }
-        BsdfSample(s, *bsdf, rng, &rec);
+        BsdfSample<ONLY>(s, *bsdf, rng, &rec);
     } else {
         rec.wi = wo;
         rec.pdf = 1.0f;

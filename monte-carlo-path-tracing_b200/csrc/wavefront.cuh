@@ -39,6 +39,21 @@ struct ShadowQueue {
     uint32_t *slot;
 };
 
+// Shading bins: a closest hit is filed under the BSDF model of the surface it found (bin = b200pt_bsdf_type; 0 = escaped
+// ray or BSDF-less surface, 1 = area light), so that each shading launch runs ONE model (DeviceScene::integrator.shade_bins).
+constexpr int kNumShadeBins = 8;
+struct ShadeBins {
+    uint32_t *lists;          // one list of queue positions per bin in use, `capacity` entries each; nullptr = no binning
+    uint32_t capacity;
+};
+__host__ __device__ inline uint32_t BinListIndex(uint32_t bins_in_use, uint32_t bin) {
+#if defined(__CUDA_ARCH__)
+    return __popc(bins_in_use & ((1u << bin) - 1u));
+#else
+    return static_cast<uint32_t>(__builtin_popcount(bins_in_use & ((1u << bin) - 1u)));
+#endif
+}
+
 enum KernelClass { kClassPrimary = 0, kClassExtend = 1, kClassShadow = 2, kClassShade = 3, kClassOther = 4, kNumClasses = 5 };
 
 struct ClassCounters {
@@ -51,9 +66,10 @@ struct Counters {             // device-resident
     uint32_t work_primary;    // next unclaimed ray of the persistent traversal loops
     uint32_t work_trace;
     uint32_t pad[3];
+    uint32_t bin_count[2][kNumShadeBins]; // entries of path queue 0 / 1 per shading bin (scenes with several BSDF models)
     ClassCounters cls[3];     // primary / extend / shadow traversal statistics (zeroed per render)
 };
-constexpr size_t kCountersPerBatchBytes = 32; // the part of Counters that is zeroed for every batch
+constexpr size_t kCountersPerBatchBytes = 32 + 2 * kNumShadeBins * sizeof(uint32_t); // the part of Counters that is zeroed for every batch
 
 struct BatchParams {
     DCamera camera;
@@ -95,17 +111,19 @@ struct LaunchConfig {
     int top_nodes;            // BVH nodes staged in shared memory per CTA (64 B each)
     int refill;               // idle lanes per warp that trigger a ray refill in the traversal loops
     int min_inner;            // lanes still walking inner nodes below which a warp switches to its pending leaves
+    int shade_only;           // the one BSDF type every scattering surface of the scene has, or -1 (generic shading kernel)
 };
 
 // kernel launchers (wavefront.cu)
-void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, float *radiance,
-                   uint32_t capacity, Counters *counters);
+void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, ShadeBins bins,
+                   float *radiance, uint32_t capacity, Counters *counters);
 // `depth` = index of the path vertex the rays leave from: with `bp` it keys the alpha-test random numbers (opacity masks).
 // which < 0: no closest-hit rays this round (last bounce), only the NEE rays.
 void LaunchTrace(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
-                 ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters);
-void LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
-                 int which_in, PathQueue qout, ShadowQueue sq, float *radiance, Counters *counters, uint32_t capacity);
+                 ShadeBins bins, ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters);
+// One launch per shading bin in use (or a single launch when the scene is not binned); returns the number of launches.
+int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
+                int which_in, PathQueue qout, ShadeBins bins, ShadowQueue sq, float *radiance, Counters *counters, uint32_t capacity);
 // Visibility pre-pass: flags[t] = 1 if local tile t can see one of the scene's cull boxes, then the ascending list of
 // such tiles in list[0 .. count) with count stored at list[num_local_tiles].
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
