@@ -460,7 +460,11 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
             for (int ch = 0; ch < 3; ++ch)
                 check(cudaMemsetAsync(ar.radiance + static_cast<uint64_t>(ch) * capacity, 0, nslots * sizeof(float), la.stream));
             check(cudaMemsetAsync(ar.counters, 0, kCountersPerBatchBytes, la.stream)); // queue lengths + work counters
-            launch(kClassPrimary, [&] { LaunchPrimary(la, c->scene, run.bp, ar.queue[0], bins, ar.radiance, capacity, ar.counters); });
+            launch(kClassPrimary, [&] {
+                const int n = LaunchPrimary(la, c->scene, run.bp, ar.queue[0], bins, ar.radiance, capacity, ar.counters);
+                launches += n - 1;
+                c->class_launches[kClassPrimary] += n - 1;
+            });
             run.in_batch = true;
             run.depth = 1;
             run.which = 0;
@@ -487,7 +491,9 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         // One traversal launch per bounce: closest hits of the survivors (queue `which`) + occlusion of the NEE rays.
         auto trace = [&](int extend_queue) {
             launch(kClassExtend, [&] {
-                LaunchTrace(la, c->scene, run.bp, depth, ar.queue[run.which], extend_queue, bins, ar.shadow, ar.radiance, capacity, ar.counters);
+                const int n = LaunchTrace(la, c->scene, run.bp, depth, ar.queue[run.which], extend_queue, bins, ar.shadow, ar.radiance, capacity, ar.counters);
+                launches += n - 1;
+                c->class_launches[kClassExtend] += n - 1;
             });
         };
         if (depth >= max_rounds) {

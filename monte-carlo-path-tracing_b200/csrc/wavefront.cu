@@ -56,25 +56,41 @@ __device__ __forceinline__ int StageTopNodes(const DeviceScene &scene, float4 *t
     return num_top;
 }
 
-// Files queue position `i` under the shading bin of its closest hit.  Callable from divergent code: the lanes that are
-// here together and share a bin reserve their list slots with one atomic.
-__device__ __forceinline__ void AppendToShadeBin(const DeviceScene &scene, ShadeBins bins, uint32_t *bin_count, const HitRec &hit, uint32_t i) {
-    const uint32_t in_use = scene.integrator.shade_bins;
-    uint32_t bin = 0;
-    if (hit.prim == kPrimMiss) {
-        if (!(in_use & 1u)) return; // an escaped ray with nothing left to do (no environment map, no medium)
-    } else if (hit.prim & kPrimAnalyticBit) {
-        const uint32_t id_bsdf = scene.instances[scene.analytic[hit.prim & ~kPrimAnalyticBit].inst].id_bsdf;
-        bin = id_bsdf == kInvalid ? 0u : scene.bsdfs[id_bsdf].type;
-    } else {
-        bin = __ldg(scene.tri_bsdf_type + (hit.prim & kPrimIndexMask));
+// Shading bin of a closest-hit record (bin = BSDF model of the surface; 0 = escaped / BSDF-less, 1 = area light).
+__device__ __forceinline__ uint32_t ShadeBinOfHit(const DeviceScene &scene, uint32_t prim) {
+    if (prim == kPrimMiss) return 0u;
+    if (prim & kPrimAnalyticBit) {
+        const uint32_t id_bsdf = scene.instances[scene.analytic[prim & ~kPrimAnalyticBit].inst].id_bsdf;
+        return id_bsdf == kInvalid ? 0u : scene.bsdfs[id_bsdf].type;
     }
-    const unsigned peers = __match_any_sync(__activemask(), bin);
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(bin_count + bin, __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    bins.lists[static_cast<uint64_t>(BinListIndex(in_use, bin)) * bins.capacity + base + __popc(peers & ((1u << lane) - 1u))] = i;
+    return __ldg(scene.tri_bsdf_type + (prim & kPrimIndexMask));
+}
+
+// k_bin_hits: files every entry of a freshly traced path queue under the shading bin of its closest hit (one coalesced
+// pass over the hit records, one atomic per warp and bin).  Doing this inside the traversal kernels costs one atomic
+// per RAY, because rays finish one lane at a time there (volumetric-caustic: +50 % traversal time).
+__global__ void __launch_bounds__(kThreads) k_bin_hits(const __grid_constant__ DeviceScene scene, const HitRec *hits, int which,
+                                                       ShadeBins bins, Counters *counters) {
+    const uint32_t n = counters->queue[which];
+    const uint32_t in_use = scene.integrator.shade_bins;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = tid - lane; i0 < n; i0 += stride) {
+        const uint32_t i = i0 + lane;
+        uint32_t bin = kNumShadeBins; // none
+        if (i < n) {
+            const uint32_t prim = hits[i].prim;
+            // an escaped ray with nothing left to do (no environment map, no medium) is dropped here
+            if (prim != kPrimMiss || (in_use & 1u)) bin = ShadeBinOfHit(scene, prim);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin == kNumShadeBins) continue;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (static_cast<int>(lane) == leader) base = atomicAdd(&counters->bin_count[which][bin], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        bins.lists[static_cast<uint64_t>(BinListIndex(in_use, bin)) * bins.capacity + base + __popc(peers & ((1u << lane) - 1u))] = i;
+    }
 }
 
 __device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounters &tc, uint32_t rays, int cls, Counters *c) {
@@ -98,7 +114,7 @@ __device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounter
 // ---------------------------------------------------------------------------------------------
 template <bool STATS, bool OPACITY, bool TOP>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(const __grid_constant__ DeviceScene scene,
-                                                      const __grid_constant__ BatchParams bp, PathQueue q, ShadeBins bins,
+                                                      const __grid_constant__ BatchParams bp, PathQueue q,
                                                       float *radiance, uint32_t capacity, Counters *counters, int max_top,
                                                       int refill, int min_inner) {
     extern __shared__ float4 top[];
@@ -145,7 +161,6 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(con
             q.wx[idx] = -cam.d.x, q.wy[idx] = -cam.d.y, q.wz[idx] = -cam.d.z;
         }
         q.hit[idx] = hit;
-        if (bins.lists != nullptr) AppendToShadeBin(scene, bins, counters->bin_count[0], hit, idx);
     };
     TraversePersistent<false, STATS, OPACITY, TOP>(scene, top, num_top, nslots, &counters->work_primary, refill, min_inner, bp.key, fetch, finish, tc, rays);
     FlushCounters(STATS, tc[0], rays[0], kClassPrimary, counters);
@@ -169,7 +184,7 @@ __device__ __forceinline__ uint3 SlotCounter(const BatchParams &bp, uint32_t slo
 template <bool STATS, bool OPACITY, bool TOP>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const __grid_constant__ DeviceScene scene,
                                                     const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue q, int which,
-                                                    ShadeBins bins, ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters,
+                                                    ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters,
                                                     int max_top, int refill, int min_inner) {
     extern __shared__ float4 top[];
     __shared__ uint64_t bar;
@@ -202,7 +217,6 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const
     auto finish = [&](uint32_t i, const HitRec &hit, bool found, bool any) {
         if (!any) {
             q.hit[i] = hit;
-            if (bins.lists != nullptr) AppendToShadeBin(scene, bins, counters->bin_count[which], hit, i);
         } else if (!found) { // unoccluded: the light sample counts
             const uint32_t j = i - n_extend, slot = sq.slot[j];
             atomicAdd(radiance + slot, sq.cr[j]);
@@ -400,14 +414,20 @@ void EnableSmem(K kernel, size_t bytes) {
         else pick_top(kernel<false, false, true>, kernel<false, false, false>);                                       \
     } while (0)
 
-void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, ShadeBins bins,
+int LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, ShadeBins bins,
                    float *radiance, uint32_t capacity, Counters *counters) {
-    B200PT_LAUNCH_TRAVERSAL(k_primary, scene, bp, q, bins, radiance, capacity, counters);
+    B200PT_LAUNCH_TRAVERSAL(k_primary, scene, bp, q, radiance, capacity, counters);
+    if (bins.lists == nullptr) return 1;
+    k_bin_hits<<<lc.blocks, kThreads, 0, lc.stream>>>(scene, q.hit, 0, bins, counters);
+    return 2;
 }
 
-void LaunchTrace(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
+int LaunchTrace(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
                  ShadeBins bins, ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters) {
-    B200PT_LAUNCH_TRAVERSAL(k_trace, scene, bp, depth, q, which, bins, sq, radiance, capacity, counters);
+    B200PT_LAUNCH_TRAVERSAL(k_trace, scene, bp, depth, q, which, sq, radiance, capacity, counters);
+    if (bins.lists == nullptr || which < 0) return 1;
+    k_bin_hits<<<lc.blocks, kThreads, 0, lc.stream>>>(scene, q.hit, which, bins, counters);
+    return 2;
 }
 
 int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,

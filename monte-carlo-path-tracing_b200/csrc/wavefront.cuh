@@ -115,11 +115,13 @@ struct LaunchConfig {
 };
 
 // kernel launchers (wavefront.cu)
-void LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, ShadeBins bins,
+// LaunchPrimary / LaunchTrace also file the traced queue's hits into the shading bins when `bins.lists` is set (one
+// extra small kernel, k_bin_hits); they return the number of kernels launched.
+int LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, ShadeBins bins,
                    float *radiance, uint32_t capacity, Counters *counters);
 // `depth` = index of the path vertex the rays leave from: with `bp` it keys the alpha-test random numbers (opacity masks).
 // which < 0: no closest-hit rays this round (last bounce), only the NEE rays.
-void LaunchTrace(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
+int LaunchTrace(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
                  ShadeBins bins, ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters);
 // One launch per shading bin in use (or a single launch when the scene is not binned); returns the number of launches.
 int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
