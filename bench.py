@@ -291,10 +291,15 @@ def run_b200(args, workload):
                 "avg_launch_ms": dk["ms"] / max(1, dk["launches"]), "share_of_step": dk["ms"] / timed["render_ms"],
                 "kernels": kernels,
                 "formula": "32 B x child-box tests + 36 B x primitive tests + 52 B x closest-hit rays (SURVEY.md §8d), counted by the kernels themselves"}
-    traffic_file = os.path.join(ROOT, "profiles", "r01_dram_traffic_k_trace.json")
-    if os.path.exists(traffic_file):
+    # DRAM bytes of the dominant kernel from the committed ncu capture of the same frame (tools/gpu_evidence.sh), per launch of
+    # THIS step: the capture's per-frame total over this step's launch count (the capture may run more, smaller launches).
+    traffic_file = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    if os.path.exists(traffic_file) and name == "dragon" and (width, height, spp) == (1024, 1024, 256):
         with open(traffic_file) as f:
-            roofline["traffic"] = json.load(f).get("k_" + dominant)
+            detail = json.load(f).get("k_" + dominant + "_detail")
+        if detail:
+            roofline["traffic"] = (detail["dram_read_bytes_total"] + detail["dram_write_bytes_total"]) / max(1, dk["launches"])
+            roofline["traffic_source"] = "profiles/r01_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over one frame)"
 
     if rank == 0:
         cpu = None

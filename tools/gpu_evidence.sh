@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round evidence run (one gpurun call): GPU tests, both bench arms, ncu launch list, per-kernel DRAM traffic, one --set full capture.
-set -u
+# Only text / compressed CSV travels back (gpurun_out is capped at 64 MiB).
+cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/gpu.txt 2>&1
@@ -14,7 +15,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "== ncu DRAM bytes of every kernel of one frame"
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 120 --csv \
     --log-file $O/dram_one_frame.csv python tools/one_frame.py dragon 1024 1024 256 > $O/one_frame_ncu.log 2>&1
+python tools/dram_traffic.py $O/dram_one_frame.csv $O/dram_traffic.json > $O/dram_traffic.txt 2>&1; cat $O/dram_traffic.txt
 echo "== ncu --set full of the first launches of each kernel"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_(primary|extend|shadow|shade)' -c 8 -f -o $O/full_first8 \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_(primary|trace|shade)' -c 5 -f -o /tmp/full_first5 \
     python tools/one_frame.py dragon 1024 1024 256 > $O/full_ncu.log 2>&1
-ls -la $O
+python tools/ncu_summary.py /tmp/full_first5.ncu-rep > $O/full_first5.txt 2>&1
+ncu -i /tmp/full_first5.ncu-rep --page source --csv --kernel-name regex:k_trace --launch-count 1 2>/dev/null | cut -d, -f1-12 | gzip -9 > $O/k_trace_source.csv.gz
+rm -f $O/*.ncu-rep
+du -sh $O
