@@ -251,6 +251,15 @@ int b200pt_render(b200pt_handle h, const b200pt_render_opts *opts, float *frame_
  * Asynchronous with respect to the host. */
 int b200pt_render_device(b200pt_handle h, const b200pt_render_opts *opts, float *frame_dev, void *stream);
 
+/* Progressive preview: replaces csrt::Renderer::Draw(index_frame, frame, frame_srgb) (renderer.cpp:97-138, 723-746), the
+ * call the reference's GLUT viewer makes once per displayed frame.  ONE sample per pixel with the sub-pixel offset
+ * (VdC_2, VdC_3)(frame_index + 1); frame_dev (DEVICE, width*height*3, row 0 = top) holds the running mean over the frames
+ * rendered so far and is updated in place: frame = (frame_index * frame + min(sample, 1)) / (frame_index + 1);
+ * frame_srgb_dev (DEVICE, may be NULL) receives its sRGB-encoded copy with row 0 at the BOTTOM, as glDrawPixels wants it.
+ * opts->spp is ignored (apps/main.cpp:53-58 forces 1).  Asynchronous with respect to the host. */
+int b200pt_render_progressive_device(b200pt_handle h, const b200pt_render_opts *opts, uint32_t frame_index, float *frame_dev,
+                                     float *frame_srgb_dev, void *stream);
+
 /* Multi-GPU tile path: render this rank's interleaved tiles into
  * a compact DEVICE buffer of b200pt_tile_buffer_floats() floats (equal on every
  * rank, so one all-gather moves it), then scatter the gathered [world][floats]

@@ -69,7 +69,7 @@ class Stats(ctypes.Structure):
 
 # Every symbol include/b200pt.h declares; tests check the library exports all of them.
 EXPORTED_SYMBOLS = [
-    "b200pt_create", "b200pt_destroy", "b200pt_render", "b200pt_render_device", "b200pt_tile_buffer_floats",
+    "b200pt_create", "b200pt_destroy", "b200pt_render", "b200pt_render_device", "b200pt_render_progressive_device", "b200pt_tile_buffer_floats",
     "b200pt_render_tiles_device", "b200pt_assemble_tiles_device", "b200pt_get_stats", "b200pt_last_error",
     "b200pt_get_kulla_conty", "b200pt_get_envmap_tables", "b200pt_scene_load", "b200pt_scene_save",
     "b200pt_scene_get_desc", "b200pt_scene_free",
@@ -93,6 +93,7 @@ def lib():
     L.b200pt_destroy.restype = None
     L.b200pt_render.argtypes = [vp, ctypes.POINTER(RenderOpts), vp]
     L.b200pt_render_device.argtypes = [vp, ctypes.POINTER(RenderOpts), vp, vp]
+    L.b200pt_render_progressive_device.argtypes = [vp, ctypes.POINTER(RenderOpts), u32, vp, vp, vp]
     L.b200pt_tile_buffer_floats.argtypes = [u32, u32, u32]
     L.b200pt_tile_buffer_floats.restype = u64
     L.b200pt_render_tiles_device.argtypes = [vp, ctypes.POINTER(RenderOpts), vp, vp]
@@ -171,6 +172,13 @@ class Renderer:
         """Frame stays in HBM: `frame_tensor` is a CUDA float32 tensor with width*height*3 elements."""
         opts = self._opts(width, height, spp, seed, stats=stats, flags=flags)
         _check(lib().b200pt_render_device(self._h, ctypes.byref(opts), frame_tensor.data_ptr(), stream), self._h)
+
+    def draw_progressive_device(self, frame_tensor, srgb_tensor, frame_index, width=0, height=0, seed=0, stream=None, flags=0):
+        """csrt::Renderer::Draw(index_frame, frame, frame_srgb) (renderer.cpp:723-746): one more sample per pixel into the running
+        mean `frame_tensor` (CUDA float32, width*height*3, updated in place); `srgb_tensor` (or None) gets the bottom-up sRGB copy."""
+        opts = self._opts(width, height, 1, seed, flags=flags)
+        _check(lib().b200pt_render_progressive_device(self._h, ctypes.byref(opts), int(frame_index), frame_tensor.data_ptr(),
+                                                      srgb_tensor.data_ptr() if srgb_tensor is not None else None, stream), self._h)
 
     def draw_tiles_device(self, tiles_tensor, tile_rank, tile_world, width=0, height=0, spp=0, seed=0, stream=None, stats=0, flags=0):
         opts = self._opts(width, height, spp, seed, tile_rank, tile_world, stats, flags)

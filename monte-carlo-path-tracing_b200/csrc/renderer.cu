@@ -308,6 +308,9 @@ struct ResolvedOpts {
     uint32_t width, height, spp, tile_rank, tile_world;
     uint64_t seed;
     bool counters, timing, tile_cull;
+    bool progressive = false;     // b200pt_render_progressive_device: one sample per pixel, running mean into the frame
+    uint32_t frame_index = 0;
+    float *frame_srgb = nullptr;
 };
 
 int ResolveOpts(b200pt_context *c, const b200pt_render_opts *o, ResolvedOpts *r) {
@@ -332,6 +335,18 @@ uint32_t PixelsPerRank(uint32_t width, uint32_t height, uint32_t world) {
     return ((tiles + world - 1) / world) * kTilePixels;
 }
 
+// math.hpp:29-41 (GetVanDerCorputSequence<base>), including its float round trip of the index.
+float VanDerCorputHost(uint32_t base, uint32_t index) {
+    const float base_inv = 1.0f / base;
+    float result = 0.0f, frac = base_inv;
+    while (index > 0) {
+        result += frac * (index % base);
+        index = static_cast<uint32_t>(index * base_inv);
+        frac *= base_inv;
+    }
+    return result;
+}
+
 // The wavefront loop.  Everything is enqueued on `stream`; the host only synchronises to poll the
 // survivor count once RR is active (every 4 rounds), so shallow scenes run without host round trips.
 int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, float *tiles_dev, cudaStream_t stream) {
@@ -345,6 +360,11 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     bp.num_tiles = bp.tiles_x * ((ro.height + kTileSize - 1) / kTileSize);
     bp.tile_rank = ro.tile_rank, bp.tile_world = ro.tile_world;
     const uint32_t local_pixels = PixelsPerRank(ro.width, ro.height, ro.tile_world);
+    if (ro.progressive) {
+        bp.progressive = 1;
+        bp.progressive_u = VanDerCorputHost(2, ro.frame_index + 1);
+        bp.progressive_v = VanDerCorputHost(3, ro.frame_index + 1);
+    }
 
     if (c->accum.count < 3ull * local_pixels) CU_CHECK(c, c->accum.Alloc(3ull * local_pixels));
     LaunchConfig lc;
@@ -454,7 +474,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
             if (pixel_begin >= job_pixels) return false;
             run.bp.pixel_begin = static_cast<uint32_t>(pixel_begin);
             run.bp.pixel_count = std::min<uint32_t>(pixels_per_chunk, job_pixels - run.bp.pixel_begin);
-            run.bp.sample_begin = run.sample_begin;
+            run.bp.sample_begin = run.sample_begin + (ro.progressive ? ro.frame_index : 0u);
             run.bp.sample_count = std::min(samples_per_batch, ro.spp - run.sample_begin);
             const uint64_t nslots = static_cast<uint64_t>(run.bp.pixel_count) * run.bp.sample_count;
             for (int ch = 0; ch < 3; ++ch)
@@ -536,7 +556,10 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         ++c->class_launches[cls];
         fn();
     };
-    launch(kClassOther, [&] { LaunchFinalize(lc, bp, local_pixels, c->accum.ptr, frame_dev, tiles_dev); });
+    if (ro.progressive)
+        launch(kClassOther, [&] { LaunchFinalizeProgressive(lc, bp, local_pixels, c->accum.ptr, ro.frame_index, frame_dev, ro.frame_srgb); });
+    else
+        launch(kClassOther, [&] { LaunchFinalize(lc, bp, local_pixels, c->accum.ptr, frame_dev, tiles_dev); });
     CU_CHECK(c, cudaEventRecord(c->ev_end, stream));
     CU_CHECK(c, cudaGetLastError());
     c->timing_pending = true;
@@ -624,6 +647,20 @@ int b200pt_render_device(b200pt_handle h, const b200pt_render_opts *opts, float 
     ResolvedOpts ro;
     int rc = ResolveOpts(h, opts, &ro);
     if (rc != B200PT_OK) return rc;
+    return RenderOnStream(h, ro, frame_dev, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int b200pt_render_progressive_device(b200pt_handle h, const b200pt_render_opts *opts, uint32_t frame_index, float *frame_dev,
+                                     float *frame_srgb_dev, void *stream) {
+    if (!h || !frame_dev) return SetGlobalError(B200PT_EINVAL, "b200pt_render_progressive_device: null argument");
+    ResolvedOpts ro;
+    int rc = ResolveOpts(h, opts, &ro);
+    if (rc != B200PT_OK) return rc;
+    if (ro.tile_world != 1) return h->Fail(B200PT_EINVAL, "progressive rendering works on the whole frame (tile_world must be 1).");
+    ro.spp = 1; // main.cpp:53-58: spp is forced to 1 when previewing
+    ro.progressive = true;
+    ro.frame_index = frame_index;
+    ro.frame_srgb = frame_srgb_dev;
     return RenderOnStream(h, ro, frame_dev, nullptr, static_cast<cudaStream_t>(stream));
 }
 

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(con
         if (!LocalPixelToImage(bp, JobPixelToLocal(bp, bp.pixel_begin + slot / bp.sample_count), &px, &py)) return false;
         const uint32_t s = bp.sample_begin + slot % bp.sample_count;
         if (OPACITY) *ctr = make_uint3(py * bp.width + px, s, 0u);
-        const float u = s * bp.spp_inv, v = VanDerCorput2(s + 1);
+        const float u = bp.progressive ? bp.progressive_u : s * bp.spp_inv, v = bp.progressive ? bp.progressive_v : VanDerCorput2(s + 1);
         const float x = 2.0f * (px + u) / static_cast<int>(bp.width) - 1.0f, y = 1.0f - 2.0f * (py + v) / static_cast<int>(bp.height);
         ray->o = mk3(bp.camera.eye);
         ray->d = Normalize(mk3(bp.camera.front) + x * mk3(bp.camera.view_dx) + y * mk3(bp.camera.view_dy));
@@ -362,6 +362,24 @@ __global__ void k_finalize(const __grid_constant__ BatchParams bp, uint32_t num_
     }
 }
 
+// renderer.cpp:118-136: running mean over the preview frames + sRGB transfer into a bottom-up copy.
+__global__ void k_finalize_progressive(const __grid_constant__ BatchParams bp, uint32_t num_local_pixels, const float *accum,
+                                       uint32_t frame_index, float *frame, float *frame_srgb) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < num_local_pixels; p += gridDim.x * blockDim.x) {
+        uint32_t i, j;
+        if (!LocalPixelToImage(bp, p, &i, &j)) continue;
+        const uint64_t offset = 3ull * (static_cast<uint64_t>(j) * bp.width + i),
+                       offset_dest = 3ull * (static_cast<uint64_t>(bp.height - 1 - j) * bp.width + i);
+        for (int c = 0; c < 3; ++c) {
+            const float color = accum[3ull * p + c]; // one sample, already clamped to <= 1 by k_resolve
+            const float mean = (frame_index * frame[offset + c] + color) / (frame_index + 1);
+            frame[offset + c] = mean;
+            if (frame_srgb != nullptr)
+                frame_srgb[offset_dest + c] = mean <= 0.0031308f ? 12.92f * mean : 1.055f * powf(mean, 1.0f / 2.4f) - 0.055f;
+        }
+    }
+}
+
 // gathered = [tile_world][pixels_per_rank*3]: the all-gathered per-rank tile buffers.
 __global__ void k_assemble(uint32_t width, uint32_t height, uint32_t tile_world, uint32_t pixels_per_rank, const float *gathered,
                            float *frame) {
@@ -481,6 +499,12 @@ void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_
                     float *tiles) {
     const int blocks = static_cast<int>(std::min<uint64_t>(lc.blocks, (num_local_pixels + kThreads - 1) / kThreads));
     k_finalize<<<std::max(blocks, 1), kThreads, 0, lc.stream>>>(bp, num_local_pixels, accum, frame, tiles);
+}
+
+void LaunchFinalizeProgressive(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,
+                               uint32_t frame_index, float *frame, float *frame_srgb) {
+    const int blocks = static_cast<int>(std::min<uint64_t>(lc.blocks, (num_local_pixels + kThreads - 1) / kThreads));
+    k_finalize_progressive<<<std::max(blocks, 1), kThreads, 0, lc.stream>>>(bp, num_local_pixels, accum, frame_index, frame, frame_srgb);
 }
 
 void LaunchAssemble(const LaunchConfig &lc, uint32_t width, uint32_t height, uint32_t tile_world, uint32_t pixels_per_rank,

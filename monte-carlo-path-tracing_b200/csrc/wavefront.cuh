@@ -85,6 +85,10 @@ struct BatchParams {
     // Tile visibility pre-pass (k_cull_tiles): the local tiles whose camera rays can reach geometry, in ascending order;
     // the job's pixel list is then [active tile 0's 64 pixels, active tile 1's, ...].  nullptr = every local tile.
     const uint32_t *active_tiles;
+    // Progressive preview (renderer.cpp:97-138): one sample per pixel per call, every pixel with the same sub-pixel offset
+    // (VdC_2, VdC_3 of frame_index + 1); the sample index of the random-number stream is the frame index.
+    uint32_t progressive;
+    float progressive_u, progressive_v;
 };
 
 // index in the job's pixel list -> local pixel (position in this rank's tile-ordered pixel buffer)
@@ -134,6 +138,9 @@ void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_q
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum);
 void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,
                     float *frame, float *tiles);
+// Progressive preview: frame = (index * frame + sample) / (index + 1), sRGB copy with row 0 at the bottom (renderer.cpp:118-136).
+void LaunchFinalizeProgressive(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,
+                               uint32_t frame_index, float *frame, float *frame_srgb);
 void LaunchAssemble(const LaunchConfig &lc, uint32_t width, uint32_t height, uint32_t tile_world, uint32_t pixels_per_rank,
                     const float *gathered, float *frame);
 

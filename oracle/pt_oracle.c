@@ -183,6 +183,16 @@ float oracle_van_der_corput2(uint32_t index) { /* math.hpp:29-41 */
     }
     return result;
 }
+float oracle_van_der_corput3(uint32_t index) { /* math.hpp:29-41 with base = 3 (the preview path's second offset) */
+    const float base_inv = 1.0f / 3;
+    float result = 0.0f, frac = base_inv;
+    while (index > 0) {
+        result += frac * (index % 3);
+        index = (uint32_t)(index * base_inv);
+        frac *= base_inv;
+    }
+    return result;
+}
 float oracle_mis_weight(float pdf1, float pdf2) { /* math.cpp:8-13 */
     pdf1 *= pdf1;
     pdf2 *= pdf2;
@@ -2504,6 +2514,36 @@ int oracle_render(const b200pt_scene_desc *desc, int width, int height, int spp,
         pthread_create(&threads[t], NULL, RenderRows, &workers[t]);
     }
     for (int t = 0; t < num_threads; ++t) pthread_join(threads[t], NULL);
+    FreeScene(os);
+    return 0;
+}
+
+/* Progressive preview frame: the body of DispathRaysCuda(camera, integrator, index_frame, frame, frame_srgb)
+ * (renderer.cpp:97-138), which the reference only runs under CUDA + GLUT (ENABLE_VIEWER), restated for the CPU on top of the
+ * pinned pieces (Tea<4>, VdC, ShadePath / ShadeVolPath).  The loop itself is NOT pinned against a reference run ("parity
+ * unpinned" for these 30 lines; everything they call is pinned).  frame: running mean, updated in place; frame_srgb: sRGB
+ * copy with row 0 at the bottom (may be NULL).  Single-threaded: meant for small frames. */
+int oracle_render_progressive(const b200pt_scene_desc *desc, int width, int height, int watertight, uint32_t index_frame, float *frame,
+                              float *frame_srgb) {
+    if (!desc || !frame) return -1;
+    OracleScene *os = CommitScene(desc, width, height, 1, watertight);
+    const Scene *s = &os->scene;
+    const float u = oracle_van_der_corput2(index_frame + 1), v = oracle_van_der_corput3(index_frame + 1);
+    for (uint32_t j = 0; j < (uint32_t)s->height; ++j)
+        for (uint32_t i = 0; i < (uint32_t)s->width; ++i) {
+            const float x = 2.0f * (i + u) / s->width - 1.0f, y = 1.0f - 2.0f * (j + v) / s->height;
+            const Vec3 look_dir = normalize(add(add(s->front, smul(x, s->view_dx)), smul(y, s->view_dy)));
+            const uint32_t pixel_offset = (j * s->width + i) * 3, offset_dest = ((s->height - 1 - j) * s->width + i) * 3;
+            uint32_t seed = oracle_tea4(pixel_offset, index_frame);
+            const Vec3 L = s->integrator_type == B200PT_INTEGRATOR_VOLPATH ? ShadeVolPath(s, s->eye, look_dir, &seed) : ShadePath(s, s->eye, look_dir, &seed);
+            const float color[3] = {fminf(L.x, 1.0f), fminf(L.y, 1.0f), fminf(L.z, 1.0f)};
+            for (int c = 0; c < 3; ++c) {
+                frame[pixel_offset + c] = (index_frame * frame[pixel_offset + c] + color[c]) / (index_frame + 1);
+                if (frame_srgb != NULL)
+                    frame_srgb[offset_dest + c] = frame[pixel_offset + c] <= 0.0031308f ? 12.92f * frame[pixel_offset + c]
+                                                                                       : 1.055f * powf(frame[pixel_offset + c], 1.0f / 2.4f) - 0.055f;
+            }
+        }
     FreeScene(os);
     return 0;
 }

@@ -160,6 +160,7 @@ uint32_t ref_tea4(uint32_t v0, uint32_t v1) { return csrt::Tea<4>(v0, v1); }
 float ref_random_float(uint32_t *seed) { return csrt::RandomFloat(seed); }
 
 float ref_van_der_corput2(uint32_t index) { return csrt::GetVanDerCorputSequence<2>(index); }
+float ref_van_der_corput3(uint32_t index) { return csrt::GetVanDerCorputSequence<3>(index); }
 
 float ref_mis_weight(float a, float b) { return csrt::MisWeight(a, b); }
 

@@ -40,6 +40,9 @@ class RefLib:
         L.ref_random_float.restype = ctypes.c_float
         L.ref_van_der_corput2.argtypes = [ctypes.c_uint32]
         L.ref_van_der_corput2.restype = ctypes.c_float
+        if hasattr(L, "ref_van_der_corput3"):
+            L.ref_van_der_corput3.argtypes = [ctypes.c_uint32]
+            L.ref_van_der_corput3.restype = ctypes.c_float
         L.ref_mis_weight.argtypes = [ctypes.c_float, ctypes.c_float]
         L.ref_mis_weight.restype = ctypes.c_float
 
@@ -87,6 +90,9 @@ class OracleLib:
         L.oracle_random_float.restype = ctypes.c_float
         L.oracle_van_der_corput2.argtypes = [ctypes.c_uint32]
         L.oracle_van_der_corput2.restype = ctypes.c_float
+        L.oracle_van_der_corput3.argtypes = [ctypes.c_uint32]
+        L.oracle_van_der_corput3.restype = ctypes.c_float
+        L.oracle_render_progressive.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_mis_weight.argtypes = [ctypes.c_float, ctypes.c_float]
         L.oracle_mis_weight.restype = ctypes.c_float
         L.oracle_sample_hemis_cos.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
@@ -109,6 +115,24 @@ class OracleLib:
             if rc != 0:
                 raise RuntimeError("oracle_render failed")
             return frame
+        finally:
+            loader.b200pt_scene_free(scene)
+
+
+    def render_progressive(self, pack_path, width, height, num_frames, watertight=True):
+        """num_frames calls of the preview path (renderer.cpp:97-138 restated): returns (running-mean frame, sRGB bottom-up copy)."""
+        loader = _pack_loader()
+        scene = ctypes.c_void_p()
+        if loader.b200pt_scene_load(pack_path.encode(), ctypes.byref(scene)) != 0:
+            raise RuntimeError(f"cannot load {pack_path}")
+        try:
+            desc = loader.b200pt_scene_get_desc(scene)
+            frame = np.zeros((height, width, 3), dtype=np.float32)
+            srgb = np.zeros((height, width, 3), dtype=np.float32)
+            for k in range(num_frames):
+                if self.lib.oracle_render_progressive(desc, width, height, 1 if watertight else 0, k, frame.ctypes.data, srgb.ctypes.data) != 0:
+                    raise RuntimeError("oracle_render_progressive failed")
+            return frame, srgb
         finally:
             loader.b200pt_scene_free(scene)
 

@@ -3,7 +3,8 @@
 
 Run once in a container that has /root/reference (after `python -c "import __graft_entry__ as g; g.build()"`):
 
-    python tests/golden/make_golden.py [--synthetic NAME ...]     (--synthetic: only (re)make the named synthetic scenes)
+    python tests/golden/make_golden.py [--synthetic NAME ... | --kats]   (--synthetic: only (re)make the named synthetic scenes;
+                                                                       --kats: only the known answers of leaf functions)
 
 Outputs (all produced by reference code, none by the oracle restatement or the CUDA path):
   kats.json                      known answers of reference leaf functions (Tea<4>, LCG, VdC, MisWeight, cos-hemisphere, LBVH)
@@ -37,16 +38,25 @@ def main():
     woop, mt = refcheck.ref_lib("woop"), refcheck.ref_lib("mt")
     L = woop.lib
     only_synthetic = sys.argv[2:] if len(sys.argv) > 2 and sys.argv[1] == "--synthetic" else None
+    if len(sys.argv) > 1 and sys.argv[1] == "--kats":  # only the known answers of the leaf functions (no renders)
+        make_kats(L)
+        return
     if only_synthetic is None:
         make_reference_scene_goldens(woop, mt, L)
     make_synthetic_goldens(woop, mt, only_synthetic)
 
 
 def make_reference_scene_goldens(woop, mt, L):
+    make_kats(L)
+    make_reference_frames(woop, mt)
+
+
+def make_kats(L):
     kats = {"tea4": [[a, b, int(L.ref_tea4(a, b))] for a, b in ((0, 0), (3, 0), (3145725, 0), (12, 7), (4294967295, 1))]}
     seed = ctypes.c_uint32(L.ref_tea4(0, 0))
     kats["lcg_from_tea4_0_0"] = [[float(L.ref_random_float(ctypes.byref(seed))), int(seed.value)] for _ in range(8)]
     kats["van_der_corput2"] = [[i, float(L.ref_van_der_corput2(i))] for i in list(range(0, 17)) + [255, 256, 4097, 65535]]
+    kats["van_der_corput3"] = [[i, float(L.ref_van_der_corput3(i))] for i in list(range(0, 17)) + [26, 27, 242, 243, 6560, 59049, 1000003]]
     kats["mis_weight"] = [[a, b, float(L.ref_mis_weight(a, b))] for a, b in ((0.3, 0.1), (1.0, 1.0), (0.01, 5.0), (7.5, 0.0))]
     L.ref_sample_hemis_cos.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
     hemis = []
@@ -82,6 +92,8 @@ def make_reference_scene_goldens(woop, mt, L):
     L.ref_kulla_conty(brdf.ctypes.data, albedo.ctypes.data)
     np.savez_compressed(os.path.join(HERE, "kulla_conty.npz"), brdf_avg=brdf, albedo_avg=albedo)
 
+
+def make_reference_frames(woop, mt):
     for name, (w, h, spp) in EXACT.items():
         pack = os.path.join(ROOT, "scenes", name + ".b200scene")
         for variant, ref in (("woop", woop), ("mt", mt)):

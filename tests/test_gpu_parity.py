@@ -206,6 +206,42 @@ def test_shared_memory_top_of_tree_is_bit_exact(pkg, monkeypatch):
     assert np.array_equal(a, b)
 
 
+def test_progressive_preview_entry(pkg, oracle):
+    """b200pt_render_progressive_device against the restated preview path (renderer.cpp:97-138): running mean over frames,
+    clamp, bottom-up sRGB copy; statistically the same image as the oracle's after the same number of frames."""
+    import torch
+    w = h = 64
+    frames = 128
+    r = renderer(pkg, "cornell-box")
+    frame = torch.zeros(h * w * 3, dtype=torch.float32, device="cuda")
+    srgb = torch.zeros(h * w * 3, dtype=torch.float32, device="cuda")
+    first = None
+    for k in range(frames):
+        r.draw_progressive_device(frame, srgb, k, width=w, height=h, seed=5)
+        if k == 0:
+            torch.cuda.synchronize()
+            first = frame.cpu().numpy().reshape(h, w, 3).copy()
+    torch.cuda.synchronize()
+    a, a_srgb = frame.cpu().numpy().reshape(h, w, 3), srgb.cpu().numpy().reshape(h, w, 3)
+    # frame 0 is exactly one clamped sample per pixel with spp = 1 semantics
+    assert first.max() <= 1.0 and not np.array_equal(first, a)
+    expected_srgb = np.where(a <= 0.0031308, 12.92 * a, 1.055 * np.power(a, np.float32(1 / 2.4)) - 0.055)[::-1]
+    assert np.allclose(a_srgb, expected_srgb, atol=2e-6)
+    # a second accumulation with another seed gives the noise floor
+    frame2 = torch.zeros_like(frame)
+    for k in range(frames):
+        r.draw_progressive_device(frame2, None, k, width=w, height=h, seed=6)
+    torch.cuda.synchronize()
+    b = frame2.cpu().numpy().reshape(h, w, 3)
+    expected, _ = oracle.render_progressive(pack("cornell-box"), w, h, frames)
+    floor_box = rel_l2(boxed(a), boxed(b))
+    assert abs(a.mean() / expected.mean() - 1.0) < 0.015, (a.mean(), expected.mean())
+    assert rel_l2(boxed(a), boxed(expected)) <= 2.0 * floor_box + 0.005, (rel_l2(boxed(a), boxed(expected)), floor_box)
+    # and it converges to the still image of the same view
+    golden = np.load(os.path.join(GOLDEN, "converged_cornell-box.npy"))
+    assert abs(a.mean() / golden.mean() - 1.0) < 0.02
+
+
 def test_kulla_conty_tables_match_reference(pkg):
     golden = np.load(os.path.join(GOLDEN, "kulla_conty.npz"))
     brdf, albedo = renderer(pkg, "matpreview").kulla_conty()

@@ -45,6 +45,8 @@ def test_van_der_corput_and_mis(oracle):
     assert [oracle.lib.oracle_van_der_corput2(i) for i in range(1, 6)] == [0.5, 0.25, 0.75, 0.125, 0.625]
     for index, value in KATS["van_der_corput2"]:
         assert oracle.lib.oracle_van_der_corput2(index) == np.float32(value)
+    for index, value in KATS["van_der_corput3"]:  # base 3: the second sub-pixel offset of the preview path (renderer.cpp:106)
+        assert oracle.lib.oracle_van_der_corput3(index) == np.float32(value)
     assert oracle.lib.oracle_mis_weight(0.3, 0.1) == np.float32(0.900000036)
     for a, b, value in KATS["mis_weight"]:
         got = oracle.lib.oracle_mis_weight(a, b)
@@ -148,3 +150,21 @@ def test_live_reference_build_when_present(oracle, scene, w, h, spp):
         pytest.skip("oracle/_ref reference build not present")
     expected, _, _ = ref.render_pack(pack(scene), w, h, spp)
     assert np.array_equal(oracle.render_pack(pack(scene), w, h, spp), expected)
+
+
+def test_progressive_preview_restatement(oracle):
+    """renderer.cpp:97-138 restated: frame k of the preview is one sample per pixel (seed Tea<4>(offset, k), sub-pixel offset
+    (VdC_2, VdC_3)(k+1)), folded into a running mean; the sRGB copy is bottom-up.  Checked through its own invariants and
+    against the pinned still-image path, whose converged frame it must approach."""
+    from conftest import pack
+    w = h = 24
+    one, srgb_one = oracle.render_progressive(pack("cornell-box"), w, h, 1)
+    many, srgb = oracle.render_progressive(pack("cornell-box"), w, h, 64)
+    assert one.max() <= 1.0 and many.max() <= 1.0 and np.isfinite(many).all()
+    expected_srgb = np.where(many <= 0.0031308, 12.92 * many, 1.055 * np.power(many, np.float32(1 / 2.4)) - 0.055)[::-1]
+    assert np.allclose(srgb, expected_srgb, atol=1e-6)
+    assert not np.array_equal(one, many)
+    still = oracle.render_pack(pack("cornell-box"), w, h, 256)
+    assert abs(many.mean() / still.mean() - 1.0) < 0.03
+    box = lambda f: f.reshape(h // 8, 8, w // 8, 8, 3).mean(axis=(1, 3))
+    assert np.linalg.norm(box(many) - box(still)) / np.linalg.norm(box(still)) < 0.06
