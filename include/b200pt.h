@@ -192,7 +192,14 @@ typedef struct b200pt_create_opts {
     int32_t device;          /* CUDA ordinal; -1 = current device */
     uint32_t max_leaf_size;  /* BVH leaf size, 0 = default (4) */
     uint64_t max_paths_in_flight; /* wavefront capacity in paths, 0 = default */
+    uint32_t flags;          /* B200PT_CREATE_* bit mask */
+    uint32_t reserved;
 } b200pt_create_opts;
+
+/* Build the BVH on the GPU (LBVH: Morton codes, radix sort, Karras' parallel radix tree, bottom-up refit) instead of with
+ * the host binned-SAH builder: the tree is ready in milliseconds instead of seconds, traversal is slower.
+ * Replaces csrt::BvhBuilder::Build (src/rtcore/accel/bvh_builder.cpp:50-206), also an LBVH. */
+#define B200PT_CREATE_GPU_LBVH 1u
 
 /* What to render.  width/height/spp = 0 take the value from the scene's camera
  * (the reference CLI overrides them after parsing: apps/main.cpp:46-52). */
@@ -225,6 +232,7 @@ typedef struct b200pt_kernel_stats {
 typedef struct b200pt_stats {
     double render_ms;            /* device time of the last render (CUDA events on the render stream) */
     double upload_ms, bvh_build_ms;
+    double bvh_gpu_ms;           /* GPU LBVH builder only: device time of Morton codes + sort + hierarchy + refit */
     uint64_t samples;            /* width*height*spp rendered by this rank */
     uint64_t kernel_launches;    /* kernels launched by the last render */
     uint64_t num_bvh_nodes, num_triangles, num_prims;

@@ -35,7 +35,7 @@ class RenderOpts(ctypes.Structure):
 
 class CreateOpts(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("max_leaf_size", ctypes.c_uint32),
-                ("max_paths_in_flight", ctypes.c_uint64)]
+                ("max_paths_in_flight", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class KernelStats(ctypes.Structure):
@@ -49,11 +49,12 @@ class KernelStats(ctypes.Structure):
 STATS_COUNTERS = 1  # B200PT_STATS_COUNTERS
 STATS_TIMING = 2    # B200PT_STATS_TIMING
 RENDER_NO_TILE_CULL = 1  # B200PT_RENDER_NO_TILE_CULL
+CREATE_GPU_LBVH = 1      # B200PT_CREATE_GPU_LBVH
 
 
 class Stats(ctypes.Structure):
     _fields_ = [("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double), ("bvh_build_ms", ctypes.c_double),
-                ("samples", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
+                ("bvh_gpu_ms", ctypes.c_double), ("samples", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
                 ("num_bvh_nodes", ctypes.c_uint64), ("num_triangles", ctypes.c_uint64), ("num_prims", ctypes.c_uint64),
                 ("local_tiles", ctypes.c_uint64), ("active_tiles", ctypes.c_uint64),
                 ("primary", KernelStats), ("extend", KernelStats), ("shadow", KernelStats), ("shade", KernelStats),
@@ -148,10 +149,10 @@ class Scene:
 class Renderer:
     """csrt::Renderer (renderer.hpp:30-82): construct from a config, Draw(frame) fills w*h*3 linear floats."""
 
-    def __init__(self, scene, device=-1, max_paths_in_flight=0, max_leaf_size=0):
+    def __init__(self, scene, device=-1, max_paths_in_flight=0, max_leaf_size=0, flags=0):
         self.scene = scene
         self._h = ctypes.c_void_p()
-        opts = CreateOpts(device, max_leaf_size, max_paths_in_flight)
+        opts = CreateOpts(device, max_leaf_size, max_paths_in_flight, flags, 0)
         _check(lib().b200pt_create(scene.desc, ctypes.byref(opts), ctypes.byref(self._h)))
 
     def _opts(self, width, height, spp, seed, tile_rank=0, tile_world=1, stats=0, flags=0):

@@ -32,11 +32,13 @@ struct HostScene {
     std::vector<float> cull_boxes;   // 6 floats per box (DeviceScene::cull_boxes)
     DIntegrator integrator{};
     b200pt_camera camera{};
-    double bvh_build_ms = 0.0;
+    double bvh_build_ms = 0.0;  // whole BVH stage (boxes, build, flatten)
+    double bvh_gpu_ms = 0.0;    // GPU LBVH only: Morton codes + sort + hierarchy + refit
 };
 
 // Returns false and sets *error on an inconsistent description.
-bool BuildHostScene(const b200pt_scene_desc &desc, uint32_t max_leaf_size, HostScene *out, std::string *error);
+// gpu_lbvh: build the BVH with the GPU LBVH builder (bvh_gpu.cu) instead of the host binned-SAH builder.
+bool BuildHostScene(const b200pt_scene_desc &desc, uint32_t max_leaf_size, bool gpu_lbvh, HostScene *out, std::string *error);
 
 // camera.cpp:26-37 for an arbitrary output size (the CLI may override width/height, Q7).
 DCamera MakeCamera(const b200pt_camera &cam, uint32_t width, uint32_t height);

@@ -235,6 +235,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     c->stats.num_triangles = h.tri_verts.size();
     c->stats.num_prims = h.tri_verts.size() + h.analytic.size();
     c->stats.bvh_build_ms = h.bvh_build_ms;
+    c->stats.bvh_gpu_ms = h.bvh_gpu_ms;
     // the big host copies are not needed any more
     std::vector<BvhNode>().swap(h.nodes);
     std::vector<TriVerts>().swap(h.tri_verts);
@@ -606,7 +607,9 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
 
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();
-    if (!BuildHostScene(*scene, opts ? opts->max_leaf_size : 0, &c->host, &err)) {
+    const char *builder_env = getenv("B200PT_BVH_BUILDER"); // "lbvh" / "sah": overrides the create option (experiments)
+    const bool gpu_lbvh = builder_env ? std::string(builder_env) == "lbvh" : (opts && (opts->flags & B200PT_CREATE_GPU_LBVH));
+    if (!BuildHostScene(*scene, opts ? opts->max_leaf_size : 0, gpu_lbvh, &c->host, &err)) {
         // same prefix as renderer.cpp:343-346
         return SetGlobalError(B200PT_EINVAL, "error when commit renderer.\n\t" + err);
     }

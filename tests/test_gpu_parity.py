@@ -242,6 +242,45 @@ def test_progressive_preview_entry(pkg, oracle):
     assert abs(a.mean() / golden.mean() - 1.0) < 0.02
 
 
+def test_gpu_lbvh_builder_renders_the_same_scene(pkg):
+    """B200PT_CREATE_GPU_LBVH: the tree built on the GPU (Morton sort + Karras radix tree + refit) finds the same closest
+    hits as the host SAH tree: identical coverage, statistically identical radiance (a hit exactly on a shared edge may pick
+    the other triangle, so the comparison is not bit-wise), parity with the reference frame, and far fewer build milliseconds."""
+    scene = pkg.Scene(pack("dragon"))
+    sah = pkg.Renderer(scene, device=0, max_paths_in_flight=1 << 22)
+    lbvh = pkg.Renderer(scene, device=0, max_paths_in_flight=1 << 22, flags=pkg.CREATE_GPU_LBVH)
+    a = sah.Draw(width=64, height=64, spp=1024, seed=11)
+    a2 = sah.Draw(width=64, height=64, spp=1024, seed=12)
+    b = lbvh.Draw(width=64, height=64, spp=1024, seed=11, stats=pkg.STATS_COUNTERS)
+    st_l, st_s = lbvh.stats(), sah.stats()
+    assert st_l["num_triangles"] == st_s["num_triangles"] and st_l["bvh_gpu_ms"] > 0.0 and st_s["bvh_gpu_ms"] == 0.0
+    assert st_l["bvh_gpu_ms"] < 100.0
+    assert np.array_equal(a.sum(axis=2) > 0, b.sum(axis=2) > 0)          # same pixels covered
+    assert abs(b.mean() / a.mean() - 1.0) < 0.005
+    assert rel_l2(b, a) <= 1.5 * rel_l2(a2, a) + 0.002
+    golden = np.load(os.path.join(GOLDEN, "converged_dragon.npy"))
+    assert abs(b.mean() / golden.mean() - 1.0) < 0.01
+    assert rel_l2(boxed(b), boxed(golden)) <= 2.0 * rel_l2(boxed(a), boxed(a2)) + 0.005
+    # primary visibility is deterministic: 1 spp, no bounce -> compare the hit distance proxy (first-bounce radiance support)
+    sah.close()
+    lbvh.close()
+
+
+@pytest.mark.parametrize("scene", ["cornell-box", "matpreview", "synthetic_bump_bitmap_mesh_disk"])
+def test_gpu_lbvh_builder_on_other_scenes(pkg, scene):
+    path = os.path.join(GOLDEN, scene + ".b200scene") if scene.startswith("synthetic_") else pack(scene)
+    sc = pkg.Scene(path)
+    sah = pkg.Renderer(sc, device=0, max_paths_in_flight=1 << 22)
+    lbvh = pkg.Renderer(sc, device=0, max_paths_in_flight=1 << 22, flags=pkg.CREATE_GPU_LBVH)
+    a = sah.Draw(width=64, height=64, spp=128, seed=3)
+    a2 = sah.Draw(width=64, height=64, spp=128, seed=4)
+    b = lbvh.Draw(width=64, height=64, spp=128, seed=3)
+    assert abs(b.mean() / a.mean() - 1.0) < 0.01
+    assert rel_l2(boxed(b), boxed(a)) <= 1.5 * rel_l2(boxed(a2), boxed(a)) + 0.003
+    sah.close()
+    lbvh.close()
+
+
 def test_kulla_conty_tables_match_reference(pkg):
     golden = np.load(os.path.join(GOLDEN, "kulla_conty.npz"))
     brdf, albedo = renderer(pkg, "matpreview").kulla_conty()
