@@ -114,6 +114,36 @@ def cpu_baseline(pack, width, height, spp_sample, spp_full):
                       f"(scene commit {r.build_seconds:.1f} s excluded)"}
 
 
+def reference_gpu_baseline(pack, width, height, spp_sample, spp_full):
+    """The reference's OWN CUDA backend (its one-thread-per-pixel megakernel DispathRaysCuda, renderer.cpp:88-95, rebuilt for
+    sm_100a into oracle/_ref/libcsrt_ref_cuda.so) on this GPU, bounded sample.  A comparator like cpu_baseline, not a target."""
+    import ctypes
+    import numpy as np
+    import __graft_entry__ as ge
+    path = os.path.join(ROOT, "oracle", "_ref", "libcsrt_ref_cuda.so")
+    if not os.path.exists(path):
+        return {"value": None, "unit": "Msamples/s", "sample": "unavailable: oracle/_ref/libcsrt_ref_cuda.so not built"}
+    L = ctypes.CDLL(path)
+    L.ref_create_cuda.restype = ctypes.c_void_p
+    L.ref_create_cuda.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    L.ref_draw_cuda.restype = ctypes.c_double
+    L.ref_draw_cuda.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.ref_destroy_cuda.argtypes = [ctypes.c_void_p]
+    L.ref_last_error.restype = ctypes.c_char_p
+    scene = ge.load_package().Scene(pack)
+    build = ctypes.c_double()
+    handle = L.ref_create_cuda(scene.desc, width, height, spp_sample, ctypes.byref(build))
+    if not handle:
+        return {"value": None, "unit": "Msamples/s", "sample": "unavailable: " + L.ref_last_error().decode(errors="replace")}
+    frame = np.zeros((height, width, 3), dtype=np.float32)
+    times = [L.ref_draw_cuda(handle, frame.ctypes.data) for _ in range(2)]  # the first Draw pages the managed scene in
+    L.ref_destroy_cuda(handle)
+    if min(times) <= 0:
+        return {"value": None, "unit": "Msamples/s", "sample": "unavailable: " + L.ref_last_error().decode(errors="replace")}
+    return {"value": width * height * spp_sample / min(times) / 1e6, "unit": "Msamples/s", "kind": "reference --gpu backend, sm_100a build",
+            "sample": f"{width}x{height} at {spp_sample} of {spp_full} spp, csrt::Renderer::Draw on BackendType::kCuda, best of 2: {min(times):.3f} s"}
+
+
 def run_reference(args, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -308,6 +338,13 @@ def run_b200(args, workload):
                 cpu = cpu_baseline(pack_path(name), width, height, REF_SPP_PER_STEP * 2, spp)
             except Exception as e:  # the reference build is test infrastructure; its absence must not hide the GPU number
                 cpu = {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
+        ref_gpu = None
+        if not args.no_cpu_baseline and world == 1:
+            renderer.close()  # frees the wavefront state before the reference allocates its managed scene
+            try:
+                ref_gpu = reference_gpu_baseline(pack_path(name), width, height, REF_SPP_PER_STEP * 2, spp)
+            except Exception as e:
+                ref_gpu = {"value": None, "unit": "Msamples/s", "sample": f"unavailable: {e}"}
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -321,6 +358,7 @@ def run_b200(args, workload):
                            "active_tiles": counted["active_tiles"], "local_tiles": counted["local_tiles"],
                            "value_with_prepass_off": (samples_per_step / min(no_cull_ms) / 1e3) if no_cull_ms else None}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "reference_gpu_baseline": ref_gpu,
         }
         print(json.dumps(line))
     if world > 1:

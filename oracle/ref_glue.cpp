@@ -153,6 +153,72 @@ double ref_draw(void *renderer, float *frame) {
 
 void ref_destroy(void *renderer) { delete static_cast<csrt::Renderer *>(renderer); }
 
+// ---- the reference's own CUDA backend (only in libcsrt_ref_cuda.so, built with -DENABLE_CUDA): BackendType::kCuda, i.e. its
+// one-thread-per-pixel megakernel DispathRaysCuda (renderer.cpp:88-95) over managed memory, as `RayTracer --gpu` runs it. ----
+int ref_has_cuda() {
+#ifdef ENABLE_CUDA
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+#ifdef ENABLE_CUDA
+namespace {
+struct CudaRef {
+    csrt::Renderer *renderer = nullptr;
+    float *frame = nullptr; // managed, as RayTracer::RayTracer allocates it (ray_tracer.cpp:133-136)
+    size_t count = 0;
+};
+} // namespace
+
+void *ref_create_cuda(const b200pt_scene_desc *desc, int width, int height, int spp, double *build_seconds) {
+    try {
+        csrt::RendererConfig cfg = b200pt_glue::InflateScene(*desc);
+        cfg.backend_type = csrt::BackendType::kCuda;
+        if (width > 0) cfg.camera.width = width;
+        if (height > 0) cfg.camera.height = height;
+        if (spp > 0) cfg.camera.spp = spp;
+        StderrSilencer quiet;
+        const auto t0 = std::chrono::steady_clock::now();
+        CudaRef *r = new CudaRef();
+        r->renderer = new csrt::Renderer(cfg);
+        r->count = static_cast<size_t>(cfg.camera.width) * cfg.camera.height * 3;
+        r->frame = csrt::MallocArray<float>(csrt::BackendType::kCuda, r->count);
+        if (build_seconds) *build_seconds = Seconds(t0, std::chrono::steady_clock::now());
+        return r;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return nullptr;
+    }
+}
+
+// One csrt::Renderer::Draw on the CUDA backend (kernel launch + cudaDeviceSynchronize, renderer.cpp:692-711); returns its
+// wall seconds or -1; the frame is then copied out of managed memory into frame_host (not timed).
+double ref_draw_cuda(void *handle, float *frame_host) {
+    try {
+        CudaRef *r = static_cast<CudaRef *>(handle);
+        StderrSilencer quiet;
+        const auto t0 = std::chrono::steady_clock::now();
+        r->renderer->Draw(r->frame);
+        const double seconds = Seconds(t0, std::chrono::steady_clock::now());
+        if (frame_host) memcpy(frame_host, r->frame, r->count * sizeof(float));
+        return seconds;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1.0;
+    }
+}
+
+void ref_destroy_cuda(void *handle) {
+    CudaRef *r = static_cast<CudaRef *>(handle);
+    if (!r) return;
+    csrt::DeleteArray(csrt::BackendType::kCuda, r->frame);
+    delete r->renderer;
+    delete r;
+}
+#endif
+
 // ---- known-answer helpers: reference leaf functions, called directly ----
 
 uint32_t ref_tea4(uint32_t v0, uint32_t v1) { return csrt::Tea<4>(v0, v1); }
