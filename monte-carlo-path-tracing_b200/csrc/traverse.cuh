@@ -189,6 +189,9 @@ struct TraversalCounters {
     uint32_t nodes = 0, prims = 0;
 };
 
+#ifndef B200PT_SPECULATIVE
+#define B200PT_SPECULATIVE 0   // measured variant, see profiles/README.md
+#endif
 constexpr int kStackSize = 64;
 constexpr int kSentinel = 0x7FFFFFFF;
 constexpr int kTopNodes = 512;     // default number of BVH nodes staged in shared memory (32 KB per CTA)
@@ -246,6 +249,9 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                                                    TraversalCounters *counters, uint32_t *rays_traced) {
     int stack[kStackSize];
     int sp = 0, cur = kSentinel;
+#if B200PT_SPECULATIVE
+    int postponed = 0; // a leaf link (< 0) waiting to be intersected, 0 = none
+#endif
     bool has = false, exhausted = false, found = false, any = false;
     uint32_t index = 0;
     Ray ray;
@@ -328,14 +334,21 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                 // Most lanes of an incoherent warp reach their next leaf within a few steps while a few stragglers
                 // keep descending; once fewer than `min_inner_lanes` lanes are still walking inner nodes the warp
                 // leaves the inner phase so the waiting lanes can intersect their leaves (stragglers resume later).
+#if B200PT_SPECULATIVE
+                // Speculative descent (Aila & Laine): the first leaf a lane reaches is put aside and the lane keeps walking
+                // inner nodes with the rest of the warp; it only waits once it holds a second one.
+                if (cur < 0 && postponed == 0) {
+                    postponed = cur;
+                    cur = sp > 0 ? stack[--sp] : kSentinel;
+                }
+#endif
                 if (__popc(__activemask()) < min_inner_lanes) break;
             }
-            // ---- leaf ----
-            if (cur < 0) {
-                const uint32_t leaf = static_cast<uint32_t>(~cur);
+            // ---- leaves ----
+            auto process_leaf = [&](int link) {
+                const uint32_t leaf = static_cast<uint32_t>(~link);
                 const uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
                 const float4 *verts = reinterpret_cast<const float4 *>(scene.tri_verts + first);
-                cur = sp > 0 ? stack[--sp] : kSentinel;
                 for (uint32_t j = 0; j < count; ++j) {
                     const float4 p0 = __ldg(verts + 3 * j), p1 = __ldg(verts + 3 * j + 1), p2 = __ldg(verts + 3 * j + 2);
                     if (STATS) ++counters[any].prims;
@@ -360,7 +373,28 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                         hit.v = v;
                     }
                 }
+            };
+#if B200PT_SPECULATIVE
+            // first the leaf that was put aside while the lane kept descending, then the one it stopped at
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                int link = 0;
+                if (pass == 0) {
+                    link = postponed;
+                    postponed = 0;
+                } else if (cur < 0) {
+                    link = cur;
+                    cur = sp > 0 ? stack[--sp] : kSentinel;
+                }
+                if (link < 0) process_leaf(link);
             }
+#else
+            if (cur < 0) {
+                const int link = cur;
+                cur = sp > 0 ? stack[--sp] : kSentinel;
+                process_leaf(link);
+            }
+#endif
             if (cur == kSentinel) {
                 finish(index, hit, found, any);
                 has = false;

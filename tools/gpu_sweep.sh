@@ -1,9 +1,11 @@
 #!/bin/bash
-# Scratch sweep: GPU tests + GPU LBVH builder vs host SAH builder (build time, render time).
+# Scratch sweep: GPU tests + speculative-descent variant of the traversal loop.
 cd "$(dirname "$0")/.."
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 D="python tools/gpu_tune.py dragon 1024 1024 256 28"
-echo "dragon sah"; $D 2>&1 | tail -1
-for v in 2 4 8; do echo "dragon lbvh leaf=$v"; B200PT_BVH_BUILDER=lbvh LEAF=$v $D 2>&1 | tail -1; done
-echo "matpreview sah"; python tools/gpu_tune.py matpreview 1024 1024 64 30 2>&1 | tail -1
-echo "matpreview lbvh"; B200PT_BVH_BUILDER=lbvh python tools/gpu_tune.py matpreview 1024 1024 64 30 2>&1 | tail -1
+P=$PWD/monte-carlo-path-tracing_b200
+echo "dragon default"; $D 2>&1 | tail -1
+echo "dragon speculative"; B200PT_LIB=$P/build_vs/libb200pt.so $D 2>&1 | tail -1
+for v in 4 12 16; do echo "dragon speculative min_inner=$v"; B200PT_MIN_INNER=$v B200PT_LIB=$P/build_vs/libb200pt.so $D 2>&1 | tail -1; done
+echo "matpreview default"; python tools/gpu_tune.py matpreview 1024 1024 64 30 2>&1 | tail -1
+echo "matpreview speculative"; B200PT_LIB=$P/build_vs/libb200pt.so python tools/gpu_tune.py matpreview 1024 1024 64 30 2>&1 | tail -1
