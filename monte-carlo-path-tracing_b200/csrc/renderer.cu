@@ -117,7 +117,7 @@ struct b200pt_context {
     bool timing_pending = false;
     int num_sms = 148;
     // launch tunables (overridable through the environment for experiments: B200PT_TOP_NODES, B200PT_REFILL, B200PT_CTAS_PER_SM)
-    int top_nodes = 0, refill = 16, ctas_per_sm = 4, min_inner = 8; // top_nodes = 0: no shared-memory staging (profiles/r01_sweep_sel3_topnodes.log)
+    int top_nodes = 0, refill = 20, ctas_per_sm = 4, min_inner = 8; // top_nodes = 0: no shared-memory staging (profiles/r01_sweep_sel3_topnodes.log)
     // B200PT_STATS_TIMING: (class, begin, end) per launch, resolved in b200pt_get_stats
     struct TimedLaunch {
         int cls;
