@@ -311,6 +311,7 @@ def run_b200(args, workload):
                   "any_hit_rays": counted["shadow"]["rays"], "algorithmic_bytes": alg_trace, "GBps": gbps(alg_trace, timed["extend"]["ms"])},
         "shade": {"ms": timed["shade"]["ms"], "launches": timed["shade"]["launches"]},
         "other": {"ms": timed["other"]["ms"], "launches": timed["other"]["launches"]},
+        "tail": {"ms": timed["tail"]["ms"], "launches": timed["tail"]["launches"]},
     }
     dominant = max(("primary", "trace"), key=lambda k: kernels[k]["ms"])
     peak, peak_src = measured_peak()

@@ -243,6 +243,8 @@ typedef struct b200pt_stats {
     b200pt_kernel_stats shadow;  /* counters of the NEE rays traced inside k_trace (ms = 0, launches = 0) */
     b200pt_kernel_stats shade;   /* k_shade  : shading, NEE generation, sampling, compaction */
     b200pt_kernel_stats other;   /* resets, resolve, finalize */
+    b200pt_kernel_stats tail;    /* k_tail: one path per lane to the end, once a batch's survivor queue is short (its rays are
+                                    counted under extend / shadow) */
 } b200pt_stats;
 
 /* ---- lifecycle: replaces csrt::Renderer ctor/dtor (renderer.cpp:259-369) ---- */

@@ -58,7 +58,7 @@ class Stats(ctypes.Structure):
                 ("num_bvh_nodes", ctypes.c_uint64), ("num_triangles", ctypes.c_uint64), ("num_prims", ctypes.c_uint64),
                 ("local_tiles", ctypes.c_uint64), ("active_tiles", ctypes.c_uint64),
                 ("primary", KernelStats), ("extend", KernelStats), ("shadow", KernelStats), ("shade", KernelStats),
-                ("other", KernelStats)]
+                ("other", KernelStats), ("tail", KernelStats)]
 
     def as_dict(self):
         out = {}

@@ -59,7 +59,7 @@ namespace {
 constexpr int kMaxArenas = 8;
 constexpr int kPollRing = 8;         // survivor-count polls in flight per arena
 constexpr uint32_t kPollLag = 4;     // a poll is read this many rounds after it was enqueued, so the host never drains the GPU
-constexpr uint32_t kFirstPollDepth = 8;
+constexpr uint32_t kFirstPollDepth = 4;
 
 // One batch of paths in flight.
 struct Arena {
@@ -99,6 +99,8 @@ struct b200pt_context {
     DeviceArray<uint32_t> tile_flags, tile_list; // visibility pre-pass: per local tile flag; ascending active list + count
     bool tile_cull = true;        // B200PT_TILE_CULL=0 turns the pre-pass off
     int shade_only = -1;          // see LaunchConfig::shade_only
+    uint32_t tail_paths = 32768;  // B200PT_TAIL_PATHS: survivor count below which k_tail finishes a batch's paths (0 = never);
+                                  // profiles/r01_sweep_tail_kernel.log: larger take-overs lose to the per-bounce launches
 
     // wavefront state: up to kMaxArenas independent batches in flight, each with private queues, counters and stream,
     // so that the latency-bound tail of one batch's launches is filled by another batch's work
@@ -501,6 +503,10 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
                 ++run.chunk;
             }
         };
+        // From the second bounce on, the tail kernel looks at the survivor queue first: once it is short enough it finishes
+        // every remaining path in this one launch and the per-bounce kernels below find nothing to do.
+        if (depth > 1 && c->tail_paths > 0)
+            launch(kClassTail, [&] { LaunchTail(la, c->scene, run.bp, depth, ar.queue[run.which], run.which, ar.radiance, capacity, ar.counters, c->tail_paths); });
         if (depth > 1) launch(kClassOther, [&] { LaunchResetCounters(la, ar.counters, run.which ^ 1, true); });
         launch(kClassShade, [&] {
             const int n = LaunchShade(la, c->scene, run.bp, depth, ar.queue[run.which], run.which, ar.queue[run.which ^ 1], bins, ar.shadow,
@@ -604,6 +610,7 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     c->min_inner = env_int("B200PT_MIN_INNER", c->min_inner, 1, 32);
     c->ctas_per_sm = env_int("B200PT_CTAS_PER_SM", c->ctas_per_sm, 1, 16);
     c->tile_cull = env_int("B200PT_TILE_CULL", 1, 0, 1) != 0;
+    c->tail_paths = static_cast<uint32_t>(env_int("B200PT_TAIL_PATHS", static_cast<int>(c->tail_paths), 0, 1 << 24));
 
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();
@@ -726,7 +733,7 @@ int b200pt_get_stats(b200pt_handle h, b200pt_stats *out) {
                 host_counters.cls[k].node_visits += per_arena[a].cls[k].node_visits;
                 host_counters.cls[k].prim_tests += per_arena[a].cls[k].prim_tests;
             }
-        b200pt_kernel_stats *ks[kNumClasses] = {&h->stats.primary, &h->stats.extend, &h->stats.shadow, &h->stats.shade, &h->stats.other};
+        b200pt_kernel_stats *ks[kNumClasses] = {&h->stats.primary, &h->stats.extend, &h->stats.shadow, &h->stats.shade, &h->stats.other, &h->stats.tail};
         for (int k = 0; k < kNumClasses; ++k) {
             *ks[k] = b200pt_kernel_stats{};
             ks[k]->launches = h->class_launches[k];

@@ -403,4 +403,92 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
     }
 }
 
+// One ray per lane, walked to the end by its own lane: the plain traversal loop, for the path-at-a-time tail kernel
+// (k_tail), where a lane owns a whole path and there is no queue to refill from.  Same node / leaf / primitive tests and
+// the same order of visits as TraversePersistent, so both find the same hit.  `opacity` / `stats` are warp-uniform
+// run-time switches here (the tail handles a few thousand paths; it does not need a variant per scene kind).
+// Returns whether something was hit (closest-hit rays: the record is in *hit_out).
+__device__ __forceinline__ bool TraverseSingle(const DeviceScene &scene, Ray ray, bool any, bool opacity, Rng rng, HitRec *hit_out,
+                                               bool stats, TraversalCounters *counters) {
+    int stack[kStackSize];
+    int sp = 0;
+    const RayPre pre = Precompute(ray);
+    HitRec hit;
+    hit.t = ray.tmax, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
+    bool found = false;
+    for (uint32_t i = 0; i < scene.num_analytic; ++i) {
+        const AnalyticPrim &p = scene.analytic[i];
+        if (stats) ++counters->nodes;
+        if (!IntersectBox(p.bmin, p.bmax, ray, pre)) continue;
+        if (stats) ++counters->prims;
+        float t;
+        V2 uv = {0.0f, 0.0f};
+        if (IntersectAnalytic(p, ray, &t, opacity ? &uv : nullptr)) {
+            if (opacity && OpacityRejects(scene, p.inst, uv, rng)) continue;
+            found = true;
+            if (any) return true;
+            ray.tmax = t;
+            hit.t = t;
+            hit.prim = kPrimAnalyticBit | i;
+        }
+    }
+    int cur = scene.num_nodes ? 0 : kSentinel;
+    while (cur != kSentinel) {
+        if (cur >= 0) {
+            float4 n0, n1, nz;
+            int child0, child1;
+            LoadNode<false>(scene.nodes, nullptr, 0, cur, &n0, &n1, &nz, &child0, &child1);
+            if (stats) counters->nodes += 2;
+            const float c0lox = fmaf(n0.x, pre.idir.x, -pre.ood.x), c0hix = fmaf(n0.y, pre.idir.x, -pre.ood.x);
+            const float c0loy = fmaf(n0.z, pre.idir.y, -pre.ood.y), c0hiy = fmaf(n0.w, pre.idir.y, -pre.ood.y);
+            const float c0loz = fmaf(nz.x, pre.idir.z, -pre.ood.z), c0hiz = fmaf(nz.y, pre.idir.z, -pre.ood.z);
+            const float c1lox = fmaf(n1.x, pre.idir.x, -pre.ood.x), c1hix = fmaf(n1.y, pre.idir.x, -pre.ood.x);
+            const float c1loy = fmaf(n1.z, pre.idir.y, -pre.ood.y), c1hiy = fmaf(n1.w, pre.idir.y, -pre.ood.y);
+            const float c1loz = fmaf(nz.z, pre.idir.z, -pre.ood.z), c1hiz = fmaf(nz.w, pre.idir.z, -pre.ood.z);
+            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), ray.tmin));
+            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), ray.tmax));
+            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), ray.tmin));
+            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), ray.tmax));
+            const bool hit0 = c0min <= c0max, hit1 = c1min <= c1max;
+            if (!hit0 && !hit1) {
+                cur = sp > 0 ? stack[--sp] : kSentinel;
+            } else if (hit0 && hit1) {
+                const bool swap = c1min < c0min;
+                stack[sp++] = swap ? child0 : child1;
+                cur = swap ? child1 : child0;
+            } else {
+                cur = hit0 ? child0 : child1;
+            }
+        } else {
+            const uint32_t leaf = static_cast<uint32_t>(~cur);
+            const uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
+            const float4 *verts = reinterpret_cast<const float4 *>(scene.tri_verts + first);
+            cur = sp > 0 ? stack[--sp] : kSentinel;
+            for (uint32_t j = 0; j < count; ++j) {
+                const float4 p0 = __ldg(verts + 3 * j), p1 = __ldg(verts + 3 * j + 1), p2 = __ldg(verts + 3 * j + 2);
+                if (stats) ++counters->prims;
+                float t, u, v;
+                bool inside;
+                if (IntersectTriangleWoop(ray, pre, p0, p1, p2, &t, &u, &v, &inside)) {
+                    if (opacity) {
+                        const float *tc = &scene.tri_shade[first + j].uv[0][0];
+                        const float w = 1.0f - u - v;
+                        const V2 uv = {u * __ldg(tc) + v * __ldg(tc + 2) + w * __ldg(tc + 4), u * __ldg(tc + 1) + v * __ldg(tc + 3) + w * __ldg(tc + 5)};
+                        if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng)) continue;
+                    }
+                    found = true;
+                    if (any) return true;
+                    ray.tmax = t;
+                    hit.t = t;
+                    hit.prim = (first + j) | (inside ? kPrimInsideBit : 0u);
+                    hit.u = u;
+                    hit.v = v;
+                }
+            }
+        }
+    }
+    *hit_out = hit;
+    return found;
+}
+
 } // namespace b200pt

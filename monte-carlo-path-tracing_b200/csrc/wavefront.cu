@@ -174,12 +174,6 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(con
 // the deep bounces when they were two launches: profiles/r01_dram_traffic.json per-launch times).
 // Ray index space: [0, n_extend) closest-hit rays of queue `which`, then [n_extend, n_extend + n_shadow) NEE rays.
 // ---------------------------------------------------------------------------------------------
-// Random-number counter (pixel, sample, depth) of the alpha tests along the ray of sample slot `slot`.
-__device__ __forceinline__ uint3 SlotCounter(const BatchParams &bp, uint32_t slot, uint32_t depth) {
-    uint32_t px = 0, py = 0;
-    LocalPixelToImage(bp, JobPixelToLocal(bp, bp.pixel_begin + slot / bp.sample_count), &px, &py);
-    return make_uint3(py * bp.width + px, bp.sample_begin + slot % bp.sample_count, depth);
-}
 
 template <bool STATS, bool OPACITY, bool TOP>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const __grid_constant__ DeviceScene scene,

@@ -54,7 +54,7 @@ __host__ __device__ inline uint32_t BinListIndex(uint32_t bins_in_use, uint32_t 
 #endif
 }
 
-enum KernelClass { kClassPrimary = 0, kClassExtend = 1, kClassShadow = 2, kClassShade = 3, kClassOther = 4, kNumClasses = 5 };
+enum KernelClass { kClassPrimary = 0, kClassExtend = 1, kClassShadow = 2, kClassShade = 3, kClassOther = 4, kClassTail = 5, kNumClasses = 6 };
 
 struct ClassCounters {
     unsigned long long rays, node_visits, prim_tests;
@@ -65,7 +65,9 @@ struct Counters {             // device-resident
     uint32_t shadow;          // entries in the shadow queue
     uint32_t work_primary;    // next unclaimed ray of the persistent traversal loops
     uint32_t work_trace;
-    uint32_t pad[3];
+    uint32_t work_tail;       // next unclaimed entry of the tail kernel
+    uint32_t tail_taken;      // != 0 once k_tail has taken over the batch's remaining paths (depth of the take-over + 1)
+    uint32_t pad[1];
     uint32_t bin_count[2][kNumShadeBins]; // entries of path queue 0 / 1 per shading bin (scenes with several BSDF models)
     ClassCounters cls[3];     // primary / extend / shadow traversal statistics (zeroed per render)
 };
@@ -107,6 +109,15 @@ __host__ __device__ inline bool LocalPixelToImage(const BatchParams &p, uint32_t
     return *i < p.width && *j < p.height;
 }
 
+#if defined(__CUDACC__)
+// Random-number counter (pixel, sample, depth) of the alpha tests along the ray of sample slot `slot`.
+__device__ __forceinline__ uint3 SlotCounter(const BatchParams &bp, uint32_t slot, uint32_t depth) {
+    uint32_t px = 0, py = 0;
+    LocalPixelToImage(bp, JobPixelToLocal(bp, bp.pixel_begin + slot / bp.sample_count), &px, &py);
+    return make_uint3(py * bp.width + px, bp.sample_begin + slot % bp.sample_count, depth);
+}
+#endif
+
 struct LaunchConfig {
     int blocks;               // persistent grid: SMs x resident CTAs
     int threads;
@@ -134,6 +145,11 @@ int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
 // such tiles in list[0 .. count) with count stored at list[num_local_tiles].
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
                      uint32_t *flags, uint32_t *list);
+// Path-at-a-time tail (tail_kernel.cu): launched after the traversal of bounce `depth - 1`; takes queue `which` over and
+// finishes its paths if it holds at most `threshold` entries, else returns at once.  `depth` = the bounce shade would run.
+void LaunchTail(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
+                float *radiance, uint32_t capacity, Counters *counters, uint32_t threshold);
+constexpr uint32_t kMaxTailDepth = 4096; // = kMaxRounds of the host loop
 void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow);
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum);
 void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,

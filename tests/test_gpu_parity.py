@@ -138,6 +138,29 @@ def test_batches_in_flight_do_not_change_the_frame(pkg, scene, monkeypatch):
     assert np.array_equal(frames[0], frames[1])  # same batch size per pixel chunk or not, 1 vs 2 arenas see whole sample ranges
 
 
+@pytest.mark.parametrize("scene,w,h,spp", [("dragon", 256, 256, 32), ("cornell-box", 128, 128, 32), ("volumetric-caustic", 96, 96, 32),
+                                           ("matpreview", 128, 128, 16), ("synthetic_opacity_masks", 96, 96, 32)])
+def test_tail_kernel_is_bit_exact(pkg, scene, w, h, spp, monkeypatch):
+    """k_tail (one path per lane to the end, once few paths survive) computes exactly the samples the per-bounce wavefront
+    launches would have: same ShadeVertex code, same counter-based random numbers, same order of additions per sample."""
+    path = os.path.join(GOLDEN, scene + ".b200scene") if scene.startswith("synthetic_") else pack(scene)
+    sc = pkg.Scene(path)
+    frames = {}
+    for paths in ("0", "4096", "16777216"):   # never / late take-over / take over right after the first bounce
+        monkeypatch.setenv("B200PT_TAIL_PATHS", paths)
+        r = pkg.Renderer(sc, device=0, max_paths_in_flight=1 << 22)
+        frames[paths] = r.Draw(width=w, height=h, spp=spp, seed=23, stats=pkg.STATS_COUNTERS)
+        st = r.stats()
+        assert (st["tail"]["launches"] > 0) == (paths != "0")
+        r.close()
+    if scene == "synthetic_opacity_masks":
+        # two emitters: the two NEE contributions of a vertex are added by atomics in either order in the wavefront path
+        assert np.allclose(frames["0"], frames["4096"], rtol=0, atol=1e-6) and np.allclose(frames["0"], frames["16777216"], rtol=0, atol=1e-6)
+    else:
+        assert np.array_equal(frames["0"], frames["4096"])
+        assert np.array_equal(frames["0"], frames["16777216"])
+
+
 def test_edge_cases(pkg):
     r = renderer(pkg, "cornell-box")
     one = r.Draw(width=16, height=16, spp=1, seed=1)

@@ -29,4 +29,4 @@ torch.cuda.synchronize()
 st = r.stats()
 print(json.dumps({"world": world, "arenas": os.environ.get("B200PT_ARENAS", "auto"), "ms": [round(x, 3) for x in ms], "timed_total_ms": round(st["render_ms"], 3),
                   "launches": st["kernel_launches"], "active_tiles": st["active_tiles"],
-                  **{k: round(st[k]["ms"], 3) for k in ("primary", "extend", "shade", "other")}}))
+                  **{k: round(st[k]["ms"], 3) for k in ("primary", "extend", "shade", "other", "tail")}}))

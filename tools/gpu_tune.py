@@ -30,5 +30,5 @@ for cap in caps:
     torch.cuda.synchronize()
     st = r.stats()
     print(json.dumps({"cap_log2": cap, "nodes": st["num_bvh_nodes"], "bvh_build_ms": round(st["bvh_build_ms"], 1), "bvh_gpu_ms": round(st["bvh_gpu_ms"], 2), "ms": ms, "Msamples_s": w * h * spp / min(ms) / 1e3, "launches": st["kernel_launches"],
-                      **{k: round(st[k]["ms"], 2) for k in ("primary", "extend", "shadow", "shade", "other")}}), flush=True)
+                      **{k: round(st[k]["ms"], 2) for k in ("primary", "extend", "shadow", "shade", "other", "tail")}}), flush=True)
     r.close()
