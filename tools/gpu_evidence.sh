@@ -13,7 +13,7 @@ echo "== ncu launch list of bench.py"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
 echo "== ncu DRAM bytes of every kernel of one frame"
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 120 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 250 --csv \
     --log-file $O/dram_one_frame.csv python tools/one_frame.py dragon 1024 1024 256 > $O/one_frame_ncu.log 2>&1
 python tools/dram_traffic.py $O/dram_one_frame.csv $O/dram_traffic.json > $O/dram_traffic.txt 2>&1; cat $O/dram_traffic.txt
 echo "== ncu --set full of the first launches of each kernel"
