@@ -346,8 +346,14 @@ __device__ __forceinline__ bool LoadPathVertex(const DeviceScene &scene, const P
     return alive;
 }
 
+// Resident CTAs per SM a variant is compiled for.  The diffuse path-integrator kernel fits 64 registers with a few spilled
+// words and gains from the fourth CTA (Dragon shade 6.6 -> 5.4 ms, Cornell 33.1 -> 26.7 ms: profiles/r01_sweep_shade_occupancy.log);
+// the other models need ~120 registers and are left to the compiler.
+#ifndef B200PT_SHADE_MIN_CTAS
+#define B200PT_SHADE_MIN_CTAS(VOL, ONLY) (((ONLY) == B200PT_BSDF_DIFFUSE && !(VOL)) ? 4 : 1)
+#endif
 template <bool VOL, int ONLY>
-__global__ void __launch_bounds__(kShadeThreads) k_shade(const __grid_constant__ DeviceScene scene,
+__global__ void __launch_bounds__(kShadeThreads, B200PT_SHADE_MIN_CTAS(VOL, ONLY)) k_shade(const __grid_constant__ DeviceScene scene,
                                                     const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue qin,
                                                     int which_in, PathQueue qout, ShadowQueue sq, float *radiance,
                                                     Counters *counters, uint32_t capacity, const uint32_t *bin_list,

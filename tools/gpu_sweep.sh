@@ -1,3 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-for t in 0 16384 131072 1048576 1073741824; do echo "prefetch_below=$t"; B200PT_PREFETCH_BELOW=$t python tools/gpu_rank_breakdown.py 1 2>&1 | tail -1; B200PT_PREFETCH_BELOW=$t python tools/gpu_rank_breakdown.py 8 2>&1 | tail -1; done
+P=$PWD/monte-carlo-path-tracing_b200
+D="python tools/gpu_tune.py dragon 1024 1024 256 28"
+echo "default"; $D 2>&1 | tail -1
+echo "diffuse shade at 4 CTAs/SM (64 regs)"; B200PT_LIB=$P/build_s4/libb200pt.so $D 2>&1 | tail -1
+echo "cornell default"; python tools/gpu_tune.py cornell-box 512 512 256 30 2>&1 | tail -1
+echo "cornell 4 CTAs"; B200PT_LIB=$P/build_s4/libb200pt.so python tools/gpu_tune.py cornell-box 512 512 256 30 2>&1 | tail -1
