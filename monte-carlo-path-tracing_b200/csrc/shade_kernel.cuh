@@ -349,7 +349,9 @@ __device__ __forceinline__ bool LoadPathVertex(const DeviceScene &scene, const P
 // Resident CTAs per SM a variant is compiled for.  The diffuse path-integrator kernel fits 64 registers with a few spilled
 // words and gains from the fourth CTA (Dragon shade 6.6 -> 5.4 ms, Cornell 33.1 -> 26.7 ms: profiles/r01_sweep_shade_occupancy.log);
 // the other models need ~120 registers and are left to the compiler.
-#ifndef B200PT_SHADE_MIN_CTAS
+#ifdef B200PT_SHADE_MIN_CTAS_OVERRIDE   // experiments: one bound for every variant of the translation unit
+#define B200PT_SHADE_MIN_CTAS(VOL, ONLY) B200PT_SHADE_MIN_CTAS_OVERRIDE
+#else
 #define B200PT_SHADE_MIN_CTAS(VOL, ONLY) (((ONLY) == B200PT_BSDF_DIFFUSE && !(VOL)) ? 4 : 1)
 #endif
 template <bool VOL, int ONLY>
