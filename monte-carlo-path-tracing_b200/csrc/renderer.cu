@@ -370,7 +370,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     }
 
     if (c->accum.count < 3ull * local_pixels) CU_CHECK(c, c->accum.Alloc(3ull * local_pixels));
-    LaunchConfig lc;
+    LaunchConfig lc{};
     lc.threads = 256;
     lc.stream = stream;
     lc.stats = ro.counters;
@@ -708,7 +708,7 @@ int b200pt_assemble_tiles_device(b200pt_handle h, uint32_t width, uint32_t heigh
     if (!h || !gathered_dev || !frame_dev || tile_world == 0)
         return SetGlobalError(B200PT_EINVAL, "b200pt_assemble_tiles_device: bad argument");
     CU_CHECK(h, cudaSetDevice(h->device));
-    LaunchConfig lc;
+    LaunchConfig lc{};
     lc.blocks = h->num_sms * 4, lc.threads = 256, lc.stream = static_cast<cudaStream_t>(stream), lc.stats = false;
     lc.top_nodes = h->top_nodes, lc.refill = h->refill, lc.min_inner = h->min_inner;
     LaunchAssemble(lc, width, height, tile_world, PixelsPerRank(width, height, tile_world), gathered_dev, frame_dev);
