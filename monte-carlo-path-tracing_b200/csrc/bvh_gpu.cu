@@ -9,14 +9,18 @@
 //   cub radix sort     (key, primitive) pairs                                   [library code, not on the render path]
 //   k_lbvh_hierarchy   Karras 2012: every internal node of the binary radix tree in parallel (direction, range, split)
 //   k_lbvh_refit       bottom-up boxes, one thread per leaf, the second arrival at a node continues upwards
+//   k_lbvh_flags/index/emit   subtrees of <= max_leaf primitives become leaves (a subtree of a radix tree always covers a
+//                      contiguous range of the sorted order); the surviving nodes are numbered in depth-first pre-order
+//                      WITHOUT walking the tree top-down — pre-order rank = (surviving nodes whose split lies left of the
+//                      node's range, a prefix sum over split positions) + (ancestors entered through their left child) —
+//                      and written straight into the 64-byte traversal layout (both child boxes + links per node).
 //
-// The tree comes back as plain arrays; scene_build.cpp collapses small subtrees into leaves of <= max_leaf triangles
-// (a subtree of a radix tree always covers a contiguous range of the sorted order) and flattens it into the traversal
-// layout exactly like the SAH tree.  Traversal quality is that of an LBVH (measured: profiles/), which is why the SAH
-// builder stays the default and this one is selected with B200PT_CREATE_GPU_LBVH / B200PT_BVH_BUILDER=lbvh.
+// Traversal quality is that of an LBVH (measured: profiles/r01_sweep_gpu_lbvh.log), which is why the SAH builder stays the
+// default and this one is selected with B200PT_CREATE_GPU_LBVH / B200PT_BVH_BUILDER=lbvh.
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "bvh_gpu.hpp"
 
@@ -61,7 +65,7 @@ __device__ __forceinline__ int Delta(const uint64_t *keys, int n, int i, int j) 
 
 // Child links: >= 0 internal node, < 0 leaf at sorted position ~link.
 __global__ void k_lbvh_hierarchy(const uint64_t *__restrict__ keys, int n, int32_t *left, int32_t *right, uint32_t *first,
-                                 uint32_t *last, int32_t *parent_of_internal, int32_t *parent_of_leaf) {
+                                 uint32_t *last, uint32_t *split, int32_t *parent_of_internal, int32_t *parent_of_leaf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     const int d = Delta(keys, n, i, i + 1) - Delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
@@ -84,6 +88,7 @@ __global__ void k_lbvh_hierarchy(const uint64_t *__restrict__ keys, int n, int32
     const int32_t r_link = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
     left[i] = l_link, right[i] = r_link;
     first[i] = lo, last[i] = hi;
+    split[i] = gamma;
     if (l_link >= 0) parent_of_internal[l_link] = i; else parent_of_leaf[~l_link] = i;
     if (r_link >= 0) parent_of_internal[r_link] = i; else parent_of_leaf[~r_link] = i;
     if (i == 0) parent_of_internal[0] = -1;
@@ -114,6 +119,61 @@ __global__ void k_lbvh_refit(const float *__restrict__ prim_boxes, const uint32_
     }
 }
 
+// flags[split position] = 1 for every node that stays an inner node (more than max_leaf primitives below it).
+__global__ void k_lbvh_flags(const uint32_t *first, const uint32_t *last, const uint32_t *split, int n, uint32_t max_leaf, uint32_t *flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    flags[split[i]] = (last[i] - first[i] + 1u > max_leaf) ? 1u : 0u;
+}
+
+// Pre-order rank of every surviving node among the surviving nodes (see the header comment).
+__global__ void k_lbvh_index(const uint32_t *first, const uint32_t *last, const int32_t *left, const int32_t *parent_of_internal, int n,
+                             uint32_t max_leaf, const uint32_t *prefix, int32_t *node_index) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    if (last[i] - first[i] + 1u <= max_leaf) {
+        node_index[i] = -1;
+        return;
+    }
+    uint32_t entered_left = 0;
+    for (int32_t child = i, parent = parent_of_internal[i]; parent >= 0; child = parent, parent = parent_of_internal[parent])
+        entered_left += left[parent] == child ? 1u : 0u;
+    node_index[i] = static_cast<int32_t>(prefix[first[i]] + entered_left);
+}
+
+__global__ void k_lbvh_emit(const float *__restrict__ prim_boxes, const uint32_t *__restrict__ order, const float *__restrict__ node_boxes,
+                            const int32_t *left, const int32_t *right, const uint32_t *first, const uint32_t *last,
+                            const int32_t *node_index, int n, uint32_t max_leaf, BvhNode *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1 || node_index[i] < 0) return;
+    BvhNode node{};
+    auto child = [&](int32_t link, int which) {
+        const float *b;
+        int32_t out_link;
+        if (link < 0) { // a single primitive
+            const uint32_t pos = static_cast<uint32_t>(~link);
+            b = prim_boxes + 6ull * order[pos];
+            out_link = ~static_cast<int32_t>(pos << 3);
+        } else {
+            b = node_boxes + 6ull * link;
+            const uint32_t count = last[link] - first[link] + 1u;
+            out_link = count <= max_leaf ? ~static_cast<int32_t>((first[link] << 3) | (count - 1u)) : node_index[link];
+        }
+        if (which == 0) {
+            node.c0xy = {b[0], b[3], b[1], b[4]};
+            node.cz.x = b[2], node.cz.y = b[5];
+            node.child0 = out_link;
+        } else {
+            node.c1xy = {b[0], b[3], b[1], b[4]};
+            node.cz.z = b[2], node.cz.w = b[5];
+            node.child1 = out_link;
+        }
+    };
+    child(left[i], 0);
+    child(right[i], 1);
+    out[node_index[i]] = node;
+}
+
 template <typename T>
 struct Dev {
     T *p = nullptr;
@@ -132,19 +192,20 @@ struct Dev {
         }                                                                                      \
     } while (0)
 
-bool BuildLbvhGpu(const float *prim_boxes, uint32_t n, const float scene_lo[3], const float scene_hi[3], LbvhResult *out,
-                  std::string *error) {
-    out->left.clear(), out->right.clear(), out->first.clear(), out->last.clear(), out->boxes.clear(), out->order.clear();
-    if (n < 2) {
-        out->order.assign(n, 0u);
-        out->gpu_ms = 0.0;
-        return true;
+// The whole build on the device: returns the tree already in traversal layout (depth-first pre-order, node 0 = root).
+// Needs n > max_leaf (otherwise the scene is a single leaf and the caller builds it on the host).
+bool BuildLbvhGpuFlat(const float *prim_boxes, uint32_t n, const float scene_lo[3], const float scene_hi[3], uint32_t max_leaf,
+                      std::vector<BvhNode> *nodes, std::vector<uint32_t> *order, double *gpu_ms, std::string *error) {
+    if (n < 2 || n <= max_leaf) {
+        *error = "GPU BVH build: too few primitives";
+        return false;
     }
     Dev<float> d_boxes, d_node_boxes;
     Dev<uint64_t> d_keys, d_keys_sorted;
-    Dev<uint32_t> d_vals, d_order, d_first, d_last, d_visits;
-    Dev<int32_t> d_left, d_right, d_parent_internal, d_parent_leaf;
+    Dev<uint32_t> d_vals, d_order, d_first, d_last, d_split, d_visits, d_flags, d_prefix;
+    Dev<int32_t> d_left, d_right, d_parent_internal, d_parent_leaf, d_index;
     Dev<uint8_t> d_temp;
+    Dev<BvhNode> d_nodes;
     LBVH_CHECK(d_boxes.Alloc(6ull * n));
     LBVH_CHECK(d_node_boxes.Alloc(6ull * (n - 1)));
     LBVH_CHECK(d_keys.Alloc(n));
@@ -153,14 +214,20 @@ bool BuildLbvhGpu(const float *prim_boxes, uint32_t n, const float scene_lo[3], 
     LBVH_CHECK(d_order.Alloc(n));
     LBVH_CHECK(d_first.Alloc(n - 1));
     LBVH_CHECK(d_last.Alloc(n - 1));
+    LBVH_CHECK(d_split.Alloc(n - 1));
     LBVH_CHECK(d_visits.Alloc(n - 1));
+    LBVH_CHECK(d_flags.Alloc(n));
+    LBVH_CHECK(d_prefix.Alloc(n));
     LBVH_CHECK(d_left.Alloc(n - 1));
     LBVH_CHECK(d_right.Alloc(n - 1));
     LBVH_CHECK(d_parent_internal.Alloc(n - 1));
     LBVH_CHECK(d_parent_leaf.Alloc(n));
-    size_t temp_bytes = 0;
-    LBVH_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, static_cast<int>(n), 0, 63));
-    LBVH_CHECK(d_temp.Alloc(temp_bytes));
+    LBVH_CHECK(d_index.Alloc(n - 1));
+    LBVH_CHECK(d_nodes.Alloc(n - 1));
+    size_t sort_bytes = 0, scan_bytes = 0;
+    LBVH_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, static_cast<int>(n), 0, 63));
+    LBVH_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flags.p, d_prefix.p, static_cast<int>(n)));
+    LBVH_CHECK(d_temp.Alloc(std::max(sort_bytes, scan_bytes)));
 
     cudaEvent_t ev0, ev1;
     LBVH_CHECK(cudaEventCreate(&ev0));
@@ -170,27 +237,31 @@ bool BuildLbvhGpu(const float *prim_boxes, uint32_t n, const float scene_lo[3], 
     const float3 lo = make_float3(scene_lo[0], scene_lo[1], scene_lo[2]);
     auto inv = [](float e) { return e > 0.0f ? 1.0f / e : 0.0f; };
     const float3 inv_extent = make_float3(inv(scene_hi[0] - scene_lo[0]), inv(scene_hi[1] - scene_lo[1]), inv(scene_hi[2] - scene_lo[2]));
-    const int blocks_n = static_cast<int>((n + kThreads - 1) / kThreads);
+    const int blocks_n = static_cast<int>((n + kThreads - 1) / kThreads), ni = static_cast<int>(n);
     k_lbvh_morton<<<blocks_n, kThreads>>>(d_boxes.p, n, lo, inv_extent, d_keys.p, d_vals.p);
-    LBVH_CHECK(cub::DeviceRadixSort::SortPairs(d_temp.p, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, static_cast<int>(n), 0, 63));
-    k_lbvh_hierarchy<<<blocks_n, kThreads>>>(d_keys_sorted.p, static_cast<int>(n), d_left.p, d_right.p, d_first.p, d_last.p,
-                                            d_parent_internal.p, d_parent_leaf.p);
+    LBVH_CHECK(cub::DeviceRadixSort::SortPairs(d_temp.p, sort_bytes, d_keys.p, d_keys_sorted.p, d_vals.p, d_order.p, ni, 0, 63));
+    k_lbvh_hierarchy<<<blocks_n, kThreads>>>(d_keys_sorted.p, ni, d_left.p, d_right.p, d_first.p, d_last.p, d_split.p, d_parent_internal.p,
+                                            d_parent_leaf.p);
     LBVH_CHECK(cudaMemsetAsync(d_visits.p, 0, (n - 1) * sizeof(uint32_t)));
-    k_lbvh_refit<<<blocks_n, kThreads>>>(d_boxes.p, d_order.p, static_cast<int>(n), d_left.p, d_right.p, d_parent_internal.p,
-                                        d_parent_leaf.p, d_visits.p, d_node_boxes.p);
+    k_lbvh_refit<<<blocks_n, kThreads>>>(d_boxes.p, d_order.p, ni, d_left.p, d_right.p, d_parent_internal.p, d_parent_leaf.p, d_visits.p,
+                                        d_node_boxes.p);
+    LBVH_CHECK(cudaMemsetAsync(d_flags.p, 0, n * sizeof(uint32_t)));
+    k_lbvh_flags<<<blocks_n, kThreads>>>(d_first.p, d_last.p, d_split.p, ni, max_leaf, d_flags.p);
+    LBVH_CHECK(cub::DeviceScan::ExclusiveSum(d_temp.p, scan_bytes, d_flags.p, d_prefix.p, ni));
+    k_lbvh_index<<<blocks_n, kThreads>>>(d_first.p, d_last.p, d_left.p, d_parent_internal.p, ni, max_leaf, d_prefix.p, d_index.p);
+    k_lbvh_emit<<<blocks_n, kThreads>>>(d_boxes.p, d_order.p, d_node_boxes.p, d_left.p, d_right.p, d_first.p, d_last.p, d_index.p, ni, max_leaf,
+                                       d_nodes.p);
     LBVH_CHECK(cudaEventRecord(ev1));
     LBVH_CHECK(cudaGetLastError());
-    out->left.resize(n - 1), out->right.resize(n - 1), out->first.resize(n - 1), out->last.resize(n - 1);
-    out->boxes.resize(6ull * (n - 1)), out->order.resize(n);
-    LBVH_CHECK(cudaMemcpy(out->left.data(), d_left.p, (n - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    LBVH_CHECK(cudaMemcpy(out->right.data(), d_right.p, (n - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    LBVH_CHECK(cudaMemcpy(out->first.data(), d_first.p, (n - 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    LBVH_CHECK(cudaMemcpy(out->last.data(), d_last.p, (n - 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    LBVH_CHECK(cudaMemcpy(out->boxes.data(), d_node_boxes.p, 6ull * (n - 1) * sizeof(float), cudaMemcpyDeviceToHost));
-    LBVH_CHECK(cudaMemcpy(out->order.data(), d_order.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint32_t num_nodes = 0; // flags has n entries (the last one is always 0), so prefix[n - 1] is the total
+    LBVH_CHECK(cudaMemcpy(&num_nodes, d_prefix.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    nodes->resize(num_nodes);
+    order->resize(n);
+    LBVH_CHECK(cudaMemcpy(nodes->data(), d_nodes.p, static_cast<size_t>(num_nodes) * sizeof(BvhNode), cudaMemcpyDeviceToHost));
+    LBVH_CHECK(cudaMemcpy(order->data(), d_order.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     float ms = 0.0f;
     LBVH_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
-    out->gpu_ms = ms;
+    *gpu_ms = ms;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
     return true;

@@ -911,50 +911,17 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             *error = "too many triangles for the leaf encoding.";
             return false;
         }
-        if (gpu_lbvh && nt >= 2) {
-            // GPU LBVH (bvh_gpu.cu): radix tree over Morton-sorted boxes; subtrees of <= max_leaf triangles become leaves.
+        if (gpu_lbvh && nt > 64) {
+            // GPU LBVH (bvh_gpu.cu): Morton sort, radix tree, refit, leaves of <= max_leaf triangles and the traversal
+            // layout are all produced on the device; the host only permutes the triangle attributes afterwards.
             std::vector<float> flat(6 * nt);
             for (size_t i = 0; i < nt; ++i) {
                 memcpy(&flat[6 * i], &boxes[i].lo, 12);
                 memcpy(&flat[6 * i + 3], &boxes[i].hi, 12);
             }
-            LbvhResult tree;
-            if (!BuildLbvhGpu(flat.data(), static_cast<uint32_t>(nt), &scene_box.lo.x, &scene_box.hi.x, &tree, error)) return false;
-            hs->bvh_gpu_ms = tree.gpu_ms;
-            std::vector<BuildNode> nodes;
-            nodes.reserve(2 * nt);
-            // explicit stack: (link, slot to patch in the parent)
-            struct Todo {
-                int32_t link, parent;
-                bool is_left;
-            };
-            std::vector<Todo> todo{{0, -1, false}};
-            int32_t root = -1;
-            while (!todo.empty()) {
-                const Todo t = todo.back();
-                todo.pop_back();
-                BuildNode node;
-                if (t.link < 0) {
-                    const uint32_t pos = static_cast<uint32_t>(~t.link);
-                    node.box = boxes[tree.order[pos]];
-                    node.first = pos, node.count = 1;
-                } else {
-                    memcpy(&node.box.lo, &tree.boxes[6ull * t.link], 12);
-                    memcpy(&node.box.hi, &tree.boxes[6ull * t.link + 3], 12);
-                    const uint32_t count = tree.last[t.link] - tree.first[t.link] + 1;
-                    if (count <= max_leaf_size) node.first = tree.first[t.link], node.count = count;
-                }
-                const int32_t id = static_cast<int32_t>(nodes.size());
-                nodes.push_back(node);
-                if (t.parent < 0) root = id;
-                else (t.is_left ? nodes[t.parent].left : nodes[t.parent].right) = id;
-                if (node.count == 0) {
-                    todo.push_back({tree.right[t.link], id, false});
-                    todo.push_back({tree.left[t.link], id, true});
-                }
-            }
-            FlattenBvh(nodes, root, 1024, &hs->nodes);
-            order = tree.order;
+            if (!BuildLbvhGpuFlat(flat.data(), static_cast<uint32_t>(nt), &scene_box.lo.x, &scene_box.hi.x, max_leaf_size, &hs->nodes, &order,
+                                  &hs->bvh_gpu_ms, error))
+                return false;
         } else {
             const char *ct_env = getenv("B200PT_SAH_TRAVERSAL_COST"); // tuning knob, default 1 triangle test per node step
             BvhBuilder builder(boxes, centers, max_leaf_size, ct_env ? static_cast<float>(atof(ct_env)) : 1.0f);
