@@ -241,7 +241,29 @@ class RayTracer:
         self.frame = np.zeros((self.height, self.width, 3), dtype=np.float32)
 
     def Draw(self, output_filename):
+        """csrt::RayTracer::Draw (ray_tracer.cpp:155-159): render, then image_io::Write.  A name ending in .pfm writes the
+        linear float frame losslessly instead of the reference's 8-bit sRGB PNG."""
         self.renderer.Draw(self.frame, self.width, self.height, self.spp)
-        from PIL import Image
-        Image.fromarray(linear_to_srgb8(self.frame)).save(output_filename)
+        if output_filename.lower().endswith(".pfm"):
+            write_pfm(output_filename, self.frame)
+        else:
+            from PIL import Image
+            Image.fromarray(linear_to_srgb8(self.frame)).save(output_filename)
         return self.frame
+
+
+def write_pfm(path, frame):
+    """Portable float map: "PF", size, negative scale = little endian, rows bottom-up, 3 x float32 per pixel."""
+    frame = np.ascontiguousarray(frame, dtype="<f4")
+    with open(path, "wb") as f:
+        f.write(f"PF\n{frame.shape[1]} {frame.shape[0]}\n-1.0\n".encode())
+        f.write(frame[::-1].tobytes())
+
+
+def read_pfm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"PF"
+        w, h = (int(x) for x in f.readline().split())
+        scale = float(f.readline())
+        data = np.frombuffer(f.read(), dtype="<f4" if scale < 0 else ">f4").reshape(h, w, 3)
+    return data[::-1].astype(np.float32)

@@ -71,3 +71,11 @@ def test_product_never_touches_the_oracle():
                 assert not re.search(r"#include\s+[\"<].*oracle/", text), name
     needed = subprocess.check_output(["readelf", "-d", os.path.join(pkg_dir, "libb200pt.so")], text=True)
     assert "oracle" not in needed and "csrt_ref" not in needed
+
+
+def test_pfm_frame_dump_round_trips(pkg, tmp_path):
+    """The float frame dump next to the reference's 8-bit PNG: lossless, top row first on read."""
+    import numpy as np
+    frame = np.random.RandomState(3).rand(5, 7, 3).astype(np.float32) * 4.0
+    pkg.write_pfm(str(tmp_path / "f.pfm"), frame)
+    assert np.array_equal(pkg.read_pfm(str(tmp_path / "f.pfm")), frame)
