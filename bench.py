@@ -334,16 +334,20 @@ def run_b200(args, workload):
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the contract asks for it at N=1 only
             try:
                 cpu = cpu_baseline(pack_path(name), width, height, REF_SPP_PER_STEP * 2, spp)
             except Exception as e:  # the reference build is test infrastructure; its absence must not hide the GPU number
                 cpu = {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
         ref_gpu = None
         if not args.no_cpu_baseline and world == 1:
-            renderer.close()  # frees the wavefront state before the reference allocates its managed scene
+            # in a child process: the comparator is foreign code on the same GPU and must not be able to take this line down
+            renderer.close()
             try:
-                ref_gpu = reference_gpu_baseline(pack_path(name), width, height, REF_SPP_PER_STEP * 2, spp)
+                import subprocess
+                probe = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--ref-gpu-probe"],
+                                       capture_output=True, text=True, timeout=600)
+                ref_gpu = json.loads(probe.stdout.strip().splitlines()[-1])
             except Exception as e:
                 ref_gpu = {"value": None, "unit": "Msamples/s", "sample": f"unavailable: {e}"}
         line = {
@@ -375,11 +379,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dragon-1024-256spp", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-gpu-probe", action="store_true", help=argparse.SUPPRESS)  # child process of the b200 arm
     args = ap.parse_args()
     workload = WORKLOADS[args.workload]
     if not os.path.exists(pack_path(workload[0])):
         raise SystemExit(f"scene pack {pack_path(workload[0])} missing; run __graft_entry__.build() where /root/reference exists")
-    if args.impl == "reference":
+    if args.ref_gpu_probe:
+        name, width, height, spp, _ = workload
+        print(json.dumps(reference_gpu_baseline(pack_path(name), width, height, REF_SPP_PER_STEP * 2, spp)))
+    elif args.impl == "reference":
         run_reference(args, workload)
     else:
         run_b200(args, workload)

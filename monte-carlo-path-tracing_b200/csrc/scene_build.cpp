@@ -1095,7 +1095,11 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
         for (uint32_t t = B200PT_BSDF_DIFFUSE; t <= B200PT_BSDF_PLASTIC; ++t) models += (bins >> t) & 1u;
         // escaped rays still need shading when an environment map lights them or a medium may scatter them first
         if (id_envmap != kInvalid || ig.type == B200PT_INTEGRATOR_VOLPATH) bins |= 1u;
-        ig.shade_bins = models >= 2 ? bins : 0u;
+        // One model only: binning is still worth it when many traced rays escape (their dead queue entries then never reach
+        // the shading kernel), i.e. in open scenes without an environment map; B200PT_BIN_SINGLE=0/1 overrides.
+        const char *bin_single = getenv("B200PT_BIN_SINGLE");
+        const bool single_binned = bin_single ? atoi(bin_single) != 0 : false;
+        ig.shade_bins = (models >= 2 || (models == 1 && single_binned)) ? bins : 0u;
         hs->tri_bsdf_type.resize(hs->tri_shade.size());
         for (size_t i = 0; i < hs->tri_shade.size(); ++i) {
             const uint32_t id_bsdf = hs->instances[hs->tri_shade[i].inst].id_bsdf;
