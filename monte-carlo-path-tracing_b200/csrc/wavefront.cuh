@@ -30,7 +30,7 @@ struct PathQueue {
     uint32_t *slot;           // sample slot inside the batch
     uint32_t *medium;         // volpath: medium the ray was scattered in, or kInvalid if it left a surface
     float *wx, *wy, *wz;      // volpath: `wo` of the last surface vertex (stale-wo behaviour of volpath.cpp)
-    HitRec *hit;              // closest hit, written by k_primary / k_extend
+    HitRec *hit;              // closest hit, written by k_primary / k_trace
 };
 
 struct ShadowQueue {
