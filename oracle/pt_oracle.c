@@ -2520,8 +2520,9 @@ int oracle_render(const b200pt_scene_desc *desc, int width, int height, int spp,
 
 /* Progressive preview frame: the body of DispathRaysCuda(camera, integrator, index_frame, frame, frame_srgb)
  * (renderer.cpp:97-138), which the reference only runs under CUDA + GLUT (ENABLE_VIEWER), restated for the CPU on top of the
- * pinned pieces (Tea<4>, VdC, ShadePath / ShadeVolPath).  The loop itself is NOT pinned against a reference run ("parity
- * unpinned" for these 30 lines; everything they call is pinned).  frame: running mean, updated in place; frame_srgb: sRGB
+ * pinned pieces (Tea<4>, VdC, ShadePath / ShadeVolPath).  The loop itself has no bit-exact pin: against the reference's CUDA
+ * build of this call it agrees statistically (profiles/r01_progressive_pin.log), as the reference's own CPU and CUDA backends
+ * do with each other; everything it calls is pinned bit for bit.  frame: running mean, updated in place; frame_srgb: sRGB
  * copy with row 0 at the bottom (may be NULL).  Single-threaded: meant for small frames. */
 int oracle_render_progressive(const b200pt_scene_desc *desc, int width, int height, int watertight, uint32_t index_frame, float *frame,
                               float *frame_srgb) {

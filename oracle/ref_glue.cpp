@@ -210,6 +210,25 @@ double ref_draw_cuda(void *handle, float *frame_host) {
     }
 }
 
+// The preview path as the reference runs it: csrt::Renderer::Draw(index_frame, frame, frame_srgb) (renderer.cpp:97-138,
+// 723-746), one call per displayed frame, running mean in managed memory.  Returns 0, or -1 with ref_last_error().
+int ref_draw_progressive_cuda(void *handle, uint32_t num_frames, float *frame_host, float *frame_srgb_host) {
+    try {
+        CudaRef *r = static_cast<CudaRef *>(handle);
+        float *srgb = csrt::MallocArray<float>(csrt::BackendType::kCuda, r->count);
+        memset(r->frame, 0, r->count * sizeof(float));
+        StderrSilencer quiet;
+        for (uint32_t k = 0; k < num_frames; ++k) r->renderer->Draw(k, r->frame, srgb);
+        if (frame_host) memcpy(frame_host, r->frame, r->count * sizeof(float));
+        if (frame_srgb_host) memcpy(frame_srgb_host, srgb, r->count * sizeof(float));
+        csrt::DeleteArray(csrt::BackendType::kCuda, srgb);
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
 void ref_destroy_cuda(void *handle) {
     CudaRef *r = static_cast<CudaRef *>(handle);
     if (!r) return;
