@@ -190,7 +190,7 @@ typedef struct b200pt_context *b200pt_handle;
 
 typedef struct b200pt_create_opts {
     int32_t device;          /* CUDA ordinal; -1 = current device */
-    uint32_t max_leaf_size;  /* BVH leaf size, 0 = default (4) */
+    uint32_t max_leaf_size;  /* BVH leaf size, 0 = default (4; the 8-wide layout holds at most 3 per leaf slot) */
     uint64_t max_paths_in_flight; /* wavefront capacity in paths, 0 = default */
     uint32_t flags;          /* B200PT_CREATE_* bit mask */
     uint32_t reserved;
@@ -200,6 +200,10 @@ typedef struct b200pt_create_opts {
  * the host binned-SAH builder: the tree is ready in milliseconds instead of seconds, traversal is slower.
  * Replaces csrt::BvhBuilder::Build (src/rtcore/accel/bvh_builder.cpp:50-206), also an LBVH. */
 #define B200PT_CREATE_GPU_LBVH 1u
+/* Keep the host SAH tree in the binary layout (two child boxes per 64-byte node) instead of collapsing it into the default
+ * compressed 8-wide layout (eight quantised child boxes per 80-byte node).  Both find the same hits; the binary walk is
+ * the slower one and stays as the cross-check of the wide one. */
+#define B200PT_CREATE_BVH2 2u
 
 /* What to render.  width/height/spp = 0 take the value from the scene's camera
  * (the reference CLI overrides them after parsing: apps/main.cpp:46-52). */
@@ -222,7 +226,8 @@ typedef struct b200pt_kernel_stats {
     double ms;                   /* summed device time of its launches (B200PT_STATS_TIMING) */
     uint64_t launches;
     uint64_t rays;               /* rays traced by it (B200PT_STATS_COUNTERS) */
-    uint64_t node_visits;        /* child-box tests, 2 per 64-byte node fetched */
+    uint64_t node_visits;        /* 8-wide layout: 80-byte nodes fetched (8 child-box tests each);
+                                    binary layout: child-box tests, 2 per 64-byte node fetched */
     uint64_t prim_tests;         /* ray-triangle / ray-analytic tests */
 } b200pt_kernel_stats;
 
@@ -236,6 +241,8 @@ typedef struct b200pt_stats {
     uint64_t samples;            /* width*height*spp rendered by this rank */
     uint64_t kernel_launches;    /* kernels launched by the last render */
     uint64_t num_bvh_nodes, num_triangles, num_prims;
+    uint32_t bvh_width;          /* 8 = compressed wide layout (80-byte nodes), 2 = binary layout (64-byte nodes) */
+    uint32_t bvh_depth;          /* levels of the wide tree (0 for the binary layout) */
     uint64_t local_tiles, active_tiles; /* 8x8 tiles owned by this rank / those that passed the visibility pre-pass */
     b200pt_kernel_stats primary; /* k_primary: ray-gen + closest hit of camera rays */
     b200pt_kernel_stats extend;  /* k_trace  : closest hit of bounce rays + any-hit of NEE rays in ONE launch per bounce;
@@ -287,6 +294,24 @@ const char *b200pt_last_error(b200pt_handle h);   /* h may be NULL: last error o
 int b200pt_get_kulla_conty(b200pt_handle h, float *brdf_avg_128x128, float *albedo_avg_128);
 int b200pt_get_envmap_tables(b200pt_handle h, float *out, uint64_t capacity_floats, uint64_t *num_floats,
                              float *normalization);
+
+/* ---- test hooks: pointwise access to the device leaf functions, so that tests can compare them with the reference's
+ * functions at fixed inputs instead of through whole images.  Not needed by a renderer host. ---- */
+typedef struct b200pt_debug_ray {
+    float o[3], d[3];        /* origin, unit direction (csrt::Ray, include/csrt/rtcore/ray.hpp:9-27) */
+    float tmin, tmax;        /* the reference constructs rays with t_min = 1e-4, t_max = FLT_MAX (ray.cpp:18-20) */
+} b200pt_debug_ray;
+typedef struct b200pt_debug_hit {
+    float t;                 /* csrt::Ray::t_max after TLAS::Intersect (tlas.cpp:13-43); tmax of the input ray on a miss */
+    uint32_t prim;           /* 0xFFFFFFFF miss | 0x80000000 + index of the sphere / disk / cylinder among the analytic
+                                instances | index of the triangle in the scene description's enumeration (instances in
+                                order, their triangles in order), + 0x40000000 when hit from its back side */
+    float u, v;              /* triangle: barycentric weights of vertex 0 and 1 (triangle.cpp:64-87) */
+} b200pt_debug_hit;
+#define B200PT_DEBUG_ANY_HIT 1u      /* TLAS::IntersectAny (tlas.cpp:44-76): prim = 0 if occluded, 0xFFFFFFFF if not */
+#define B200PT_DEBUG_PER_LANE_LOOP 2u /* the tail kernel's one-ray-per-lane loop instead of the persistent loop */
+/* rays_host / hits_host: n elements each, HOST memory.  Runs the product's traversal kernels on the scene's tree. */
+int b200pt_debug_trace(b200pt_handle h, const b200pt_debug_ray *rays_host, uint64_t n, uint32_t flags, b200pt_debug_hit *hits_host);
 
 /* ---- scene packs: a lossless binary serialisation of b200pt_scene_desc, so a
  * scene parsed once by the reference's XML parser can travel without it. ---- */

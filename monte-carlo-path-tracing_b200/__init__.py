@@ -50,12 +50,16 @@ STATS_COUNTERS = 1  # B200PT_STATS_COUNTERS
 STATS_TIMING = 2    # B200PT_STATS_TIMING
 RENDER_NO_TILE_CULL = 1  # B200PT_RENDER_NO_TILE_CULL
 CREATE_GPU_LBVH = 1      # B200PT_CREATE_GPU_LBVH
+CREATE_BVH2 = 2          # B200PT_CREATE_BVH2
+DEBUG_ANY_HIT = 1        # B200PT_DEBUG_ANY_HIT
+DEBUG_PER_LANE_LOOP = 2  # B200PT_DEBUG_PER_LANE_LOOP
 
 
 class Stats(ctypes.Structure):
     _fields_ = [("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double), ("bvh_build_ms", ctypes.c_double),
                 ("bvh_gpu_ms", ctypes.c_double), ("samples", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
                 ("num_bvh_nodes", ctypes.c_uint64), ("num_triangles", ctypes.c_uint64), ("num_prims", ctypes.c_uint64),
+                ("bvh_width", ctypes.c_uint32), ("bvh_depth", ctypes.c_uint32),
                 ("local_tiles", ctypes.c_uint64), ("active_tiles", ctypes.c_uint64),
                 ("primary", KernelStats), ("extend", KernelStats), ("shadow", KernelStats), ("shade", KernelStats),
                 ("other", KernelStats), ("tail", KernelStats)]
@@ -73,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "b200pt_create", "b200pt_destroy", "b200pt_render", "b200pt_render_device", "b200pt_render_progressive_device", "b200pt_tile_buffer_floats",
     "b200pt_render_tiles_device", "b200pt_assemble_tiles_device", "b200pt_get_stats", "b200pt_last_error",
     "b200pt_get_kulla_conty", "b200pt_get_envmap_tables", "b200pt_scene_load", "b200pt_scene_save",
-    "b200pt_scene_get_desc", "b200pt_scene_free",
+    "b200pt_scene_get_desc", "b200pt_scene_free", "b200pt_debug_trace",
 ]
 
 _lib = None
@@ -110,6 +114,7 @@ def lib():
     L.b200pt_scene_get_desc.restype = vp
     L.b200pt_scene_free.argtypes = [vp]
     L.b200pt_scene_free.restype = None
+    L.b200pt_debug_trace.argtypes = [vp, vp, u64, u32, vp]
     _lib = L
     return L
 
@@ -188,6 +193,15 @@ class Renderer:
     def assemble_tiles_device(self, gathered_tensor, frame_tensor, width, height, tile_world, stream=None):
         _check(lib().b200pt_assemble_tiles_device(self._h, width, height, tile_world, gathered_tensor.data_ptr(),
                                                   frame_tensor.data_ptr(), stream), self._h)
+
+    def debug_trace(self, rays, any_hit=False, per_lane_loop=False):
+        """Test hook (b200pt_debug_trace): rays = float32 [n, 8] (origin, direction, tmin, tmax) through the traversal kernels.
+        Returns (t [n] float32, prim [n] uint32, uv [n, 2] float32)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        out = np.zeros((len(rays), 4), dtype=np.float32)
+        flags = (DEBUG_ANY_HIT if any_hit else 0) | (DEBUG_PER_LANE_LOOP if per_lane_loop else 0)
+        _check(lib().b200pt_debug_trace(self._h, rays.ctypes.data, len(rays), flags, out.ctypes.data), self._h)
+        return out[:, 0].copy(), out[:, 1].copy().view(np.uint32), out[:, 2:4].copy()
 
     def stats(self):
         s = Stats()

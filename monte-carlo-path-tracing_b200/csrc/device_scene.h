@@ -43,8 +43,27 @@ struct BvhNode {            // 64 B
 };
 
 struct TriVerts {           // 48 B
-    F4 v0, v1, v2;          // .w of v0 = bit pattern of instance id
+    F4 v0, v1, v2;          // .w of v0 = bit pattern of instance id; .w of v1 = bit pattern of the triangle's index in
+                            // the scene description (instances in order, triangles in order: the debug ray entry reports it)
 };
+
+// Compressed 8-wide BVH node (Ylitie, Karras, Laine 2017), 80 B = 5 x 16 B loads.  Child boxes are quantised to 8 bits per
+// plane on the grid origin + q * 2^e of the node's own box (rounded outwards, so a quantised box contains the exact one).
+// Children sit in octant slots: slot s holds the child whose centre lies furthest in direction (s&1 ? +x : -x, s&2 ? +y : -y,
+// s&4 ? +z : -z), so a ray visits slots in descending order of (s ^ r), r = bits of the ray's positive direction components.
+//   meta[s] = 0                              empty slot
+//           = 0b001'00000 | (24 + s)         inner node: the k-th set bit of imask below s is child_base + k
+//           = unary(count) << 5 | offset     leaf of 1..3 triangles tri_base + offset .. (offset < 24)
+struct WideNode {
+    float origin[3];
+    uint8_t e[3];           // biased exponents of the grid spacing per axis: 2^(e - 127)
+    uint8_t imask;          // slots that hold inner nodes
+    uint32_t child_base;    // first inner child (children of one node are contiguous, in slot order)
+    uint32_t tri_base;      // first triangle of this node's leaves
+    uint8_t meta[8];
+    uint8_t qlo_x[8], qlo_y[8], qlo_z[8], qhi_x[8], qhi_y[8], qhi_z[8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
 
 struct TriShade {           // 112 B
     float n[3][3];          // per-vertex shading normals (world, unnormalised as in scene.cpp:261-281)
@@ -127,7 +146,8 @@ struct DIntegrator {
 
 // Everything the kernels dereference.  Passed by value as a kernel parameter.
 struct DeviceScene {
-    const BvhNode *nodes;        uint32_t num_nodes;
+    const BvhNode *nodes;        uint32_t num_nodes;     // BVH2 layout (B200PT_CREATE_BVH2 / the GPU LBVH builder), else empty
+    const WideNode *wide_nodes;  uint32_t num_wide_nodes; // compressed BVH8 layout (default); exactly one of the two is populated
     const TriVerts *tri_verts;   uint32_t num_tris;
     const TriShade *tri_shade;
     const uint8_t *tri_bsdf_type; // per triangle: b200pt_bsdf_type of its instance's BSDF (0 = none), the shading bin of a hit

@@ -18,6 +18,7 @@
 #include "b200pt.h"
 #include "host_scene.hpp"
 #include "host_util.hpp"
+#include "traverse_wide.cuh"
 #include "wavefront.cuh"
 
 using namespace b200pt;
@@ -83,6 +84,7 @@ struct b200pt_context {
     b200pt_stats stats{};
 
     DeviceArray<BvhNode> nodes;
+    DeviceArray<WideNode> wide_nodes;
     DeviceArray<TriVerts> tri_verts;
     DeviceArray<TriShade> tri_shade;
     DeviceArray<uint8_t> tri_bsdf_type;
@@ -120,6 +122,8 @@ struct b200pt_context {
     int num_sms = 148;
     // launch tunables (overridable through the environment for experiments: B200PT_TOP_NODES, B200PT_REFILL, B200PT_CTAS_PER_SM)
     int top_nodes = 0, refill = 20, ctas_per_sm = 4, min_inner = 8; // top_nodes = 0: no shared-memory staging (profiles/r01_sweep_sel3_topnodes.log)
+    int tri_min = 8;              // B200PT_TRI_MIN: triangle postponing threshold of the wide traversal (LaunchConfig::tri_min)
+    uint32_t wide_top_nodes = 0;  // nodes at the head of the wide node array that were laid out breadth-first
     // B200PT_STATS_TIMING: (class, begin, end) per launch, resolved in b200pt_get_stats
     struct TimedLaunch {
         int cls;
@@ -177,6 +181,7 @@ namespace {
 int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     HostScene &h = c->host;
     CU_CHECK(c, c->nodes.Upload(h.nodes));
+    CU_CHECK(c, c->wide_nodes.Upload(h.wide_nodes));
     CU_CHECK(c, c->tri_verts.Upload(h.tri_verts));
     CU_CHECK(c, c->tri_shade.Upload(h.tri_shade));
     CU_CHECK(c, c->tri_bsdf_type.Upload(h.tri_bsdf_type));
@@ -200,6 +205,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
 
     DeviceScene &s = c->scene;
     s.nodes = c->nodes.ptr, s.num_nodes = static_cast<uint32_t>(h.nodes.size());
+    s.wide_nodes = c->wide_nodes.ptr, s.num_wide_nodes = static_cast<uint32_t>(h.wide_nodes.size());
     s.tri_verts = c->tri_verts.ptr, s.num_tris = static_cast<uint32_t>(h.tri_verts.size());
     s.tri_shade = c->tri_shade.ptr;
     s.tri_bsdf_type = c->tri_bsdf_type.ptr;
@@ -233,13 +239,17 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
         }
         c->shade_only = (mixed || getenv("B200PT_GENERIC_SHADE")) ? -1 : only;
     }
-    c->stats.num_bvh_nodes = h.nodes.size();
+    c->stats.num_bvh_nodes = h.wide_nodes.empty() ? h.nodes.size() : h.wide_nodes.size();
+    c->stats.bvh_width = h.wide_nodes.empty() ? 2u : 8u;
+    c->stats.bvh_depth = h.wide_depth;
+    c->wide_top_nodes = h.wide_top_nodes;
     c->stats.num_triangles = h.tri_verts.size();
     c->stats.num_prims = h.tri_verts.size() + h.analytic.size();
     c->stats.bvh_build_ms = h.bvh_build_ms;
     c->stats.bvh_gpu_ms = h.bvh_gpu_ms;
     // the big host copies are not needed any more
     std::vector<BvhNode>().swap(h.nodes);
+    std::vector<WideNode>().swap(h.wide_nodes);
     std::vector<TriVerts>().swap(h.tri_verts);
     std::vector<TriShade>().swap(h.tri_shade);
     return B200PT_OK;
@@ -377,6 +387,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     lc.top_nodes = c->top_nodes;
     lc.refill = c->refill;
     lc.min_inner = c->min_inner;
+    lc.tri_min = c->tri_min;
     lc.blocks = c->num_sms * c->ctas_per_sm;
     lc.shade_only = c->shade_only;
 
@@ -426,7 +437,9 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     const uint32_t num_chunks = chunks_per_arena * S;
     const uint32_t pixels_per_chunk = std::max<uint32_t>(1, (job_pixels + num_chunks - 1) / num_chunks);
     const uint32_t samples_per_batch = std::max<uint32_t>(1, std::min<uint32_t>(ro.spp, capacity / pixels_per_chunk));
-    const uint32_t max_rounds = std::min<uint32_t>(ig.depth_max, kMaxRounds);
+    // path.cpp:57-60: `depth < depth_rr || (depth < depth_max && rand < pdf_rr)` keeps a path going until
+    // max(depth_rr, depth_max) — a scene with max_depth below rr_depth (parser default 5) still walks rr_depth - 1 vertices.
+    const uint32_t max_rounds = std::min<uint32_t>(std::max(ig.depth_rr, ig.depth_max), kMaxRounds);
 
     CU_CHECK(c, cudaMemsetAsync(c->accum.ptr, 0, 3ull * local_pixels * sizeof(float), stream));
     CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, sizeof(Counters) * kMaxArenas, stream));
@@ -605,7 +618,8 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
         const char *v = getenv(name);
         return v ? std::min(std::max(atoi(v), lo), hi) : fallback;
     };
-    c->top_nodes = env_int("B200PT_TOP_NODES", c->top_nodes, 0, kTopNodesMax);
+    c->top_nodes = env_int("B200PT_TOP_NODES", c->top_nodes, 0, kWideTopNodesMax);
+    c->tri_min = env_int("B200PT_TRI_MIN", c->tri_min, 0, 32);
     c->refill = env_int("B200PT_REFILL", c->refill, 1, 32);
     c->min_inner = env_int("B200PT_MIN_INNER", c->min_inner, 1, 32);
     c->ctas_per_sm = env_int("B200PT_CTAS_PER_SM", c->ctas_per_sm, 1, 16);
@@ -616,7 +630,9 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     const auto t0 = std::chrono::steady_clock::now();
     const char *builder_env = getenv("B200PT_BVH_BUILDER"); // "lbvh" / "sah": overrides the create option (experiments)
     const bool gpu_lbvh = builder_env ? std::string(builder_env) == "lbvh" : (opts && (opts->flags & B200PT_CREATE_GPU_LBVH));
-    if (!BuildHostScene(*scene, opts ? opts->max_leaf_size : 0, gpu_lbvh, &c->host, &err)) {
+    const char *layout_env = getenv("B200PT_BVH_LAYOUT");   // "2" / "8": overrides the create option (experiments)
+    const bool bvh2 = layout_env ? atoi(layout_env) == 2 : (opts && (opts->flags & B200PT_CREATE_BVH2));
+    if (!BuildHostScene(*scene, opts ? opts->max_leaf_size : 0, gpu_lbvh, bvh2, &c->host, &err)) {
         // same prefix as renderer.cpp:343-346
         return SetGlobalError(B200PT_EINVAL, "error when commit renderer.\n\t" + err);
     }
@@ -710,7 +726,7 @@ int b200pt_assemble_tiles_device(b200pt_handle h, uint32_t width, uint32_t heigh
     CU_CHECK(h, cudaSetDevice(h->device));
     LaunchConfig lc{};
     lc.blocks = h->num_sms * 4, lc.threads = 256, lc.stream = static_cast<cudaStream_t>(stream), lc.stats = false;
-    lc.top_nodes = h->top_nodes, lc.refill = h->refill, lc.min_inner = h->min_inner;
+    lc.top_nodes = h->top_nodes, lc.refill = h->refill, lc.min_inner = h->min_inner, lc.tri_min = h->tri_min;
     LaunchAssemble(lc, width, height, tile_world, PixelsPerRank(width, height, tile_world), gathered_dev, frame_dev);
     CU_CHECK(h, cudaGetLastError());
     return B200PT_OK;
@@ -751,6 +767,30 @@ int b200pt_get_stats(b200pt_handle h, b200pt_stats *out) {
         h->timing_pending = false;
     }
     *out = h->stats;
+    return B200PT_OK;
+}
+
+int b200pt_debug_trace(b200pt_handle h, const b200pt_debug_ray *rays_host, uint64_t n, uint32_t flags, b200pt_debug_hit *hits_host) {
+    if (!h || (n && (!rays_host || !hits_host))) return SetGlobalError(B200PT_EINVAL, "b200pt_debug_trace: null argument");
+    if (n == 0) return B200PT_OK;
+    if (n > (1ull << 30)) return h->Fail(B200PT_EINVAL, "b200pt_debug_trace: too many rays.");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    DeviceArray<b200pt_debug_ray> rays;
+    DeviceArray<b200pt_debug_hit> hits;
+    DeviceArray<uint32_t> counter;
+    CU_CHECK(h, rays.Alloc(n));
+    CU_CHECK(h, hits.Alloc(n));
+    CU_CHECK(h, counter.Alloc(1));
+    CU_CHECK(h, cudaMemcpyAsync(rays.ptr, rays_host, n * sizeof(b200pt_debug_ray), cudaMemcpyHostToDevice, h->stream));
+    CU_CHECK(h, cudaMemsetAsync(counter.ptr, 0, sizeof(uint32_t), h->stream));
+    LaunchConfig lc{};
+    lc.blocks = h->num_sms * h->ctas_per_sm, lc.threads = 256, lc.stream = h->stream, lc.stats = false;
+    lc.top_nodes = 0, lc.refill = h->refill, lc.min_inner = h->min_inner, lc.tri_min = h->tri_min;
+    LaunchDebugTrace(lc, h->scene, rays.ptr, static_cast<uint32_t>(n), (flags & B200PT_DEBUG_ANY_HIT) != 0, (flags & B200PT_DEBUG_PER_LANE_LOOP) != 0,
+                     hits.ptr, counter.ptr);
+    CU_CHECK(h, cudaGetLastError());
+    CU_CHECK(h, cudaMemcpyAsync(hits_host, hits.ptr, n * sizeof(b200pt_debug_hit), cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
     return B200PT_OK;
 }
 

@@ -23,6 +23,7 @@
 #include <thread>
 
 #include "bvh_gpu.hpp"
+#include "bvh_wide.hpp"
 #include "host_scene.hpp"
 
 namespace b200pt {
@@ -33,6 +34,7 @@ constexpr float kPi = 3.141592653589793f;
 constexpr float k2Pi = kPi * 2.0f;
 constexpr float k1DivPi = 1.0f / kPi;
 constexpr float kFltMax = 3.402823466e+38f;
+constexpr uint32_t kBvh2StackSize = 64; // = kStackSize of traverse.cuh
 
 struct V3 {
     float x, y, z;
@@ -288,6 +290,7 @@ public:
 
 private:
     static constexpr int kBins = 32;
+    static constexpr int kMedianSplitDepth = 32; // + ceil(log2(2^28 triangles)) = 60 levels at most < kStackSize (64)
 
     // Sub-ranges of order_ are disjoint, node slots come from an atomic counter: large subtrees build on their own thread.
     int32_t Recurse(uint32_t begin, uint32_t end, int depth) {
@@ -347,8 +350,9 @@ private:
         if (n <= max_leaf_ && (best_axis < 0 || best_cost + traversal_cost_ * box.HalfArea() >= leaf_cost)) return make_leaf();
 
         uint32_t mid;
-        if (best_axis < 0) {
-            mid = begin + n / 2; // all centroids coincide: split the list
+        if (best_axis < 0 || depth >= kMedianSplitDepth) {
+            // all centroids coincide, or the tree is getting deep (peeling off a sliver per level): split the list in halves,
+            // which bounds the depth by kMedianSplitDepth + log2(n) and keeps the traversal stacks (traverse.cuh) safe
         } else {
             const float lo = (&cbox.lo.x)[best_axis], scale = kBins / (&ext.x)[best_axis];
             auto it = std::partition(order_.begin() + begin, order_.begin() + end, [&](uint32_t t) {
@@ -443,6 +447,21 @@ void FlattenBvh(const std::vector<BuildNode> &bn, int32_t root, uint32_t top_nod
         n.child1 = r.left >= 0 ? out_index[src.right] : EncodeLeaf(r.first, r.count);
         (*out)[i] = n;
     }
+}
+
+// Number of inner-node levels of a flattened tree = the most entries a traversal can have on its stack, plus one.
+uint32_t FlatBvhDepth(const std::vector<BvhNode> &nodes) {
+    if (nodes.empty()) return 0;
+    uint32_t deepest = 0;
+    std::vector<std::pair<int32_t, uint32_t>> stack{{0, 1u}};
+    while (!stack.empty()) {
+        const auto [id, depth] = stack.back();
+        stack.pop_back();
+        deepest = std::max(deepest, depth);
+        if (nodes[id].child0 >= 0) stack.push_back({nodes[id].child0, depth + 1});
+        if (nodes[id].child1 >= 0) stack.push_back({nodes[id].child1, depth + 1});
+    }
+    return deepest;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -639,7 +658,8 @@ DCamera MakeCamera(const b200pt_camera &cam, uint32_t width, uint32_t height) {
     return c;
 }
 
-bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu_lbvh, HostScene *hs, std::string *error) {
+bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu_lbvh, bool bvh2, HostScene *hs, std::string *error) {
+    const bool wide = !bvh2 && !gpu_lbvh; // the GPU builder emits the binary layout directly
     if (d.abi_version != B200PT_ABI_VERSION) {
         *error = "b200pt_scene_desc.abi_version mismatch";
         return false;
@@ -906,11 +926,14 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
         scene_box.Grow(boxes[i]);
     }
     std::vector<uint32_t> order;
+    std::vector<Bvh2Node> binary; // the SAH tree as handed to the wide collapse / the cull-box cut
+    int32_t binary_root = -1;
     if (nt > 0) {
         if (nt >= (1u << 28)) {
             *error = "too many triangles for the leaf encoding.";
             return false;
         }
+        bool built = false;
         if (gpu_lbvh && nt > 64) {
             // GPU LBVH (bvh_gpu.cu): Morton sort, radix tree, refit, leaves of <= max_leaf triangles and the traversal
             // layout are all produced on the device; the host only permutes the triangle attributes afterwards.
@@ -922,12 +945,37 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             if (!BuildLbvhGpuFlat(flat.data(), static_cast<uint32_t>(nt), &scene_box.lo.x, &scene_box.hi.x, max_leaf_size, &hs->nodes, &order,
                                   &hs->bvh_gpu_ms, error))
                 return false;
-        } else {
+            // A radix tree over 63-bit Morton keys + index tie-break can be ~95 levels deep on clustered input; the
+            // traversal stack holds kStackSize entries.  Such a tree is rebuilt with the (depth-bounded) SAH builder.
+            built = FlatBvhDepth(hs->nodes) < kBvh2StackSize;
+            if (!built) hs->nodes.clear();
+        }
+        if (!built) {
             const char *ct_env = getenv("B200PT_SAH_TRAVERSAL_COST"); // tuning knob, default 1 triangle test per node step
-            BvhBuilder builder(boxes, centers, max_leaf_size, ct_env ? static_cast<float>(atof(ct_env)) : 1.0f);
-            const int32_t root = builder.Build();
-            FlattenBvh(builder.nodes(), root, 1024, &hs->nodes);
+            BvhBuilder builder(boxes, centers, wide ? std::min(max_leaf_size, kWideMaxLeaf) : max_leaf_size,
+                               ct_env ? static_cast<float>(atof(ct_env)) : 1.0f);
+            binary_root = builder.Build();
             order = builder.order();
+            if (wide) {
+                const std::vector<BuildNode> &bn = builder.nodes();
+                binary.resize(bn.size());
+                for (size_t i = 0; i < bn.size(); ++i) {
+                    memcpy(binary[i].lo, &bn[i].box.lo, 12), memcpy(binary[i].hi, &bn[i].box.hi, 12);
+                    binary[i].left = bn[i].left, binary[i].right = bn[i].right;
+                    binary[i].first = bn[i].first, binary[i].count = bn[i].count;
+                }
+                const char *top_env = getenv("B200PT_WIDE_TOP_TARGET");
+                WideBuildInfo info;
+                if (!BuildWideBvh(binary, binary_root, top_env ? static_cast<uint32_t>(atoi(top_env)) : 2048u, &order, &hs->wide_nodes, &info, error))
+                    return false;
+                hs->wide_depth = info.depth, hs->wide_top_nodes = info.top_nodes;
+            } else {
+                FlattenBvh(builder.nodes(), binary_root, 1024, &hs->nodes);
+                if (FlatBvhDepth(hs->nodes) >= kBvh2StackSize) {
+                    *error = "BVH too deep for the traversal stack.";
+                    return false;
+                }
+            }
         }
     }
     hs->tri_verts.resize(nt);
@@ -938,7 +986,9 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
         float inst_bits;
         memcpy(&inst_bits, &t.inst, 4);
         v.v0 = {t.p[0].x, t.p[0].y, t.p[0].z, inst_bits};
-        v.v1 = {t.p[1].x, t.p[1].y, t.p[1].z, 0.0f};
+        float id_bits; // index of the triangle in the scene description (instances in order): what the debug ray entry reports
+        memcpy(&id_bits, &order[i], 4);
+        v.v1 = {t.p[1].x, t.p[1].y, t.p[1].z, id_bits};
         v.v2 = {t.p[2].x, t.p[2].y, t.p[2].z, 0.0f};
         TriShade &s = hs->tri_shade[i];
         memset(&s, 0, sizeof(s));
@@ -965,15 +1015,25 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
                 return dx * dy + dy * dz + dz * dx;
             }
         };
+        // children of an inner node of whichever binary tree exists: the flattened layout, or the SAH tree behind the wide layout
         auto children = [&](int32_t node, CutBox *a, CutBox *b) {
+            if (!binary.empty()) {
+                const Bvh2Node &l = binary[binary[node].left], &r = binary[binary[node].right];
+                *a = {{l.lo[0], l.lo[1], l.lo[2]}, {l.hi[0], l.hi[1], l.hi[2]}, l.left >= 0 ? binary[node].left : -1};
+                *b = {{r.lo[0], r.lo[1], r.lo[2]}, {r.hi[0], r.hi[1], r.hi[2]}, r.left >= 0 ? binary[node].right : -1};
+                return;
+            }
             const BvhNode &n = hs->nodes[node];
             *a = {{n.c0xy.x, n.c0xy.z, n.cz.x}, {n.c0xy.y, n.c0xy.w, n.cz.y}, n.child0};
             *b = {{n.c1xy.x, n.c1xy.z, n.cz.z}, {n.c1xy.y, n.c1xy.w, n.cz.w}, n.child1};
         };
         std::vector<CutBox> cut;
-        if (!hs->nodes.empty()) {
+        if (!binary.empty() && binary[binary_root].left < 0) { // the whole scene is one leaf
+            const Bvh2Node &n = binary[binary_root];
+            cut.push_back({{n.lo[0], n.lo[1], n.lo[2]}, {n.hi[0], n.hi[1], n.hi[2]}, -1});
+        } else if (!binary.empty() || !hs->nodes.empty()) {
             CutBox a, b;
-            children(0, &a, &b);
+            children(binary.empty() ? 0 : binary_root, &a, &b);
             cut.push_back(a);
             cut.push_back(b);
             while (cut.size() < kMaxCullBoxes) {

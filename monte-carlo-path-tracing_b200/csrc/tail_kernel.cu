@@ -13,12 +13,20 @@
 // Taking over earlier (more paths) loses: the generic shading code and lane-divergent traversal are much less efficient
 // per path than the binned, compacted wavefront kernels.
 #include "shade_kernel.cuh"
+#include "traverse_wide.cuh"
 
 namespace b200pt {
 
 namespace {
 
 constexpr int kTailThreads = 128;
+
+// The per-lane traversal of whichever tree the scene was created with (a warp-uniform choice).
+__device__ __forceinline__ bool TraceSingle(const DeviceScene &scene, const Ray &ray, bool any, bool opacity, const Rng &rng, HitRec *hit,
+                                            bool stats, TraversalCounters *counters) {
+    if (scene.num_wide_nodes > 0) return TraverseSingleWide(scene, ray, any, opacity, rng, hit, stats, counters);
+    return TraverseSingle(scene, ray, any, opacity, rng, hit, stats, counters);
+}
 
 template <bool VOL>
 __global__ void __launch_bounds__(kTailThreads) k_tail(const __grid_constant__ DeviceScene scene, const __grid_constant__ BatchParams bp,
@@ -61,7 +69,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const __grid_constant__ D
                     }
                     HitRec unused;
                     ++rays[1];
-                    if (!TraverseSingle(scene, ray, true, opacity, Rng(ctr.x, ctr.y, ctr.z, bp.key, kRngDomainShadow), &unused, stats, &tc[1])) {
+                    if (!TraceSingle(scene, ray, true, opacity, Rng(ctr.x, ctr.y, ctr.z, bp.key, kRngDomainShadow), &unused, stats, &tc[1])) {
                         radiance[slot] += sc.c.x;
                         radiance[capacity + slot] += sc.c.y;
                         radiance[2 * capacity + slot] += sc.c.z;
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const __grid_constant__ D
                 uint3 ctr = make_uint3(0, 0, 0);
                 if (opacity) ctr = SlotCounter(bp, slot, depth);
                 ++rays[0];
-                TraverseSingle(scene, v.ray, false, opacity, Rng(ctr.x, ctr.y, ctr.z, bp.key, kRngDomainClosest), &v.hit, stats, &tc[0]);
+                TraceSingle(scene, v.ray, false, opacity, Rng(ctr.x, ctr.y, ctr.z, bp.key, kRngDomainClosest), &v.hit, stats, &tc[0]);
                 // same shortcut as LoadPathVertex: an escaped ray with no environment map to see is finished
                 if (!VOL && v.hit.prim == kPrimMiss && ig.id_envmap == kInvalid) alive = false;
             }

@@ -13,6 +13,7 @@
 
 #include "shade_kernel.cuh"
 #include "shading.cuh"
+#include "traverse_wide.cuh"
 #include "wavefront.cuh"
 
 namespace b200pt {
@@ -26,13 +27,11 @@ constexpr int kThreads = 256;
 
 __device__ __forceinline__ uint32_t SmemAddr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-// Stage the top of the BVH (nodes [0, num_top), breadth-first order) into shared memory with one
-// TMA bulk copy (cp.async.bulk, completion signalled on an mbarrier).  Every ray walks these
-// nodes, so they are served at shared-memory latency instead of L2.
-__device__ __forceinline__ int StageTopNodes(const DeviceScene &scene, float4 *top, uint64_t *bar, int max_top) {
-    const int num_top = min(static_cast<int>(scene.num_nodes), max_top);
-    if (num_top == 0) return 0;
-    const uint32_t bytes = static_cast<uint32_t>(num_top) * sizeof(BvhNode);
+// Stage the top of the BVH (the first `bytes` of the node array, stored breadth-first) into shared memory with one
+// TMA bulk copy (cp.async.bulk, completion signalled on an mbarrier).  Every ray walks these nodes, so they are
+// served at shared-memory latency instead of L1/L2.
+__device__ __forceinline__ void StageTop(const void *nodes, uint32_t bytes, void *top, uint64_t *bar) {
+    if (bytes == 0) return;
     const uint32_t bar_addr = SmemAddr(bar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
@@ -43,7 +42,7 @@ __device__ __forceinline__ int StageTopNodes(const DeviceScene &scene, float4 *t
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          SmemAddr(top)),
-                     "l"(scene.nodes), "r"(bytes), "r"(bar_addr)
+                     "l"(nodes), "r"(bytes), "r"(bar_addr)
                      : "memory");
     }
     uint32_t done = 0;
@@ -53,7 +52,22 @@ __device__ __forceinline__ int StageTopNodes(const DeviceScene &scene, float4 *t
                      : "r"(bar_addr)
                      : "memory");
     }
-    return num_top;
+}
+
+// Which tree the traversal kernels walk: the binary layout (cross-check / GPU-built trees), the compressed 8-wide layout
+// (default), or the wide layout with its top nodes staged in shared memory.
+enum TraversalLayout { kLayoutBinary = 0, kLayoutWide = 1, kLayoutWideTop = 2 };
+
+// The persistent traversal loop of the layout the kernel was instantiated for.
+template <bool MIXED, bool STATS, bool OPACITY, int LAYOUT, typename Fetch, typename Finish>
+__device__ __forceinline__ void TraverseLayout(const DeviceScene &scene, const uint4 *top, uint32_t num_top, uint32_t num_rays, uint32_t *work_counter,
+                                               int refill, int phase_lanes, uint2 key, Fetch fetch, Finish finish, TraversalCounters *tc,
+                                               uint32_t *rays) {
+    if constexpr (LAYOUT == kLayoutBinary)
+        TraversePersistent<MIXED, STATS, OPACITY, false>(scene, nullptr, 0, num_rays, work_counter, refill, phase_lanes, key, fetch, finish, tc, rays);
+    else
+        TraversePersistentWide<MIXED, STATS, OPACITY, LAYOUT == kLayoutWideTop>(scene, top, num_top, num_rays, work_counter, refill, phase_lanes, key,
+                                                                                 fetch, finish, tc, rays);
 }
 
 // Shading bin of a closest-hit record (bin = BSDF model of the surface; 0 = escaped / BSDF-less, 1 = area light).
@@ -112,14 +126,15 @@ __device__ __forceinline__ void FlushCounters(bool stats, const TraversalCounter
 // ---------------------------------------------------------------------------------------------
 // k_primary: camera-ray generation (renderer.cpp:62-75) fused with the first closest hit.
 // ---------------------------------------------------------------------------------------------
-template <bool STATS, bool OPACITY, bool TOP>
+template <bool STATS, bool OPACITY, int LAYOUT>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(const __grid_constant__ DeviceScene scene,
                                                       const __grid_constant__ BatchParams bp, PathQueue q,
                                                       float *radiance, uint32_t capacity, Counters *counters, int max_top,
-                                                      int refill, int min_inner) {
-    extern __shared__ float4 top[];
+                                                      int refill, int phase_lanes) {
+    extern __shared__ uint4 top[];
     __shared__ uint64_t bar;
-    const int num_top = TOP ? StageTopNodes(scene, top, &bar, max_top) : 0;
+    const uint32_t num_top = LAYOUT == kLayoutWideTop ? min(scene.num_wide_nodes, static_cast<uint32_t>(max_top)) : 0u;
+    if (LAYOUT == kLayoutWideTop) StageTop(scene.wide_nodes, num_top * static_cast<uint32_t>(sizeof(WideNode)), top, &bar);
     const uint32_t nslots = bp.pixel_count * bp.sample_count;
     TraversalCounters tc[2];
     uint32_t rays[2] = {0, 0};
@@ -162,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(con
         }
         q.hit[idx] = hit;
     };
-    TraversePersistent<false, STATS, OPACITY, TOP>(scene, top, num_top, nslots, &counters->work_primary, refill, min_inner, bp.key, fetch, finish, tc, rays);
+    TraverseLayout<false, STATS, OPACITY, LAYOUT>(scene, top, num_top, nslots, &counters->work_primary, refill, phase_lanes, bp.key, fetch, finish, tc, rays);
     FlushCounters(STATS, tc[0], rays[0], kClassPrimary, counters);
 }
 
@@ -175,17 +190,18 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(con
 // Ray index space: [0, n_extend) closest-hit rays of queue `which`, then [n_extend, n_extend + n_shadow) NEE rays.
 // ---------------------------------------------------------------------------------------------
 
-template <bool STATS, bool OPACITY, bool TOP>
+template <bool STATS, bool OPACITY, int LAYOUT>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const __grid_constant__ DeviceScene scene,
                                                     const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue q, int which,
                                                     ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters,
-                                                    int max_top, int refill, int min_inner) {
-    extern __shared__ float4 top[];
+                                                    int max_top, int refill, int phase_lanes) {
+    extern __shared__ uint4 top[];
     __shared__ uint64_t bar;
     const uint32_t n_extend = which >= 0 ? counters->queue[which] : 0u, n_shadow = counters->shadow;
     const uint32_t n = n_extend + n_shadow;
     if (blockIdx.x * blockDim.x >= n) return;
-    const int num_top = TOP ? StageTopNodes(scene, top, &bar, max_top) : 0;
+    const uint32_t num_top = LAYOUT == kLayoutWideTop ? min(scene.num_wide_nodes, static_cast<uint32_t>(max_top)) : 0u;
+    if (LAYOUT == kLayoutWideTop) StageTop(scene.wide_nodes, num_top * static_cast<uint32_t>(sizeof(WideNode)), top, &bar);
     TraversalCounters tc[2];
     uint32_t rays[2] = {0, 0};
     auto fetch = [&](uint32_t i, Ray *ray, uint3 *ctr, bool *any) {
@@ -218,9 +234,58 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const
             atomicAdd(radiance + 2 * capacity + slot, sq.cb[j]);
         }
     };
-    TraversePersistent<true, STATS, OPACITY, TOP>(scene, top, num_top, n, &counters->work_trace, refill, min_inner, bp.key, fetch, finish, tc, rays);
+    TraverseLayout<true, STATS, OPACITY, LAYOUT>(scene, top, num_top, n, &counters->work_trace, refill, phase_lanes, bp.key, fetch, finish, tc, rays);
     FlushCounters(STATS, tc[0], rays[0], kClassExtend, counters);
     FlushCounters(STATS, tc[1], rays[1], kClassShadow, counters);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_debug_trace: caller-supplied rays through the SAME traversal loops as k_primary / k_trace (b200pt_debug_trace, the test
+// hook behind the pointwise parity tests of the Woop / box / analytic tests against the reference's TLAS::Intersect).
+// `single`: the per-lane loop of the tail kernel instead of the persistent one.
+// ---------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_debug_trace(const __grid_constant__ DeviceScene scene, const b200pt_debug_ray *rays_in,
+                                                                                uint32_t n, bool any_hit, bool single, b200pt_debug_hit *out,
+                                                                                uint32_t *work_counter, int refill, int phase_lanes) {
+    auto report = [&](uint32_t i, const HitRec &hit, bool found, bool any) {
+        b200pt_debug_hit h;
+        h.t = hit.t, h.u = hit.u, h.v = hit.v, h.prim = hit.prim;
+        if (any) {
+            h.prim = found ? 0u : kPrimMiss;
+        } else if (hit.prim != kPrimMiss && !(hit.prim & kPrimAnalyticBit)) { // leaf order -> index in the scene description
+            const uint32_t original = __float_as_uint(__ldg(&scene.tri_verts[hit.prim & kPrimIndexMask].v1.w));
+            h.prim = original | (hit.prim & kPrimInsideBit);
+        }
+        out[i] = h;
+    };
+    auto load = [&](uint32_t i, Ray *ray) {
+        const b200pt_debug_ray r = rays_in[i];
+        ray->o = mk3(r.o[0], r.o[1], r.o[2]), ray->d = mk3(r.d[0], r.d[1], r.d[2]);
+        ray->tmin = r.tmin, ray->tmax = r.tmax;
+    };
+    if (single) {
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            Ray ray;
+            load(i, &ray);
+            HitRec hit;
+            hit.t = ray.tmax, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
+            const Rng rng(0, 0, 0, make_uint2(0u, 0u), kRngDomainClosest);
+            const bool found = LAYOUT == kLayoutBinary ? TraverseSingle(scene, ray, any_hit, false, rng, &hit, false, nullptr)
+                                                       : TraverseSingleWide(scene, ray, any_hit, false, rng, &hit, false, nullptr);
+            report(i, hit, found, any_hit);
+        }
+        return;
+    }
+    extern __shared__ uint4 top[];
+    TraversalCounters tc[2];
+    uint32_t traced[2] = {0, 0};
+    auto fetch = [&](uint32_t i, Ray *ray, uint3 *, bool *any) {
+        load(i, ray);
+        *any = any_hit;
+        return true;
+    };
+    TraverseLayout<true, false, false, LAYOUT>(scene, top, 0u, n, work_counter, refill, phase_lanes, make_uint2(0u, 0u), fetch, report, tc, traced);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -395,35 +460,39 @@ __global__ void k_assemble(uint32_t width, uint32_t height, uint32_t tile_world,
     }
 }
 
-size_t TopSmemBytes(const LaunchConfig &lc) { return static_cast<size_t>(std::max(lc.top_nodes, 1)) * sizeof(BvhNode); }
+size_t TopSmemBytes(const LaunchConfig &lc) { return static_cast<size_t>(std::max(lc.top_nodes, 1)) * sizeof(WideNode); }
 
-// Dynamic shared memory above 48 KB needs an opt-in per kernel function (only reached with B200PT_TOP_NODES > 768).
+// Dynamic shared memory above 48 KB needs an opt-in per kernel function (only reached with B200PT_TOP_NODES > 614).
 template <typename K>
 void EnableSmem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024)
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTopNodesMax * sizeof(BvhNode)));
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWideTopNodesMax * sizeof(WideNode)));
 }
 
 } // namespace
 
-// Picks the <STATS, OPACITY, TOP> instantiation of a traversal kernel and launches it on the persistent grid.
-// lc.top_nodes == 0 selects the variants without the shared-memory copy of the top of the tree.
+// Picks the <STATS, OPACITY, LAYOUT> instantiation of a traversal kernel and launches it on the persistent grid.
+// The layout follows the tree the scene was created with; lc.top_nodes > 0 selects the wide variant that stages the top
+// of the tree in shared memory.
 #define B200PT_LAUNCH_TRAVERSAL(kernel, ...)                                                                          \
     do {                                                                                                              \
-        const bool opacity = scene.integrator.has_opacity != 0, top = lc.top_nodes > 0;                               \
+        const bool opacity = scene.integrator.has_opacity != 0, wide = scene.num_wide_nodes > 0;                     \
+        const bool top = wide && lc.top_nodes > 0;                                                                    \
         const size_t smem = top ? TopSmemBytes(lc) : 0;                                                               \
+        const int phase_lanes = wide ? lc.tri_min : lc.min_inner;                                                     \
         auto go = [&](auto k) {                                                                                       \
             EnableSmem(k, smem);                                                                                      \
-            k<<<lc.blocks, kThreads, smem, lc.stream>>>(__VA_ARGS__, lc.top_nodes, lc.refill, lc.min_inner);          \
+            k<<<lc.blocks, kThreads, smem, lc.stream>>>(__VA_ARGS__, lc.top_nodes, lc.refill, phase_lanes);           \
         };                                                                                                            \
-        auto pick_top = [&](auto with_top, auto without_top) {                                                        \
-            if (top) go(with_top);                                                                                    \
-            else go(without_top);                                                                                     \
+        auto pick_layout = [&](auto binary, auto wide_plain, auto wide_top) {                                         \
+            if (!wide) go(binary);                                                                                    \
+            else if (top) go(wide_top);                                                                               \
+            else go(wide_plain);                                                                                      \
         };                                                                                                            \
-        if (lc.stats && opacity) pick_top(kernel<true, true, true>, kernel<true, true, false>);                       \
-        else if (lc.stats) pick_top(kernel<true, false, true>, kernel<true, false, false>);                           \
-        else if (opacity) pick_top(kernel<false, true, true>, kernel<false, true, false>);                            \
-        else pick_top(kernel<false, false, true>, kernel<false, false, false>);                                       \
+        if (lc.stats && opacity) pick_layout(kernel<true, true, 0>, kernel<true, true, 1>, kernel<true, true, 2>);    \
+        else if (lc.stats) pick_layout(kernel<true, false, 0>, kernel<true, false, 1>, kernel<true, false, 2>);       \
+        else if (opacity) pick_layout(kernel<false, true, 0>, kernel<false, true, 1>, kernel<false, true, 2>);        \
+        else pick_layout(kernel<false, false, 0>, kernel<false, false, 1>, kernel<false, false, 2>);                  \
     } while (0)
 
 int LaunchPrimary(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, PathQueue q, ShadeBins bins,
@@ -471,6 +540,14 @@ int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
         ++launches;
     }
     return launches;
+}
+
+void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b200pt_debug_ray *rays, uint32_t n, bool any_hit, bool single,
+                      b200pt_debug_hit *out, uint32_t *work_counter) {
+    if (scene.num_wide_nodes > 0)
+        k_debug_trace<kLayoutWide><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, out, work_counter, lc.refill, lc.tri_min);
+    else
+        k_debug_trace<kLayoutBinary><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, out, work_counter, lc.refill, lc.min_inner);
 }
 
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "b200pt.h"
 #include "device_scene.h"
 #include "traverse.cuh"
 
@@ -123,9 +124,10 @@ struct LaunchConfig {
     int threads;
     cudaStream_t stream;
     bool stats;
-    int top_nodes;            // BVH nodes staged in shared memory per CTA (64 B each)
+    int top_nodes;            // wide-BVH nodes staged in shared memory per CTA (80 B each), 0 = none
     int refill;               // idle lanes per warp that trigger a ray refill in the traversal loops
-    int min_inner;            // lanes still walking inner nodes below which a warp switches to its pending leaves
+    int min_inner;            // binary layout: lanes still walking inner nodes below which a warp switches to its pending leaves
+    int tri_min;              // wide layout: lanes holding triangles below which they are postponed in favour of inner nodes
     int shade_only;           // the one BSDF type every scattering surface of the scene has, or -1 (generic shading kernel)
 };
 
@@ -149,6 +151,9 @@ void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const Bat
 // finishes its paths if it holds at most `threshold` entries, else returns at once.  `depth` = the bounce shade would run.
 void LaunchTail(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
                 float *radiance, uint32_t capacity, Counters *counters, uint32_t threshold);
+// Test hook (b200pt_debug_trace): rays[0..n) through the persistent traversal loop (or the per-lane one) of the scene's tree.
+void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b200pt_debug_ray *rays, uint32_t n, bool any_hit, bool single,
+                      b200pt_debug_hit *out, uint32_t *work_counter);
 constexpr uint32_t kMaxTailDepth = 4096; // = kMaxRounds of the host loop
 void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow);
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum);

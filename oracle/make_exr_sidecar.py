@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""TEST INFRASTRUCTURE ONLY — writes the RGBA float32 sidecar that oracle/shims/tinyexr.h reads.
+"""TEST INFRASTRUCTURE ONLY — writes the RGBA float32 sidecar that monte-carlo-path-tracing_b200/host/shims/tinyexr.h reads.
 
 Usage: make_exr_sidecar.py <in.exr> <out_dir>
 Decodes with OpenCV's OpenEXR reader (BGR float32) and stores int32 w, int32 h, RGBA float32 (A=1),

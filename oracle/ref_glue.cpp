@@ -21,6 +21,7 @@
 #include "csrt/renderer/bsdfs/kulla_conty.hpp"
 #include "csrt/renderer/renderer.hpp"
 #include "csrt/rtcore/accel/bvh_builder.hpp"
+#include "csrt/rtcore/scene.hpp"
 
 #include "b200pt.h"
 #include "csrc/host_util.hpp"
@@ -237,6 +238,67 @@ void ref_destroy_cuda(void *handle) {
     delete r;
 }
 #endif
+
+// ---- pointwise traversal: csrt::Scene (scene.cpp:118-141) + TLAS::Intersect / IntersectAny (tlas.cpp:13-76) on caller-supplied
+// rays, without BSDFs (no opacity masks).  rays: 8 floats each (origin, direction, t_min, t_max). ----
+namespace {
+struct RefScene {
+    std::unique_ptr<csrt::Scene> scene;
+    std::vector<uint32_t> map_instance_bsdf;
+};
+} // namespace
+
+struct ref_hit {
+    float t;             // ray.t_max after the call
+    uint32_t valid, inside, id_instance, id_primitive;
+    float position[3], normal[3], texcoord[2];
+};
+
+void *ref_scene_create(const b200pt_scene_desc *desc) {
+    try {
+        csrt::RendererConfig cfg = b200pt_glue::InflateScene(*desc);
+        StderrSilencer quiet;
+        RefScene *s = new RefScene();
+        s->scene.reset(new csrt::Scene(csrt::BackendType::kCpu, cfg.instances));
+        s->map_instance_bsdf.assign(cfg.instances.size() + 1, csrt::kInvalidId);
+        return s;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return nullptr;
+    }
+}
+
+void ref_scene_destroy(void *handle) { delete static_cast<RefScene *>(handle); }
+
+int ref_trace(void *handle, uint64_t n, const float *rays, int any_hit, ref_hit *out) {
+    try {
+        RefScene *s = static_cast<RefScene *>(handle);
+        const csrt::TLAS *tlas = s->scene->GetTlas();
+        for (uint64_t i = 0; i < n; ++i) {
+            const float *r = rays + 8 * i;
+            csrt::Ray ray(csrt::Vec3(r[0], r[1], r[2]), csrt::Vec3(r[3], r[4], r[5])); // ray.cpp:18-47: dir_rcp, Woop k / shear
+            ray.t_min = r[6], ray.t_max = r[7];
+            uint32_t seed = 0;
+            ref_hit h{};
+            if (any_hit) {
+                h.valid = tlas->IntersectAny(nullptr, s->map_instance_bsdf.data(), &seed, &ray) ? 1u : 0u;
+                h.t = ray.t_max;
+            } else {
+                const csrt::Hit hit = tlas->Intersect(nullptr, s->map_instance_bsdf.data(), &seed, &ray);
+                h.t = ray.t_max;
+                h.valid = hit.valid, h.inside = hit.inside, h.id_instance = hit.id_instance, h.id_primitive = hit.id_primitve;
+                h.position[0] = hit.position.x, h.position[1] = hit.position.y, h.position[2] = hit.position.z;
+                h.normal[0] = hit.normal.x, h.normal[1] = hit.normal.y, h.normal[2] = hit.normal.z;
+                h.texcoord[0] = hit.texcoord.u, h.texcoord[1] = hit.texcoord.v;
+            }
+            out[i] = h;
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
 
 // ---- known-answer helpers: reference leaf functions, called directly ----
 

@@ -74,6 +74,50 @@ class RefLib:
             self.lib.b200pt_scene_free(scene)
 
 
+class RefHit(ctypes.Structure):
+    """struct ref_hit of oracle/ref_glue.cpp."""
+    _fields_ = [("t", ctypes.c_float), ("valid", ctypes.c_uint32), ("inside", ctypes.c_uint32), ("id_instance", ctypes.c_uint32),
+                ("id_primitive", ctypes.c_uint32), ("position", ctypes.c_float * 3), ("normal", ctypes.c_float * 3),
+                ("texcoord", ctypes.c_float * 2)]
+
+
+class RefTracer:
+    """csrt::Scene + TLAS::Intersect / IntersectAny (tlas.cpp:13-76) of the reference build on caller-supplied rays."""
+
+    def __init__(self, ref, pack_path=None, desc=None):
+        self.ref = ref
+        L = ref.lib
+        L.ref_scene_create.argtypes = [ctypes.c_void_p]
+        L.ref_scene_create.restype = ctypes.c_void_p
+        L.ref_scene_destroy.argtypes = [ctypes.c_void_p]
+        L.ref_scene_destroy.restype = None
+        L.ref_trace.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        self.scene = ctypes.c_void_p()
+        if pack_path is not None:
+            if L.b200pt_scene_load(pack_path.encode(), ctypes.byref(self.scene)) != 0:
+                raise RuntimeError(f"cannot load {pack_path}")
+            desc = L.b200pt_scene_get_desc(self.scene)
+        self.handle = L.ref_scene_create(desc)
+        if not self.handle:
+            raise RuntimeError(ref.error())
+
+    def trace(self, rays, any_hit=False):
+        """rays: float32 [n, 8] (origin, direction, t_min, t_max) -> numpy record array of RefHit."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        out = (RefHit * len(rays))()
+        if self.ref.lib.ref_trace(self.handle, len(rays), rays.ctypes.data, 1 if any_hit else 0, out) != 0:
+            raise RuntimeError(self.ref.error())
+        return np.ctypeslib.as_array(out).copy() if len(rays) else np.zeros(0, dtype=RefHit)
+
+    def close(self):
+        if self.handle:
+            self.ref.lib.ref_scene_destroy(self.handle)
+            self.handle = None
+        if self.scene:
+            self.ref.lib.b200pt_scene_free(self.scene)
+            self.scene = ctypes.c_void_p()
+
+
 class OracleLib:
     """The plain-C restatement (oracle/pt_oracle.c -> oracle/_ref/liboracle.so)."""
 

@@ -410,4 +410,20 @@ def synthetic_scenes():
     b.cylinder(b.diffuse(b.constant(0.6, 0.3, 0.6), opacity=b.constant(0.5)), (0.3, 0.0, -0.8), (0.3, 1.8, -0.8), 0.35)
     b.point((2.0, 3.0, 3.0), (25, 25, 25))
     scenes["opacity_masks"] = b
+
+    # Depth limits of the path loop `depth < depth_rr || (depth < depth_max && rand < pdf_rr)` (path.cpp:57-60):
+    # a max_depth below rr_depth still walks rr_depth - 1 vertices; Russian roulette from the first vertex on.
+    b = SceneBuilder(depth_max=2, depth_rr=5)
+    stage(b)
+    b.sphere(b.diffuse(b.constant(0.75, 0.7, 0.3)), (-0.8, 0.7, 0.4), 0.7)
+    b.cube(b.conductor(0.15, 0.15, (0.2, 0.92, 1.1), (3.9, 2.45, 2.14)), translate(1.1, 0.5, 0.3) @ rotate_y(25) @ scale(0.5, 0.5, 0.5))
+    b.constant_env((0.3, 0.35, 0.45))
+    scenes["depth_max_below_rr"] = b
+
+    b = SceneBuilder(depth_max=3, depth_rr=1, pdf_rr=0.4)
+    stage(b)
+    b.sphere(b.diffuse(b.constant(0.3, 0.7, 0.75)), (0.0, 0.8, 0.2), 0.8)
+    b.directional((0.3, -1.0, -0.6), (1.5, 1.4, 1.3))
+    b.constant_env((0.2, 0.2, 0.25))
+    scenes["early_rr"] = b
     return scenes

@@ -139,7 +139,10 @@ def test_batches_in_flight_do_not_change_the_frame(pkg, scene, monkeypatch):
 
 
 @pytest.mark.parametrize("scene,w,h,spp", [("dragon", 256, 256, 32), ("cornell-box", 128, 128, 32), ("volumetric-caustic", 96, 96, 32),
-                                           ("matpreview", 128, 128, 16), ("synthetic_opacity_masks", 96, 96, 32)])
+                                           ("matpreview", 128, 128, 16), ("synthetic_opacity_masks", 96, 96, 32),
+                                           # path.cpp:57-60 with max_depth < rr_depth / roulette from the first vertex: the host loop
+                                           # must run max(depth_rr, depth_max) rounds whatever the take-over point
+                                           ("synthetic_depth_max_below_rr", 96, 96, 32), ("synthetic_early_rr", 96, 96, 32)])
 def test_tail_kernel_is_bit_exact(pkg, scene, w, h, spp, monkeypatch):
     """k_tail (one path per lane to the end, once few paths survive) computes exactly the samples the per-bounce wavefront
     launches would have: same ShadeVertex code, same counter-based random numbers, same order of additions per sample."""
@@ -153,7 +156,7 @@ def test_tail_kernel_is_bit_exact(pkg, scene, w, h, spp, monkeypatch):
         st = r.stats()
         assert (st["tail"]["launches"] > 0) == (paths != "0")
         r.close()
-    if scene == "synthetic_opacity_masks":
+    if scene in ("synthetic_opacity_masks", "synthetic_early_rr"):
         # two emitters: the two NEE contributions of a vertex are added by atomics in either order in the wavefront path
         assert np.allclose(frames["0"], frames["4096"], rtol=0, atol=1e-6) and np.allclose(frames["0"], frames["16777216"], rtol=0, atol=1e-6)
     else:

@@ -1,0 +1,196 @@
+"""Pointwise parity of the traversal kernels (-m gpu): caller-supplied rays through b200pt_debug_trace, i.e. through the
+same persistent loops k_primary / k_trace run, against the UNMODIFIED reference's csrt::Scene + TLAS::Intersect /
+IntersectAny (tlas.cpp:13-76, blas.cpp:18-77, triangle.cpp:23-87 Woop variant) called through oracle/ref_glue.cpp.
+
+Bar: hit / miss identical, distance t BIT-EXACT (same Woop arithmetic on the same world-space vertices), hit side
+identical, hit instance identical — for random rays and for rays aimed exactly at shared vertices, shared edges and
+degenerate triangles.  The primitive may differ only where two triangles report the same t (a ray through a shared
+edge: the winner depends on the order of the tests, which differs between trees).  The compressed 8-wide tree (default),
+the binary tree (B200PT_CREATE_BVH2) and both loop shapes (persistent / one ray per lane) must all agree."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, pack
+
+import refcheck
+import scene_builder as sb
+
+pytestmark = pytest.mark.gpu
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+
+def make_rays(origins, dirs, tmin=1e-4, tmax=FLT_MAX):
+    origins, dirs = np.asarray(origins, dtype=np.float32), np.asarray(dirs, dtype=np.float32)
+    dirs = dirs / np.linalg.norm(dirs.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    rays = np.zeros((len(origins), 8), dtype=np.float32)
+    rays[:, 0:3], rays[:, 3:6], rays[:, 6], rays[:, 7] = origins, dirs, tmin, tmax
+    return rays
+
+
+def instance_table(desc_ptr):
+    """Per instance of a b200pt_scene_desc: (first triangle in the scene's triangle enumeration, triangle count, analytic rank)."""
+    desc = ctypes.cast(desc_ptr, ctypes.POINTER(sb.SceneDesc)).contents
+    inst = ctypes.cast(desc.instances, ctypes.POINTER(sb.Instance))
+    rows, tri, analytic = [], 0, 0
+    for i in range(desc.num_instances):
+        kind = inst[i].type
+        count = {sb.INST_CUBE: 12, sb.INST_RECTANGLE: 2, sb.INST_MESHES: int(inst[i].num_triangles)}.get(kind, 0)
+        rows.append((tri, count, analytic if count == 0 else -1))
+        tri += count
+        analytic += 1 if count == 0 else 0
+    return rows
+
+
+def ours_to_instance(prim, table):
+    """prim of b200pt_debug_hit -> (instance, local primitive index)."""
+    firsts = np.array([r[0] for r in table] + [1 << 62])
+    counts = np.array([r[1] for r in table])
+    analytic_inst = {r[2]: i for i, r in enumerate(table) if r[2] >= 0}
+    inst = np.full(len(prim), -1, dtype=np.int64)
+    local = np.full(len(prim), -1, dtype=np.int64)
+    for k, p in enumerate(prim):
+        if p == 0xFFFFFFFF:
+            continue
+        if p & 0x80000000:
+            inst[k], local[k] = analytic_inst[int(p & 0x0FFFFFFF)], 0
+        else:
+            t = int(p & 0x0FFFFFFF)
+            i = int(np.searchsorted(firsts, t, side="right") - 1)
+            while counts[i] == 0:  # analytic instances own no triangles: same `first` as the next mesh
+                i += 1
+            inst[k], local[k] = i, t - firsts[i]
+    return inst, local
+
+
+def check_against_reference(r, tracer, table, rays, name, allow_prim_ties):
+    ref = tracer.trace(rays)
+    ref_any = tracer.trace(rays, any_hit=True)
+    for per_lane in (False, True):
+        t, prim, uv = r.debug_trace(rays, per_lane_loop=per_lane)
+        hit = prim != 0xFFFFFFFF
+        assert np.array_equal(hit, ref["valid"] != 0), f"{name}: hit/miss differs on {np.flatnonzero(hit != (ref['valid'] != 0))[:5]}"
+        assert np.array_equal(t.view(np.uint32), ref["t"].view(np.uint32)), f"{name}: t differs from TLAS::Intersect (not bit-exact)"
+        inside = (prim & 0x40000000) != 0
+        tri = hit & ((prim & 0x80000000) == 0)
+        inst, local = ours_to_instance(prim, table)
+        same_prim = (inst == ref["id_instance"].astype(np.int64)) & (local == ref["id_primitive"].astype(np.int64))
+        same_prim |= ~hit
+        if not allow_prim_ties:
+            assert same_prim.mean() > 0.999, f"{name}: primitive differs on {(~same_prim).sum()} of {len(rays)} rays"
+        ok = same_prim | ~tri  # side / instance are compared where the same primitive was reported
+        assert np.array_equal(inside[tri & same_prim], (ref["inside"] != 0)[tri & same_prim])
+        assert ok.all() or allow_prim_ties or same_prim.mean() > 0.999
+        occluded = r.debug_trace(rays, any_hit=True, per_lane_loop=per_lane)[1] == 0
+        assert np.array_equal(occluded, ref_any["valid"] != 0), f"{name}: IntersectAny differs"
+
+
+def random_rays(lo, hi, n, rng):
+    span = hi - lo
+    origins = lo - 0.3 * span + rng.rand(n, 3) * 1.6 * span
+    targets = lo + rng.rand(n, 3) * span
+    return make_rays(origins, targets - origins)
+
+
+@pytest.mark.parametrize("scene", ["cornell-box", "dragon", "matpreview", "volumetric-caustic", "mercury", "synthetic_bump_bitmap_mesh_disk",
+                                   "synthetic_dielectrics_conductor_cylinder"])
+def test_random_rays_match_reference_tlas(pkg, scene):
+    path = os.path.join(GOLDEN, scene + ".b200scene") if scene.startswith("synthetic_") else pack(scene)
+    sc = pkg.Scene(path)
+    tracer = refcheck.RefTracer(refcheck.ref_lib("woop"), path)
+    table = instance_table(sc.desc)
+    rng = np.random.RandomState(3)
+    # the extent of the geometry: probe with axis rays is overkill — use a generous cube around the camera target instead
+    probe = make_rays(rng.randn(4096, 3) * 1e3, rng.randn(4096, 3))
+    n = 200000 if scene == "dragon" else 60000
+    for flags in (0, pkg.CREATE_BVH2):
+        r = pkg.Renderer(sc, device=0, flags=flags)
+        assert r.stats()["bvh_width"] == (2 if flags else 8)
+        # bounding box of what random probes from far away hit
+        far = make_rays(rng.randn(20000, 3) * 50.0, rng.randn(20000, 3))
+        far[:, 3:6] = -far[:, 0:3] / np.linalg.norm(far[:, 0:3], axis=1, keepdims=True)  # towards the origin
+        t, prim, _ = r.debug_trace(far)
+        pts = far[:, 0:3] + t[:, None] * far[:, 3:6]
+        pts = pts[prim != 0xFFFFFFFF]
+        lo, hi = (pts.min(axis=0), pts.max(axis=0)) if len(pts) > 16 else (np.full(3, -5.0), np.full(3, 5.0))
+        rays = np.concatenate([random_rays(lo, hi, n, rng), probe, far[:2000]])
+        rays[::5, 7] = np.float32(0.5) * np.linalg.norm(hi - lo)  # bounded segments (shadow-ray style) on a fifth of the rays
+        check_against_reference(r, tracer, table, rays, f"{scene}/bvh{2 if flags else 8}", allow_prim_ties=False)
+        r.close()
+    tracer.close()
+
+
+def lattice_scene():
+    """A 12 x 12 grid of quads (shared vertices and edges at exactly representable coordinates), a second sheet behind it,
+    plus zero-area and needle triangles."""
+    b = sb.SceneBuilder()
+    n = 12
+    xs = np.arange(n + 1, dtype=np.float32) * 0.25 - 1.5
+    pos = np.array([(x, y, 0.0) for y in xs for x in xs], dtype=np.float32)
+    idx = []
+    for j in range(n):
+        for i in range(n):
+            a = j * (n + 1) + i
+            idx += [(a, a + 1, a + n + 2), (a, a + n + 2, a + n + 1)]
+    white = b.diffuse(b.constant(0.7))
+    b.mesh(white, pos, idx)
+    b.mesh(white, pos + np.float32([0.125, 0.0625, -0.75]), idx)
+    degenerate = np.array([(0, 0, 0.5), (0, 0, 0.5), (1, 1, 0.5),          # two coincident vertices
+                           (-1, -1, 0.5), (0, 0, 0.5), (1, 1, 0.5),        # collinear
+                           (-1, 0.5, 0.5), (1, 0.5, 0.5), (0, 0.5 + 1e-6, 0.5)], dtype=np.float32)  # needle
+    b.mesh(white, degenerate, [(0, 1, 2), (3, 4, 5), (6, 7, 8)])
+    b.directional((0, 0, -1), (1, 1, 1))
+    return b, xs
+
+
+def test_rays_through_shared_vertices_edges_and_degenerate_triangles(pkg, tmp_path):
+    """Woop's watertight test with its double-precision edge fallback (triangle.cpp:50-63): rays aimed EXACTLY at lattice
+    vertices and edge midpoints must be hit (no leaks between neighbours) with the reference's t, from both trees."""
+    b, xs = lattice_scene()
+    desc = b.desc()
+    path = str(tmp_path / "lattice.b200scene")
+    assert pkg.lib().b200pt_scene_save(ctypes.byref(desc), path.encode()) == 0
+    sc = pkg.Scene(path)
+    tracer = refcheck.RefTracer(refcheck.ref_lib("woop"), path)
+    table = instance_table(sc.desc)
+    rng = np.random.RandomState(11)
+    mids = (xs[:-1] + xs[1:]) * np.float32(0.5)
+    targets = [(x, y, 0.0) for x in xs for y in xs] + [(x, y, 0.0) for x in mids for y in xs] + [(x, y, 0.0) for x in xs for y in mids] \
+        + [(x, y, 0.0) for x in mids for y in mids]  # vertices, both edge families, diagonals' midpoints
+    targets = np.array(targets, dtype=np.float32)
+    origins, aims = [], []
+    for eye in ([0, 0, 4], [0.3, -0.2, 3], [2.5, 1.0, 2.0], [0, 0, -4], [1e-3, 7.0, 0.25]):
+        origins.append(np.tile(np.float32(eye), (len(targets), 1)))
+        aims.append(targets)
+    # axis-parallel rays straight down the lattice lines (zero direction components: ray.cpp:21-22)
+    origins.append(targets + np.float32([0, 0, 5]))
+    aims.append(targets)
+    origins, aims = np.concatenate(origins), np.concatenate(aims)
+    rays = np.concatenate([make_rays(origins, aims - origins), random_rays(np.float32([-1.6, -1.6, -0.8]), np.float32([1.6, 1.6, 0.6]), 20000, rng)])
+    for flags in (0, pkg.CREATE_BVH2):
+        r = pkg.Renderer(sc, device=0, flags=flags)
+        check_against_reference(r, tracer, table, rays, f"lattice/bvh{2 if flags else 8}", allow_prim_ties=True)
+        t, prim, _ = r.debug_trace(rays[: 5 * len(targets)])
+        inside_grid = (np.abs(aims[: 5 * len(targets), 0]) <= 1.5) & (np.abs(aims[: 5 * len(targets), 1]) <= 1.5)
+        assert (prim[inside_grid] != 0xFFFFFFFF).all(), "a ray leaked through a shared vertex / edge"
+        r.close()
+    tracer.close()
+
+
+@pytest.mark.parametrize("scene,w,h,spp", [("dragon", 192, 192, 16), ("cornell-box", 96, 96, 32), ("matpreview", 96, 96, 16),
+                                           ("volumetric-caustic", 64, 64, 32), ("synthetic_opacity_masks", 64, 64, 32)])
+def test_wide_and_binary_trees_render_the_same_frame(pkg, scene, w, h, spp):
+    """Same hits => same paths: the frames of the two layouts agree except where a tie on a shared edge picked the neighbour."""
+    path = os.path.join(GOLDEN, scene + ".b200scene") if scene.startswith("synthetic_") else pack(scene)
+    sc = pkg.Scene(path)
+    frames = []
+    for flags in (0, pkg.CREATE_BVH2):
+        r = pkg.Renderer(sc, device=0, flags=flags, max_paths_in_flight=1 << 22)
+        frames.append(r.Draw(width=w, height=h, spp=spp, seed=5))
+        r.close()
+    a, b = frames
+    differing = np.any(a != b, axis=2).mean()
+    assert differing < 0.02, f"{scene}: {differing:.4f} of the pixels differ between the wide and the binary tree"
+    assert abs(a.mean() / b.mean() - 1.0) < 2e-3
