@@ -200,10 +200,12 @@ typedef struct b200pt_create_opts {
  * the host binned-SAH builder: the tree is ready in milliseconds instead of seconds, traversal is slower.
  * Replaces csrt::BvhBuilder::Build (src/rtcore/accel/bvh_builder.cpp:50-206), also an LBVH. */
 #define B200PT_CREATE_GPU_LBVH 1u
-/* Keep the host SAH tree in the binary layout (two child boxes per 64-byte node) instead of collapsing it into the default
- * compressed 8-wide layout (eight quantised child boxes per 80-byte node).  Both find the same hits; the binary walk is
- * the slower one and stays as the cross-check of the wide one. */
-#define B200PT_CREATE_BVH2 2u
+/* Collapse the host SAH tree into the compressed 8-wide layout (eight quantised child boxes per 80-byte node, Ylitie et al.
+ * 2017) instead of the default binary layout (two exact child boxes per 64-byte node).  Both find the same hits.  A ray
+ * fetches 2.6x fewer nodes in the wide tree, but on B200 traversal is bound by instruction issue, not by fetches, and the
+ * eight-box test costs more instructions than the 2.6 binary steps it replaces: measured 1.4x slower, so
+ * the wide tree is the option and the cross-check, not the default. */
+#define B200PT_CREATE_BVH8 2u
 
 /* What to render.  width/height/spp = 0 take the value from the scene's camera
  * (the reference CLI overrides them after parsing: apps/main.cpp:46-52). */
@@ -241,7 +243,7 @@ typedef struct b200pt_stats {
     uint64_t samples;            /* width*height*spp rendered by this rank */
     uint64_t kernel_launches;    /* kernels launched by the last render */
     uint64_t num_bvh_nodes, num_triangles, num_prims;
-    uint32_t bvh_width;          /* 8 = compressed wide layout (80-byte nodes), 2 = binary layout (64-byte nodes) */
+    uint32_t bvh_width;          /* 2 = binary layout (64-byte nodes, default), 8 = compressed wide layout (80-byte nodes) */
     uint32_t bvh_depth;          /* levels of the wide tree (0 for the binary layout) */
     uint64_t local_tiles, active_tiles; /* 8x8 tiles owned by this rank / those that passed the visibility pre-pass */
     b200pt_kernel_stats primary; /* k_primary: ray-gen + closest hit of camera rays */
@@ -310,8 +312,37 @@ typedef struct b200pt_debug_hit {
 } b200pt_debug_hit;
 #define B200PT_DEBUG_ANY_HIT 1u      /* TLAS::IntersectAny (tlas.cpp:44-76): prim = 0 if occluded, 0xFFFFFFFF if not */
 #define B200PT_DEBUG_PER_LANE_LOOP 2u /* the tail kernel's one-ray-per-lane loop instead of the persistent loop */
+#define B200PT_DEBUG_RAW_PRIM 4u      /* prim as the kernels store it (leaf-order triangle index): input of B200PT_EVAL_SURFACE */
 /* rays_host / hits_host: n elements each, HOST memory.  Runs the product's traversal kernels on the scene's tree. */
 int b200pt_debug_trace(b200pt_handle h, const b200pt_debug_ray *rays_host, uint64_t n, uint32_t flags, b200pt_debug_hit *hits_host);
+
+/* Leaf functions of the shading stage at caller-supplied inputs: `in_host` = n x B200PT_EVAL_IN floats, `out_host` = n x
+ * B200PT_EVAL_OUT floats, `id` = index of the BSDF / emitter / medium / texture.  Sampling routines draw their random
+ * numbers from the reference's LCG (math.hpp:57-63) started at the seed whose bit pattern is in[18]; out[15] returns the
+ * state after the call (so the NUMBER of draws is checked too).
+ *   what                    reference function                                    in                                   out
+ *   BSDF_EVALUATE           Bsdf::Evaluate      (bsdf.cpp:213-236)                wi[0:3] wo[3:6] n[6:9] t[9:12]       valid pdf att[2:5]
+ *                                                                                 b[12:15] uv[15:17] inside[17]
+ *   BSDF_SAMPLE             Bsdf::Sample        (bsdf.cpp:188-211)                same, wi ignored, seed[18]           valid pdf att[2:5] wi[5:8]
+ *   EMITTER_SAMPLE          Emitter::Sample / Evaluate(rec) / Pdf(-wi)            origin[0:3] xi_0[3] xi_1[4]          valid harsh distance wi[3:6]
+ *                           (emitter.cpp:177-261)                                                                      Le[6:9] pdf[9]
+ *   EMITTER_DIR             Emitter::Evaluate(dir) / Pdf(dir)                     dir[0:3]                             Le[0:3] pdf[3]
+ *   MEDIUM_SAMPLE           Medium::Sample      (homogeneous.cpp:9-51)            max_distance[0] seed[18]             valid scattered pdf distance att[4:7]
+ *   MEDIUM_EVALUATE         Medium::Evaluate    (homogeneous.cpp:53-82)           distance[0]                          same
+ *   PHASE_SAMPLE            Medium::SamplePhase (medium.cpp:58-72)                wo[3:6] seed[18]                     valid pdf att[2:5] wi[5:8]
+ *   PHASE_EVALUATE          Medium::EvaluatePhase (medium.cpp:74-87)              wi[0:3] wo[3:6]                      valid pdf att[2:5]
+ *   TEXTURE                 Texture::GetColor   (texture.cpp)                     uv[0:2]                              rgb[0:3]
+ *   SURFACE                 hit attributes of Primitive::Intersect (triangle.cpp:115-148, sphere.cpp:46-88, ...)
+ *                           prim bits[0] (leaf-order index as the traversal kernels store it: NOT the b200pt_debug_hit
+ *                           numbering) u[1] v[2] ray origin[3:6] dir[6:9] t[9]      pos[0:3] n[3:6] t[6:9] b[9:12] uv[12:14] inside[14] inst bits[15] */
+enum {
+    B200PT_EVAL_BSDF_EVALUATE = 0, B200PT_EVAL_BSDF_SAMPLE = 1, B200PT_EVAL_EMITTER_SAMPLE = 2, B200PT_EVAL_EMITTER_DIR = 3,
+    B200PT_EVAL_MEDIUM_SAMPLE = 4, B200PT_EVAL_MEDIUM_EVALUATE = 5, B200PT_EVAL_PHASE_SAMPLE = 6, B200PT_EVAL_PHASE_EVALUATE = 7,
+    B200PT_EVAL_TEXTURE = 8, B200PT_EVAL_SURFACE = 9
+};
+#define B200PT_EVAL_IN 32
+#define B200PT_EVAL_OUT 16
+int b200pt_debug_eval(b200pt_handle h, uint32_t what, uint32_t id, uint64_t n, const float *in_host, float *out_host);
 
 /* ---- scene packs: a lossless binary serialisation of b200pt_scene_desc, so a
  * scene parsed once by the reference's XML parser can travel without it. ---- */

@@ -50,9 +50,13 @@ STATS_COUNTERS = 1  # B200PT_STATS_COUNTERS
 STATS_TIMING = 2    # B200PT_STATS_TIMING
 RENDER_NO_TILE_CULL = 1  # B200PT_RENDER_NO_TILE_CULL
 CREATE_GPU_LBVH = 1      # B200PT_CREATE_GPU_LBVH
-CREATE_BVH2 = 2          # B200PT_CREATE_BVH2
+CREATE_BVH8 = 2          # B200PT_CREATE_BVH8
 DEBUG_ANY_HIT = 1        # B200PT_DEBUG_ANY_HIT
 DEBUG_PER_LANE_LOOP = 2  # B200PT_DEBUG_PER_LANE_LOOP
+DEBUG_RAW_PRIM = 4       # B200PT_DEBUG_RAW_PRIM
+(EVAL_BSDF_EVALUATE, EVAL_BSDF_SAMPLE, EVAL_EMITTER_SAMPLE, EVAL_EMITTER_DIR, EVAL_MEDIUM_SAMPLE, EVAL_MEDIUM_EVALUATE,
+ EVAL_PHASE_SAMPLE, EVAL_PHASE_EVALUATE, EVAL_TEXTURE, EVAL_SURFACE) = range(10)
+EVAL_IN, EVAL_OUT = 32, 16
 
 
 class Stats(ctypes.Structure):
@@ -77,7 +81,7 @@ EXPORTED_SYMBOLS = [
     "b200pt_create", "b200pt_destroy", "b200pt_render", "b200pt_render_device", "b200pt_render_progressive_device", "b200pt_tile_buffer_floats",
     "b200pt_render_tiles_device", "b200pt_assemble_tiles_device", "b200pt_get_stats", "b200pt_last_error",
     "b200pt_get_kulla_conty", "b200pt_get_envmap_tables", "b200pt_scene_load", "b200pt_scene_save",
-    "b200pt_scene_get_desc", "b200pt_scene_free", "b200pt_debug_trace",
+    "b200pt_scene_get_desc", "b200pt_scene_free", "b200pt_debug_trace", "b200pt_debug_eval",
 ]
 
 _lib = None
@@ -115,6 +119,7 @@ def lib():
     L.b200pt_scene_free.argtypes = [vp]
     L.b200pt_scene_free.restype = None
     L.b200pt_debug_trace.argtypes = [vp, vp, u64, u32, vp]
+    L.b200pt_debug_eval.argtypes = [vp, u32, u32, u64, vp, vp]
     _lib = L
     return L
 
@@ -194,14 +199,21 @@ class Renderer:
         _check(lib().b200pt_assemble_tiles_device(self._h, width, height, tile_world, gathered_tensor.data_ptr(),
                                                   frame_tensor.data_ptr(), stream), self._h)
 
-    def debug_trace(self, rays, any_hit=False, per_lane_loop=False):
+    def debug_trace(self, rays, any_hit=False, per_lane_loop=False, raw_prim=False):
         """Test hook (b200pt_debug_trace): rays = float32 [n, 8] (origin, direction, tmin, tmax) through the traversal kernels.
         Returns (t [n] float32, prim [n] uint32, uv [n, 2] float32)."""
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
         out = np.zeros((len(rays), 4), dtype=np.float32)
-        flags = (DEBUG_ANY_HIT if any_hit else 0) | (DEBUG_PER_LANE_LOOP if per_lane_loop else 0)
+        flags = (DEBUG_ANY_HIT if any_hit else 0) | (DEBUG_PER_LANE_LOOP if per_lane_loop else 0) | (DEBUG_RAW_PRIM if raw_prim else 0)
         _check(lib().b200pt_debug_trace(self._h, rays.ctypes.data, len(rays), flags, out.ctypes.data), self._h)
         return out[:, 0].copy(), out[:, 1].copy().view(np.uint32), out[:, 2:4].copy()
+
+    def debug_eval(self, what, index, inputs):
+        """Test hook (b200pt_debug_eval): inputs float32 [n, 32] -> float32 [n, 16]; layouts in include/b200pt.h."""
+        inputs = np.ascontiguousarray(inputs, dtype=np.float32).reshape(-1, EVAL_IN)
+        out = np.zeros((len(inputs), EVAL_OUT), dtype=np.float32)
+        _check(lib().b200pt_debug_eval(self._h, what, index, len(inputs), inputs.ctypes.data, out.ctypes.data), self._h)
+        return out
 
     def stats(self):
         s = Stats()

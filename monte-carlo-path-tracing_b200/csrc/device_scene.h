@@ -146,8 +146,8 @@ struct DIntegrator {
 
 // Everything the kernels dereference.  Passed by value as a kernel parameter.
 struct DeviceScene {
-    const BvhNode *nodes;        uint32_t num_nodes;     // BVH2 layout (B200PT_CREATE_BVH2 / the GPU LBVH builder), else empty
-    const WideNode *wide_nodes;  uint32_t num_wide_nodes; // compressed BVH8 layout (default); exactly one of the two is populated
+    const BvhNode *nodes;        uint32_t num_nodes;     // binary layout (default / the GPU LBVH builder), else empty
+    const WideNode *wide_nodes;  uint32_t num_wide_nodes; // compressed 8-wide layout (B200PT_CREATE_BVH8); exactly one of the two is populated
     const TriVerts *tri_verts;   uint32_t num_tris;
     const TriShade *tri_shade;
     const uint8_t *tri_bsdf_type; // per triangle: b200pt_bsdf_type of its instance's BSDF (0 = none), the shading bin of a hit

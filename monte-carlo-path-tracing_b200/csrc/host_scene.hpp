@@ -11,8 +11,8 @@
 namespace b200pt {
 
 struct HostScene {
-    std::vector<BvhNode> nodes;          // binary layout (B200PT_CREATE_BVH2 or the GPU LBVH builder) ...
-    std::vector<WideNode> wide_nodes;    // ... or the compressed 8-wide layout (default); never both
+    std::vector<BvhNode> nodes;          // binary layout (default, and what the GPU LBVH builder emits) ...
+    std::vector<WideNode> wide_nodes;    // ... or the compressed 8-wide layout (B200PT_CREATE_BVH8); never both
     uint32_t wide_depth = 0, wide_top_nodes = 0;
     std::vector<TriVerts> tri_verts;
     std::vector<TriShade> tri_shade;
@@ -40,8 +40,8 @@ struct HostScene {
 
 // Returns false and sets *error on an inconsistent description.
 // gpu_lbvh: build the BVH with the GPU LBVH builder (bvh_gpu.cu) instead of the host binned-SAH builder (binary layout).
-// bvh2: keep the host SAH tree in the binary 64-byte layout instead of collapsing it into the compressed 8-wide one.
-bool BuildHostScene(const b200pt_scene_desc &desc, uint32_t max_leaf_size, bool gpu_lbvh, bool bvh2, HostScene *out, std::string *error);
+// bvh8: collapse the host SAH tree into the compressed 8-wide layout instead of flattening it into the binary one.
+bool BuildHostScene(const b200pt_scene_desc &desc, uint32_t max_leaf_size, bool gpu_lbvh, bool bvh8, HostScene *out, std::string *error);
 
 // camera.cpp:26-37 for an arbitrary output size (the CLI may override width/height, Q7).
 DCamera MakeCamera(const b200pt_camera &cam, uint32_t width, uint32_t height);

@@ -508,6 +508,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         }
         const uint32_t depth = run.depth;
         auto finish_batch = [&] {
+            launch(kClassOther, [&] { LaunchSettle(la, ar.counters, -1, true, ar.shadow, ar.radiance, capacity); }); // NEE of the last bounce
             launch(kClassOther, [&] { LaunchResolve(la, run.bp, ar.radiance, capacity, c->accum.ptr); });
             run.in_batch = false;
             run.sample_begin += run.bp.sample_count;
@@ -518,9 +519,11 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         };
         // From the second bounce on, the tail kernel looks at the survivor queue first: once it is short enough it finishes
         // every remaining path in this one launch and the per-bounce kernels below find nothing to do.
+        // Settle first: the NEE contributions of the previous bounce are added before anything of this bounce, whichever
+        // kernel handles it (the order of float additions per sample is then the same with and without the tail kernel).
+        if (depth > 1) launch(kClassOther, [&] { LaunchSettle(la, ar.counters, run.which ^ 1, true, ar.shadow, ar.radiance, capacity); });
         if (depth > 1 && c->tail_paths > 0)
             launch(kClassTail, [&] { LaunchTail(la, c->scene, run.bp, depth, ar.queue[run.which], run.which, ar.radiance, capacity, ar.counters, c->tail_paths); });
-        if (depth > 1) launch(kClassOther, [&] { LaunchResetCounters(la, ar.counters, run.which ^ 1, true); });
         launch(kClassShade, [&] {
             const int n = LaunchShade(la, c->scene, run.bp, depth, ar.queue[run.which], run.which, ar.queue[run.which ^ 1], bins, ar.shadow,
                                       ar.radiance, ar.counters, capacity);
@@ -631,8 +634,8 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     const char *builder_env = getenv("B200PT_BVH_BUILDER"); // "lbvh" / "sah": overrides the create option (experiments)
     const bool gpu_lbvh = builder_env ? std::string(builder_env) == "lbvh" : (opts && (opts->flags & B200PT_CREATE_GPU_LBVH));
     const char *layout_env = getenv("B200PT_BVH_LAYOUT");   // "2" / "8": overrides the create option (experiments)
-    const bool bvh2 = layout_env ? atoi(layout_env) == 2 : (opts && (opts->flags & B200PT_CREATE_BVH2));
-    if (!BuildHostScene(*scene, opts ? opts->max_leaf_size : 0, gpu_lbvh, bvh2, &c->host, &err)) {
+    const bool bvh8 = layout_env ? atoi(layout_env) == 8 : (opts && (opts->flags & B200PT_CREATE_BVH8));
+    if (!BuildHostScene(*scene, opts ? opts->max_leaf_size : 0, gpu_lbvh, bvh8, &c->host, &err)) {
         // same prefix as renderer.cpp:343-346
         return SetGlobalError(B200PT_EINVAL, "error when commit renderer.\n\t" + err);
     }
@@ -787,9 +790,35 @@ int b200pt_debug_trace(b200pt_handle h, const b200pt_debug_ray *rays_host, uint6
     lc.blocks = h->num_sms * h->ctas_per_sm, lc.threads = 256, lc.stream = h->stream, lc.stats = false;
     lc.top_nodes = 0, lc.refill = h->refill, lc.min_inner = h->min_inner, lc.tri_min = h->tri_min;
     LaunchDebugTrace(lc, h->scene, rays.ptr, static_cast<uint32_t>(n), (flags & B200PT_DEBUG_ANY_HIT) != 0, (flags & B200PT_DEBUG_PER_LANE_LOOP) != 0,
-                     hits.ptr, counter.ptr);
+                     (flags & B200PT_DEBUG_RAW_PRIM) != 0, hits.ptr, counter.ptr);
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaMemcpyAsync(hits_host, hits.ptr, n * sizeof(b200pt_debug_hit), cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    return B200PT_OK;
+}
+
+int b200pt_debug_eval(b200pt_handle h, uint32_t what, uint32_t id, uint64_t n, const float *in_host, float *out_host) {
+    if (!h || (n && (!in_host || !out_host))) return SetGlobalError(B200PT_EINVAL, "b200pt_debug_eval: null argument");
+    if (n == 0) return B200PT_OK;
+    const DeviceScene &s = h->scene;
+    uint64_t limit = 0;
+    switch (what) {
+    case B200PT_EVAL_BSDF_EVALUATE: case B200PT_EVAL_BSDF_SAMPLE: limit = s.num_bsdfs; break;
+    case B200PT_EVAL_EMITTER_SAMPLE: case B200PT_EVAL_EMITTER_DIR: limit = s.integrator.num_emitters; break;
+    case B200PT_EVAL_MEDIUM_SAMPLE: case B200PT_EVAL_MEDIUM_EVALUATE: case B200PT_EVAL_PHASE_SAMPLE: case B200PT_EVAL_PHASE_EVALUATE: limit = s.num_media; break;
+    case B200PT_EVAL_TEXTURE: limit = s.num_textures; break;
+    case B200PT_EVAL_SURFACE: limit = 1; break;
+    default: return h->Fail(B200PT_EINVAL, "b200pt_debug_eval: unknown function.");
+    }
+    if (id >= limit || n > (1ull << 26)) return h->Fail(B200PT_EINVAL, "b200pt_debug_eval: index out of range.");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    DeviceArray<float> in, out;
+    CU_CHECK(h, in.Alloc(n * B200PT_EVAL_IN));
+    CU_CHECK(h, out.Alloc(n * B200PT_EVAL_OUT));
+    CU_CHECK(h, cudaMemcpyAsync(in.ptr, in_host, n * B200PT_EVAL_IN * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    LaunchDebugEval(h->stream, s, what, id, static_cast<uint32_t>(n), in.ptr, out.ptr);
+    CU_CHECK(h, cudaGetLastError());
+    CU_CHECK(h, cudaMemcpyAsync(out_host, out.ptr, n * B200PT_EVAL_OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     return B200PT_OK;
 }

@@ -658,8 +658,8 @@ DCamera MakeCamera(const b200pt_camera &cam, uint32_t width, uint32_t height) {
     return c;
 }
 
-bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu_lbvh, bool bvh2, HostScene *hs, std::string *error) {
-    const bool wide = !bvh2 && !gpu_lbvh; // the GPU builder emits the binary layout directly
+bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu_lbvh, bool bvh8, HostScene *hs, std::string *error) {
+    const bool wide = bvh8 && !gpu_lbvh; // the GPU builder emits the binary layout directly
     if (d.abi_version != B200PT_ABI_VERSION) {
         *error = "b200pt_scene_desc.abi_version mismatch";
         return false;

@@ -195,7 +195,7 @@ __device__ __forceinline__ bool ShadeVertex(const DeviceScene &scene, const Batc
         ShadowCandidate sc;
         if (alive) {
             const DEmitter &em = scene.emitters[e];
-            const float xi_0 = rng.Next(), xi_1 = rng.Next();
+            const float xi_1 = rng.Next(), xi_0 = rng.Next(); // path.cpp:149 argument order as GCC evaluates it (Q16)
             const EmitterRec erec = EmitterSample(scene, em, vertex_pos, xi_0, xi_1);
             bool ok = erec.valid;
             if (ok && !scattering && Dot(-erec.wi, surf.n) < kEpsilonFloat) ok = false;
@@ -242,7 +242,7 @@ __device__ __forceinline__ bool ShadeVertex(const DeviceScene &scene, const Batc
             const float xi_l = rng.Next();
             const uint32_t index_area_light = BinarySearch(ig.num_area_lights + 1, scene.cdf_area_light, xi_l) - 1; // Q4
             const uint32_t light_inst = __ldg(scene.map_area_light_instance + index_area_light);
-            const float xi_0 = rng.Next(), xi_1 = rng.Next(), xi_2 = rng.Next();
+            const float xi_2 = rng.Next(), xi_1 = rng.Next(), xi_0 = rng.Next(); // path.cpp:196 (Q16)
             const LightPoint lp = SampleInstance(scene, light_inst, xi_0, xi_1, xi_2);
             const V3 d_vec = vertex_pos - lp.pos;
             const float distance = Length(d_vec);
@@ -364,11 +364,38 @@ __global__ void __launch_bounds__(kShadeThreads, B200PT_SHADE_MIN_CTAS(VOL, ONLY
     // positions, appended by k_bin_hits), so that the warps of this launch all run the same BSDF model.
     // Nothing to do once the tail kernel has taken the batch's remaining paths over.
     const uint32_t n = counters->tail_taken ? 0u : (bin_list != nullptr ? counters->bin_count[which_in][bin] : counters->queue[which_in]);
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (uint32_t i0 = tid - lane; i0 < n; i0 += stride) {
-        const bool active = i0 + lane < n;
-        const uint32_t i = !active ? 0u : (bin_list != nullptr ? bin_list[i0 + lane] : i0 + lane);
+    // Warp-local compaction of the live entries.  From the second bounce on most queue entries of an open scene are dead
+    // (Dragon: 55 % of the rays escaped, and without an environment map an escaped ray has nothing left to do): a warp
+    // that shaded its 32 consecutive entries would run the whole vertex code at half its lanes.  Instead it scans
+    // chunks of 32 hit records, keeps the positions of the live ones in a small per-warp list and shades 32 of them at a
+    // time — no global atomics (a per-ray atomic inside the traversal kernel, or a separate binning pass, cost more than
+    // the dead lanes did: profiles/README.md), and entries that are all live pass straight through.
+    __shared__ uint32_t pending_all[kShadeThreads / 32][64];
+    uint32_t *pending = pending_all[warp];
+    const bool dead_possible = !VOL && scene.integrator.id_envmap == kInvalid; // the shortcut of LoadPathVertex
+    uint32_t count = 0;                                                         // live positions waiting in `pending` (warp-uniform)
+    for (uint32_t i0 = tid - lane; i0 < n || count > 0;) {
+        while (count < 32u && i0 < n) {
+            const uint32_t k = i0 + lane;
+            bool live = k < n;
+            uint32_t pos = 0;
+            if (live) {
+                pos = bin_list != nullptr ? bin_list[k] : k;
+                if (dead_possible) live = qin.hit[pos].prim != kPrimMiss;
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, live);
+            if (live) pending[count + __popc(ballot & ((1u << lane) - 1u))] = pos;
+            count += __popc(ballot);
+            i0 += stride;
+        }
+        __syncwarp();
+        const uint32_t take = min(count, 32u);
+        const bool active = lane < take;
+        const uint32_t i = active ? pending[count - take + lane] : 0u;
+        count -= take;
+        __syncwarp();
         PathVertex v;
         bool alive = LoadPathVertex<VOL>(scene, qin, i, active, &v);
         PathNext next;

@@ -302,16 +302,19 @@ __device__ __forceinline__ V3 FresnelSchlick(float cos_theta, V3 r) { return (1.
 // kulla_conty.cpp:82-131
 __device__ __forceinline__ float GetBrdfAvg(const float *buf, float cos_theta, float roughness) {
     constexpr int R = kLutResolution;
-    // EvaluateDielectric's transmission branch passes N_dot_O < 0 (dielectric.cpp:207-212): the reference reads
-    // out of bounds there (arbitrary heap value); clamped here, as in the oracle.
-    cos_theta = fmaxf(cos_theta, 0.0f);
+    // Quirk found by the pointwise tests: kLutResolution is a uint32_t in the reference (kulla_conty.hpp:9), so its
+    // `offset_int2 >= kLutResolution - 1` compares UNSIGNED.  EvaluateDielectric passes negative cosines (N_dot_O < 0 in the
+    // transmission branch, dielectric.cpp:207-212; N_dot_I < 0 for light arriving from below): a column <= -1 wraps to a
+    // huge value and takes the "last column" branch — a cosine below -1/128 reads the table at cosine 1.  Cosines in
+    // (-1/128, 0) truncate to column 0 and extrapolate with a negative weight.
     const float offset1 = roughness * R, offset2 = cos_theta * R;
     const int i1 = static_cast<int>(offset1), i2 = static_cast<int>(offset2);
+    const bool last_column = static_cast<uint32_t>(i2) >= static_cast<uint32_t>(R - 1);
     if (i1 >= R - 1) {
-        if (i2 >= R - 1) return __ldg(buf + (R - 1) * R + R - 1);
+        if (last_column) return __ldg(buf + (R - 1) * R + R - 1);
         return Lerp(__ldg(buf + (R - 1) * R + i2), __ldg(buf + (R - 1) * R + i2 + 1), offset2 - i2);
     }
-    if (i2 >= R - 1) return Lerp(__ldg(buf + i1 * R + R - 1), __ldg(buf + (i1 + 1) * R + R - 1), offset1 - i1);
+    if (last_column) return Lerp(__ldg(buf + i1 * R + R - 1), __ldg(buf + (i1 + 1) * R + R - 1), offset1 - i1);
     return Lerp(Lerp(__ldg(buf + i1 * R + i2), __ldg(buf + (i1 + 1) * R + i2), offset1 - i1),
                 Lerp(__ldg(buf + i1 * R + i2 + 1), __ldg(buf + (i1 + 1) * R + i2 + 1), offset1 - i1), offset2 - i2);
 }
@@ -334,7 +337,7 @@ __device__ __forceinline__ void EvaluateDiffuse(const DeviceScene &s, const DBsd
 }
 __device__ __forceinline__ void SampleDiffuse(const DeviceScene &s, const DBsdf &d, Rng &rng, BsdfRec *rec) {
     V3 wi_local;
-    const float xi_0 = rng.Next(), xi_1 = rng.Next();
+    const float xi_1 = rng.Next(), xi_0 = rng.Next(); // drawn in the reference's order (Q16: GCC evaluates call arguments right to left)
     SampleHemisCos(xi_0, xi_1, &wi_local, &rec->pdf);
     if (rec->pdf < kEpsilon) return; // Q6
     rec->wi = -rec->ToWorld(wi_local);
@@ -396,7 +399,7 @@ __device__ __forceinline__ void OrenNayar(float roughness, V3 albedo, bool fast,
 // rough_diffuse.cpp:99-129
 __device__ __forceinline__ void SampleRoughDiffuse(const DeviceScene &s, const DBsdf &d, Rng &rng, BsdfRec *rec) {
     V3 wi;
-    const float xi_0 = rng.Next(), xi_1 = rng.Next();
+    const float xi_1 = rng.Next(), xi_0 = rng.Next(); // drawn in the reference's order (Q16: GCC evaluates call arguments right to left)
     SampleHemisCos(xi_0, xi_1, &wi, &rec->pdf);
     if (rec->pdf < kEpsilon) return;
     rec->wi = -Normalize(wi.x * rec->t + wi.y * rec->b + wi.z * rec->n);
@@ -424,7 +427,7 @@ __device__ __forceinline__ void SampleConductor(const DeviceScene &s, const DBsd
     V3 h_local = mk3(0.0f);
     float D = 0;
     const float alpha_u = TexColor(s, d.id_roughness_u, rec->uv).x, alpha_v = TexColor(s, d.id_roughness_v, rec->uv).x;
-    const float xi_0 = rng.Next(), xi_1 = rng.Next();
+    const float xi_1 = rng.Next(), xi_0 = rng.Next(); // drawn in the reference's order (Q16: GCC evaluates call arguments right to left)
     SampleGgx(xi_0, xi_1, alpha_u, alpha_v, &h_local, &D);
     const V3 h_world = rec->ToWorld(h_local);
     const float h_dot_o = Dot(rec->wo, h_world);
@@ -480,7 +483,7 @@ __device__ __forceinline__ void SampleDielectric(const DeviceScene &s, const DBs
     const float alpha_u = TexColor(s, d.id_roughness_u, rec->uv).x * scale, alpha_v = TexColor(s, d.id_roughness_v, rec->uv).x * scale;
     V3 h_local = mk3(0.0f);
     float D = 0;
-    const float xi_0 = rng.Next(), xi_1 = rng.Next();
+    const float xi_1 = rng.Next(), xi_0 = rng.Next(); // drawn in the reference's order (Q16: GCC evaluates call arguments right to left)
     SampleGgx(xi_0, xi_1, alpha_u, alpha_v, &h_local, &D);
     const V3 h_world = rec->ToWorld(h_local);
     float h_dot_o = Dot(rec->wo, h_world);
@@ -568,7 +571,7 @@ __device__ __forceinline__ void SampleThinDielectric(const DeviceScene &s, const
     V3 h_local = mk3(0.0f);
     float D = 0;
     const float alpha_u = TexColor(s, d.id_roughness_u, rec->uv).x, alpha_v = TexColor(s, d.id_roughness_v, rec->uv).x;
-    const float xi_0 = rng.Next(), xi_1 = rng.Next();
+    const float xi_1 = rng.Next(), xi_0 = rng.Next(); // drawn in the reference's order (Q16: GCC evaluates call arguments right to left)
     SampleGgx(xi_0, xi_1, alpha_u, alpha_v, &h_local, &D);
     const V3 h_world = rec->ToWorld(h_local);
     const float h_dot_o = Dot(rec->wo, h_world);
@@ -636,7 +639,7 @@ __device__ __forceinline__ void SamplePlastic(const DeviceScene &s, const DBsdf 
     const float alpha = TexColor(s, d.id_roughness_u, rec->uv).x;
     float n_dot_i = 0;
     if (rng.Next() < pdf_spec) {
-        const float xi_0 = rng.Next(), xi_1 = rng.Next();
+        const float xi_1 = rng.Next(), xi_0 = rng.Next(); // drawn in the reference's order (Q16: GCC evaluates call arguments right to left)
         SampleGgx(xi_0, xi_1, alpha, &h_local, &D);
         h_world = rec->ToWorld(h_local);
         rec->wi = -Reflect(-rec->wo, h_world);
@@ -651,7 +654,7 @@ __device__ __forceinline__ void SamplePlastic(const DeviceScene &s, const DBsdf 
     } else {
         V3 wi_local = mk3(0.0f);
         float pdf_diff_local = 0.0f;
-        const float xi_0 = rng.Next(), xi_1 = rng.Next();
+        const float xi_1 = rng.Next(), xi_0 = rng.Next(); // drawn in the reference's order (Q16: GCC evaluates call arguments right to left)
         SampleHemisCos(xi_0, xi_1, &wi_local, &pdf_diff_local);
         rec->wi = -rec->ToWorld(wi_local);
         n_dot_i = Dot(-rec->wi, rec->n);
@@ -960,7 +963,7 @@ __device__ __forceinline__ void PhaseSample(const DMedium &m, Rng &rng, PhaseRec
         rec->valid = true;
         rec->att = mk3(k1Div4Pi);
         rec->pdf = k1Div4Pi;
-        const float xi_0 = rng.Next(), xi_1 = rng.Next();
+        const float xi_1 = rng.Next(), xi_0 = rng.Next(); // drawn in the reference's order (Q16: GCC evaluates call arguments right to left)
         rec->wi = SampleSphereUniform(xi_0, xi_1);
         return;
     }

@@ -88,7 +88,9 @@ __device__ __forceinline__ bool IntersectTriangleWoop(const Ray &ray, const RayP
     const float det = U + V + W;
     if (det == 0.0f) return false;
     const float Az = pre.Sz * Akz, Bz = pre.Sz * Bkz, Cz = pre.Sz * Ckz;
-    const float T = U * Az + V * Bz + W * Cz;
+    // un-fused like the reference build (g++ for baseline x86-64 has no fma to contract into): t is then BIT-EQUAL to
+    // TLAS::Intersect's (tests/test_gpu_traversal.py)
+    const float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
     const float det_inv = 1.0f / det;
     const float t = T * det_inv;
     if (t > ray.tmax || t < ray.tmin) return false;
@@ -171,14 +173,15 @@ __device__ __forceinline__ bool IntersectAnalytic(const AnalyticPrim &p, const R
 
 // Stochastic alpha test of a candidate hit: Bsdf::IsTransparent (bsdf.cpp:272-276) as the reference calls it from inside
 // every primitive test (triangle.cpp:116-118, sphere.cpp:42, disk.cpp:41, cylinder.cpp:50).  A transparent verdict makes
-// the primitive invisible to THIS ray only; the random number comes from the ray's own Philox stream (the reference
-// advances the per-pixel LCG here).
-__device__ __forceinline__ bool OpacityRejects(const DeviceScene &scene, uint32_t inst, V2 uv, Rng &rng) {
+// the primitive invisible to THIS ray only; the random number is a function of the ray's own Philox stream AND the
+// primitive (the reference advances the per-pixel LCG here), so the verdict does not depend on the order in which a
+// traversal happens to meet the candidates: both tree layouts and both loop shapes take the same decisions.
+__device__ __forceinline__ bool OpacityRejects(const DeviceScene &scene, uint32_t inst, V2 uv, const Rng &rng, uint32_t prim) {
     const uint32_t id_bsdf = scene.instances[inst].id_bsdf;
     if (id_bsdf == kInvalid) return false;
     const uint32_t id_opacity = scene.bsdfs[id_bsdf].id_opacity;
     if (id_opacity == kInvalid) return false;
-    return TexIsTransparent(scene, id_opacity, uv, rng.Next());
+    return TexIsTransparent(scene, id_opacity, uv, rng.ForPrimitive(prim));
 }
 
 // Random-number domains (4th Philox counter word) of the alpha tests inside closest-hit and any-hit traversal; the
@@ -290,7 +293,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                     float t;
                     V2 uv = {0.0f, 0.0f};
                     if (IntersectAnalytic(p, ray, &t, OPACITY ? &uv : nullptr)) {
-                        if (OPACITY && OpacityRejects(scene, p.inst, uv, rng)) continue;
+                        if (OPACITY && OpacityRejects(scene, p.inst, uv, rng, kPrimAnalyticBit | i)) continue;
                         found = true;
                         if (any) {
                             cur = kSentinel;
@@ -359,7 +362,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                             const float *tc = &scene.tri_shade[first + j].uv[0][0];
                             const float w = 1.0f - u - v;
                             const V2 uv = {u * __ldg(tc) + v * __ldg(tc + 2) + w * __ldg(tc + 4), u * __ldg(tc + 1) + v * __ldg(tc + 3) + w * __ldg(tc + 5)};
-                            if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng)) continue;
+                            if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng, __float_as_uint(p1.w))) continue;
                         }
                         found = true;
                         if (any) {
@@ -424,7 +427,7 @@ __device__ __forceinline__ bool TraverseSingle(const DeviceScene &scene, Ray ray
         float t;
         V2 uv = {0.0f, 0.0f};
         if (IntersectAnalytic(p, ray, &t, opacity ? &uv : nullptr)) {
-            if (opacity && OpacityRejects(scene, p.inst, uv, rng)) continue;
+            if (opacity && OpacityRejects(scene, p.inst, uv, rng, kPrimAnalyticBit | i)) continue;
             found = true;
             if (any) return true;
             ray.tmax = t;
@@ -474,7 +477,7 @@ __device__ __forceinline__ bool TraverseSingle(const DeviceScene &scene, Ray ray
                         const float *tc = &scene.tri_shade[first + j].uv[0][0];
                         const float w = 1.0f - u - v;
                         const V2 uv = {u * __ldg(tc) + v * __ldg(tc + 2) + w * __ldg(tc + 4), u * __ldg(tc + 1) + v * __ldg(tc + 3) + w * __ldg(tc + 5)};
-                        if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng)) continue;
+                        if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng, __float_as_uint(p1.w))) continue;
                     }
                     found = true;
                     if (any) return true;

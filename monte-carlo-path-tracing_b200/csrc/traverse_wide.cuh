@@ -21,6 +21,14 @@ __device__ __forceinline__ float ByteAsBiasedFloat(uint32_t w) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + J));
 }
 
+// 0xff in every byte of the result whose counterpart in `x` has its top bit set, 0x00 elsewhere.  PTX prmt with the
+// "replicate sign" selector bit; __byte_perm() masks that bit off, hence the inline PTX.
+__device__ __forceinline__ uint32_t SignExtendBytes(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
 #ifndef B200PT_WIDE_X2
 #define B200PT_WIDE_X2 0   // 1: packed fp32x2 plane distances (measured variant, profiles/README.md)
 #endif
@@ -67,7 +75,7 @@ __device__ __forceinline__ uint32_t WideNodeHits(const uint4 &n0, const uint4 &n
     for (int half = 0; half < 2; ++half) {
         const uint32_t meta4 = half ? n1.w : n1.z;
         const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = __byte_perm(is_inner4 << 3, 0u, 0xba98u); // 0xff in the bytes of inner children
+        const uint32_t inner_mask4 = SignExtendBytes(is_inner4 << 3); // 0xff in the bytes of inner children
         const uint32_t bit_index4 = (meta4 ^ (wr.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
         const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
         const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
@@ -129,7 +137,7 @@ __device__ __forceinline__ void LoadWideNode(const WideNode *__restrict__ nodes,
 
 // One candidate triangle of a leaf: the Woop test, the alpha test, the hit record.  Returns true when an occlusion ray is done.
 template <bool OPACITY>
-__device__ __forceinline__ bool WideTestTriangle(const DeviceScene &scene, uint32_t tri, Ray &ray, const RayPre &pre, bool any, Rng &rng,
+__device__ __forceinline__ bool WideTestTriangle(const DeviceScene &scene, uint32_t tri, Ray &ray, const RayPre &pre, bool any, const Rng &rng,
                                                  HitRec &hit, bool &found) {
     const float4 *verts = reinterpret_cast<const float4 *>(scene.tri_verts + tri);
     const float4 p0 = __ldg(verts), p1 = __ldg(verts + 1), p2 = __ldg(verts + 2);
@@ -140,7 +148,8 @@ __device__ __forceinline__ bool WideTestTriangle(const DeviceScene &scene, uint3
         const float *tc = &scene.tri_shade[tri].uv[0][0];
         const float w = 1.0f - u - v;
         const V2 uv = {u * __ldg(tc) + v * __ldg(tc + 2) + w * __ldg(tc + 4), u * __ldg(tc + 1) + v * __ldg(tc + 3) + w * __ldg(tc + 5)};
-        if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng)) return false;
+        // keyed by the triangle's index in the scene description, which both tree layouts share
+        if (OpacityRejects(scene, __float_as_uint(p0.w), uv, rng, __float_as_uint(p1.w))) return false;
     }
     found = true;
     if (any) return true;
@@ -204,7 +213,7 @@ __device__ __forceinline__ void TraversePersistentWide(const DeviceScene &scene,
                     float t;
                     V2 uv = {0.0f, 0.0f};
                     if (IntersectAnalytic(p, ray, &t, OPACITY ? &uv : nullptr)) {
-                        if (OPACITY && OpacityRejects(scene, p.inst, uv, rng)) continue;
+                        if (OPACITY && OpacityRejects(scene, p.inst, uv, rng, kPrimAnalyticBit | i)) continue;
                         found = true;
                         if (any) {
                             ngroup.y = 0u;
@@ -283,7 +292,7 @@ __device__ __forceinline__ bool TraverseSingleWide(const DeviceScene &scene, Ray
         float t;
         V2 uv = {0.0f, 0.0f};
         if (IntersectAnalytic(p, ray, &t, opacity ? &uv : nullptr)) {
-            if (opacity && OpacityRejects(scene, p.inst, uv, rng)) continue;
+            if (opacity && OpacityRejects(scene, p.inst, uv, rng, kPrimAnalyticBit | i)) continue;
             found = true;
             if (any) return true;
             ray.tmax = t;

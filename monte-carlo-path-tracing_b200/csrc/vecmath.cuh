@@ -223,6 +223,7 @@ __device__ __forceinline__ uint4 Philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
+#if !defined(B200PT_RNG_REPLAY)
 struct Rng {
     uint32_t c0, c1, c2, domain;
     uint2 key;
@@ -242,7 +243,34 @@ struct Rng {
         ++idx;
         return static_cast<float>(v >> 8) * (1.0f / 16777216.0f); // 24-bit mantissa, as math.hpp:60-62
     }
+    // One number per (stream, primitive), independent of how many were drawn before: the alpha tests inside traversal.
+    __device__ __forceinline__ float ForPrimitive(uint32_t prim) const {
+        const uint4 r = Philox4x32_10(make_uint4(c0, c1, c2 ^ 0x80000000u, domain ^ (prim * 0x9E3779B9u)), key);
+        return static_cast<float>(r.x >> 8) * (1.0f / 16777216.0f);
+    }
 };
+#else
+// Test build only (csrc/debug_eval.cu, -DB200PT_RNG_REPLAY): the reference's own generator — the per-pixel LCG RandomFloat
+// (include/csrt/utils/math.hpp:57-63) — behind the same interface, so that the sampling routines can be compared with the
+// reference's POINTWISE from a common seed (the device code draws its numbers in the order GCC evaluates the reference's
+// call arguments, right to left).  The inline namespace gives every function that takes an Rng a different mangled
+// name from the product's, so the two definitions never meet.
+inline namespace lcg_replay {
+struct Rng {
+    uint32_t state;
+    __device__ __forceinline__ explicit Rng(uint32_t seed) : state(seed) {}
+    __device__ __forceinline__ Rng(uint32_t, uint32_t, uint32_t, uint2, uint32_t = 0) : state(0) {}
+    __device__ __forceinline__ float Next() {
+        state = state * 1664525u + 1013904223u;
+        return static_cast<float>(state & 0x00FFFFFFu) / static_cast<float>(0x01000000u);
+    }
+    __device__ __forceinline__ float ForPrimitive(uint32_t prim) const {
+        const uint32_t s = (state ^ prim) * 1664525u + 1013904223u;
+        return static_cast<float>(s & 0x00FFFFFFu) / static_cast<float>(0x01000000u);
+    }
+};
+} // namespace lcg_replay
+#endif
 
 // math.hpp:29-41
 __device__ __forceinline__ float VanDerCorput2(uint32_t index) {

@@ -227,11 +227,12 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const
     auto finish = [&](uint32_t i, const HitRec &hit, bool found, bool any) {
         if (!any) {
             q.hit[i] = hit;
-        } else if (!found) { // unoccluded: the light sample counts
-            const uint32_t j = i - n_extend, slot = sq.slot[j];
-            atomicAdd(radiance + slot, sq.cr[j]);
-            atomicAdd(radiance + capacity + slot, sq.cg[j]);
-            atomicAdd(radiance + 2 * capacity + slot, sq.cb[j]);
+        } else if (!found) {
+            // Unoccluded: the light sample counts.  Rays end one lane at a time here, so reading the contribution and adding it
+            // with three atomics cost seven scattered memory instructions at ~4 active lanes (7.7 % of this kernel's stall
+            // samples, profiles/r01_k_trace_source.csv.gz).  The ray is only MARKED (one store); k_settle, the coalesced pass
+            // that opens the next bounce, adds the marked contributions.
+            sq.tmax[i - n_extend] = kShadowUnoccluded;
         }
     };
     TraverseLayout<true, STATS, OPACITY, LAYOUT>(scene, top, num_top, n, &counters->work_trace, refill, phase_lanes, bp.key, fetch, finish, tc, rays);
@@ -246,14 +247,14 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const
 // ---------------------------------------------------------------------------------------------
 template <int LAYOUT>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_debug_trace(const __grid_constant__ DeviceScene scene, const b200pt_debug_ray *rays_in,
-                                                                                uint32_t n, bool any_hit, bool single, b200pt_debug_hit *out,
-                                                                                uint32_t *work_counter, int refill, int phase_lanes) {
+                                                                                uint32_t n, bool any_hit, bool single, bool raw_prim,
+                                                                                b200pt_debug_hit *out, uint32_t *work_counter, int refill, int phase_lanes) {
     auto report = [&](uint32_t i, const HitRec &hit, bool found, bool any) {
         b200pt_debug_hit h;
         h.t = hit.t, h.u = hit.u, h.v = hit.v, h.prim = hit.prim;
         if (any) {
             h.prim = found ? 0u : kPrimMiss;
-        } else if (hit.prim != kPrimMiss && !(hit.prim & kPrimAnalyticBit)) { // leaf order -> index in the scene description
+        } else if (!raw_prim && hit.prim != kPrimMiss && !(hit.prim & kPrimAnalyticBit)) { // leaf order -> index in the scene description
             const uint32_t original = __float_as_uint(__ldg(&scene.tri_verts[hit.prim & kPrimIndexMask].v1.w));
             h.prim = original | (hit.prim & kPrimInsideBit);
         }
@@ -291,13 +292,32 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_debug_trace
 // ---------------------------------------------------------------------------------------------
 // Small kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void k_reset(Counters *c, int which_queue, bool reset_shadow) {
-    if (which_queue >= 0) {
-        c->queue[which_queue] = 0;
-        for (int b = 0; b < kNumShadeBins; ++b) c->bin_count[which_queue][b] = 0;
+// k_settle: between two bounces.  Adds the contributions of the NEE rays the last k_trace found unoccluded (marked in place,
+// see k_trace) to their samples — a coalesced pass over the shadow queue — and then, in the last CTA to finish, resets the
+// queue lengths and work counters for the next bounce (what a one-thread launch did before).
+__global__ void __launch_bounds__(kThreads) k_settle(Counters *c, int which_queue, bool reset_shadow, ShadowQueue sq, float *radiance, uint32_t capacity) {
+    const uint32_t n = c->shadow;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        if (sq.tmax[j] != kShadowUnoccluded) continue;
+        const uint32_t slot = sq.slot[j];
+        // several NEE rays of one vertex (one per emitter) may share the slot: atomics; with one emitter the sum has one order
+        atomicAdd(radiance + slot, sq.cr[j]);
+        atomicAdd(radiance + capacity + slot, sq.cg[j]);
+        atomicAdd(radiance + 2 * capacity + slot, sq.cb[j]);
     }
-    if (reset_shadow) c->shadow = 0;
-    c->work_trace = 0;
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&c->settle_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        if (which_queue >= 0) {
+            c->queue[which_queue] = 0;
+            for (int b = 0; b < kNumShadeBins; ++b) c->bin_count[which_queue][b] = 0;
+        }
+        if (reset_shadow) c->shadow = 0;
+        c->work_trace = 0;
+        c->settle_ticket = 0;
+    }
 }
 
 // Visibility pre-pass for camera rays.  Every camera ray of a tile starts at the eye and runs inside the pyramid spanned
@@ -543,11 +563,11 @@ int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
 }
 
 void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b200pt_debug_ray *rays, uint32_t n, bool any_hit, bool single,
-                      b200pt_debug_hit *out, uint32_t *work_counter) {
+                      bool raw_prim, b200pt_debug_hit *out, uint32_t *work_counter) {
     if (scene.num_wide_nodes > 0)
-        k_debug_trace<kLayoutWide><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, out, work_counter, lc.refill, lc.tri_min);
+        k_debug_trace<kLayoutWide><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, raw_prim, out, work_counter, lc.refill, lc.tri_min);
     else
-        k_debug_trace<kLayoutBinary><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, out, work_counter, lc.refill, lc.min_inner);
+        k_debug_trace<kLayoutBinary><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, raw_prim, out, work_counter, lc.refill, lc.min_inner);
 }
 
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
@@ -558,8 +578,9 @@ void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const Bat
     k_compact_tiles<<<1, 1024, 0, lc.stream>>>(flags, num_local_tiles, list);
 }
 
-void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow) {
-    k_reset<<<1, 1, 0, lc.stream>>>(counters, which_queue, reset_shadow);
+void LaunchSettle(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow, ShadowQueue sq, float *radiance,
+                  uint32_t capacity) {
+    k_settle<<<lc.blocks, kThreads, 0, lc.stream>>>(counters, which_queue, reset_shadow, sq, radiance, capacity);
 }
 
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum) {

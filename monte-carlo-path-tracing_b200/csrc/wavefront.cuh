@@ -6,7 +6,8 @@
 //   k_shade     hit attributes, emitter hit / env miss MIS, Russian roulette, NEE shadow-ray
 //               generation, BSDF / phase sampling, warp-ballot compaction of survivors
 //   k_trace     one launch per bounce: closest hit for the compacted survivor queue + any-hit for the NEE rays
-//               (adds the unoccluded contributions)
+//               (marks the unoccluded ones)
+//   k_settle    adds the marked NEE contributions (coalesced), resets the counters for the next bounce
 //   k_resolve   per-sample clamp + per-pixel sum (renderer.cpp:77-84)
 // All per-path state is SoA so that a warp's loads/stores are 128-byte transactions.
 #pragma once
@@ -68,7 +69,7 @@ struct Counters {             // device-resident
     uint32_t work_trace;
     uint32_t work_tail;       // next unclaimed entry of the tail kernel
     uint32_t tail_taken;      // != 0 once k_tail has taken over the batch's remaining paths (depth of the take-over + 1)
-    uint32_t pad[1];
+    uint32_t settle_ticket;   // CTAs of k_settle that have finished (the last one resets the counters)
     uint32_t bin_count[2][kNumShadeBins]; // entries of path queue 0 / 1 per shading bin (scenes with several BSDF models)
     ClassCounters cls[3];     // primary / extend / shadow traversal statistics (zeroed per render)
 };
@@ -153,9 +154,15 @@ void LaunchTail(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
                 float *radiance, uint32_t capacity, Counters *counters, uint32_t threshold);
 // Test hook (b200pt_debug_trace): rays[0..n) through the persistent traversal loop (or the per-lane one) of the scene's tree.
 void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b200pt_debug_ray *rays, uint32_t n, bool any_hit, bool single,
-                      b200pt_debug_hit *out, uint32_t *work_counter);
+                      bool raw_prim, b200pt_debug_hit *out, uint32_t *work_counter);
+// Test hook (b200pt_debug_eval, debug_eval.cu): leaf functions of the shading stage at caller-supplied inputs.
+void LaunchDebugEval(cudaStream_t stream, const DeviceScene &scene, uint32_t what, uint32_t id, uint32_t n, const float *in, float *out);
 constexpr uint32_t kMaxTailDepth = 4096; // = kMaxRounds of the host loop
-void LaunchResetCounters(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow);
+// Adds the contributions of the shadow rays the last k_trace marked unoccluded, then resets queue `which_queue` (>= 0), the
+// shadow queue (reset_shadow) and the traversal work counter for the next bounce.
+void LaunchSettle(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow, ShadowQueue sq, float *radiance,
+                  uint32_t capacity);
+constexpr float kShadowUnoccluded = -1.0f; // written over ShadowQueue::tmax by k_trace (a real tmax is never negative)
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum);
 void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,
                     float *frame, float *tiles);

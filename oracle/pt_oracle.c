@@ -546,17 +546,19 @@ static Vec3 FresnelSchlick3(float cos_theta, Vec3 r) { return add(muls(ssub(1.0f
 /* kulla_conty.cpp */
 static float GetBrdfAvg(const float *buf, float cos_theta, float roughness) { /* :82-131 */
     const int R = kLutResolution;
-    /* EvaluateDielectric's transmission branch (dielectric.cpp:207-212) passes N_dot_O < 0 here; the reference then
-     * indexes the table with a negative offset (an out-of-bounds heap read whose value is arbitrary).  Both
-     * restatements clamp instead; frames that take this branch match the reference only to ~1e-5. */
-    if (cos_theta < 0.0f) cos_theta = 0.0f;
+    /* Quirk (found by tests/test_oracle_pointwise.py): kLutResolution is a uint32_t (kulla_conty.hpp:9), so the reference's
+     * `offset_int2 >= kLutResolution - 1` compares UNSIGNED.  EvaluateDielectric passes negative cosines here (N_dot_O < 0 in its
+     * transmission branch, dielectric.cpp:207-212; N_dot_I < 0 for light arriving from below): a column <= -1 wraps to a huge
+     * value and takes the "last column" branch, i.e. a cosine below -1/128 reads the table at cosine 1.  Cosines in
+     * (-1/128, 0) truncate to column 0 and extrapolate with a negative weight. */
     const float offset1 = roughness * R, offset2 = cos_theta * R;
     const int i1 = (int)offset1, i2 = (int)offset2;
+    const int last_column = (uint32_t)i2 >= (uint32_t)(R - 1);
     if (i1 >= R - 1) {
-        if (i2 >= R - 1) return buf[(R - 1) * R + R - 1];
+        if (last_column) return buf[(R - 1) * R + R - 1];
         return lerpf(buf[(R - 1) * R + i2], buf[(R - 1) * R + i2 + 1], offset2 - i2);
     }
-    if (i2 >= R - 1) return lerpf(buf[i1 * R + R - 1], buf[(i1 + 1) * R + R - 1], offset1 - i1);
+    if (last_column) return lerpf(buf[i1 * R + R - 1], buf[(i1 + 1) * R + R - 1], offset1 - i1);
     return lerpf(lerpf(buf[i1 * R + i2], buf[(i1 + 1) * R + i2], offset1 - i1),
                  lerpf(buf[i1 * R + i2 + 1], buf[(i1 + 1) * R + i2 + 1], offset1 - i1), offset2 - i2);
 }
@@ -2557,5 +2559,126 @@ int oracle_shade(const b200pt_scene_desc *desc, int watertight, const float *eye
                                                                  : ShadePath(s, v3(eye[0], eye[1], eye[2]), v3(dir[0], dir[1], dir[2]), seed);
     rgb[0] = L.x, rgb[1] = L.y, rgb[2] = L.z;
     FreeScene(os);
+    return 0;
+}
+
+/* ---- pointwise entries: the restated leaf functions at caller-supplied inputs, same record layout as b200pt_debug_eval
+ * (include/b200pt.h) and ref_eval (oracle/ref_glue.cpp).  tests/test_oracle_pointwise.py pins them on the reference's own
+ * functions without a GPU; tests/test_gpu_pointwise.py compares the device functions with the reference's. ---- */
+void *oracle_scene_create(const b200pt_scene_desc *desc, int watertight) { return CommitScene(desc, 0, 0, 0, watertight); }
+void oracle_scene_destroy(void *handle) { if (handle) FreeScene((OracleScene *)handle); }
+
+int oracle_eval(void *handle, uint32_t what, uint32_t id, uint64_t n, const float *in_all, float *out_all) {
+    const Scene *s = &((OracleScene *)handle)->scene;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *in = in_all + i * B200PT_EVAL_IN;
+        float *out = out_all + i * B200PT_EVAL_OUT;
+        memset(out, 0, sizeof(float) * B200PT_EVAL_OUT);
+        uint32_t seed;
+        memcpy(&seed, in + 18, 4);
+#define IN3(p) v3((p)[0], (p)[1], (p)[2])
+#define OUT3(p, v) ((p)[0] = (v).x, (p)[1] = (v).y, (p)[2] = (v).z)
+        switch (what) {
+        case B200PT_EVAL_BSDF_EVALUATE:
+        case B200PT_EVAL_BSDF_SAMPLE: {
+            BsdfSampleRec rec = RecInit();
+            rec.wi = IN3(in), rec.wo = IN3(in + 3), rec.normal = IN3(in + 6), rec.tangent = IN3(in + 9), rec.bitangent = IN3(in + 12);
+            rec.texcoord.u = in[15], rec.texcoord.v = in[16];
+            rec.inside = in[17] != 0.0f;
+            if (what == B200PT_EVAL_BSDF_EVALUATE) BsdfEvaluate(s, s->bsdfs + id, &rec);
+            else BsdfSample(s, s->bsdfs + id, &seed, &rec);
+            out[0] = (float)rec.valid, out[1] = rec.pdf;
+            OUT3(out + 2, rec.attenuation), OUT3(out + 5, rec.wi);
+            break;
+        }
+        case B200PT_EVAL_EMITTER_SAMPLE: {
+            const Emitter *e = s->emitters + id;
+            const EmitterSampleRec rec = EmitterSample(e, IN3(in), in[3], in[4]);
+            out[0] = (float)rec.valid, out[1] = (float)rec.harsh, out[2] = rec.distance;
+            OUT3(out + 3, rec.wi);
+            if (rec.valid) {
+                const Vec3 Le = EmitterEvaluateRec(e, &rec);
+                OUT3(out + 6, Le);
+                out[9] = EmitterPdf(e, neg(rec.wi));
+            }
+            break;
+        }
+        case B200PT_EVAL_EMITTER_DIR: {
+            const Vec3 Le = EmitterEvaluateDir(s->emitters + id, IN3(in));
+            OUT3(out, Le);
+            out[3] = EmitterPdf(s->emitters + id, IN3(in));
+            break;
+        }
+        case B200PT_EVAL_MEDIUM_SAMPLE:
+        case B200PT_EVAL_MEDIUM_EVALUATE: {
+            MediumSampleRec rec = MediumRecInit();
+            if (what == B200PT_EVAL_MEDIUM_SAMPLE) {
+                MediumSample(s->media + id, in[0], &seed, &rec);
+            } else {
+                rec.distance = in[0];
+                MediumEvaluate(s->media + id, &rec);
+            }
+            out[0] = (float)rec.valid, out[1] = (float)rec.scattered, out[2] = rec.pdf, out[3] = rec.distance;
+            OUT3(out + 4, rec.attenuation);
+            break;
+        }
+        case B200PT_EVAL_PHASE_SAMPLE:
+        case B200PT_EVAL_PHASE_EVALUATE: {
+            PhaseSampleRec rec;
+            memset(&rec, 0, sizeof(rec));
+            rec.wi = IN3(in), rec.wo = IN3(in + 3);
+            if (what == B200PT_EVAL_PHASE_SAMPLE) PhaseSample(s->media + id, &seed, &rec);
+            else PhaseEvaluate(s->media + id, &rec);
+            out[0] = (float)rec.valid, out[1] = rec.pdf;
+            OUT3(out + 2, rec.attenuation), OUT3(out + 5, rec.wi);
+            break;
+        }
+        case B200PT_EVAL_TEXTURE: {
+            Vec2 uv = {in[0], in[1]};
+            const Vec3 c = GetColor(s->textures + id, uv);
+            OUT3(out, c);
+            break;
+        }
+        default: return -1;
+        }
+#undef IN3
+#undef OUT3
+        memcpy(out + B200PT_EVAL_OUT - 1, &seed, 4);
+    }
+    return 0;
+}
+
+/* struct ref_hit of oracle/ref_glue.cpp */
+typedef struct {
+    float t;
+    uint32_t valid, inside, id_instance, id_primitive;
+    float position[3], normal[3], texcoord[2], tangent[3], bitangent[3];
+} OracleHit;
+
+/* TlasIntersect / TlasIntersectAny with the scene's BSDFs (bump maps, opacity masks drawing from `seed` = 0 per ray). */
+int oracle_trace(void *handle, uint64_t n, const float *rays, int any_hit, OracleHit *out) {
+    const Scene *s = &((OracleScene *)handle)->scene;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *q = rays + 8 * i;
+        Ray ray = MakeRay(s, v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]));
+        ray.t_min = q[6], ray.t_max = q[7];
+        uint32_t seed = 0;
+        OracleHit h;
+        memset(&h, 0, sizeof(h));
+        if (any_hit) {
+            h.valid = (uint32_t)TlasIntersectAny(s, &seed, &ray);
+            h.t = ray.t_max;
+        } else {
+            const Hit hit = TlasIntersect(s, &seed, &ray);
+            h.t = ray.t_max;
+            h.valid = (uint32_t)hit.valid, h.inside = (uint32_t)hit.inside, h.id_instance = hit.id_instance, h.id_primitive = hit.id_primitve;
+            h.position[0] = hit.position.x, h.position[1] = hit.position.y, h.position[2] = hit.position.z;
+            h.normal[0] = hit.normal.x, h.normal[1] = hit.normal.y, h.normal[2] = hit.normal.z;
+            h.texcoord[0] = hit.texcoord.u, h.texcoord[1] = hit.texcoord.v;
+            h.tangent[0] = hit.tangent.x, h.tangent[1] = hit.tangent.y, h.tangent[2] = hit.tangent.z;
+            h.bitangent[0] = hit.bitangent.x, h.bitangent[1] = hit.bitangent.y, h.bitangent[2] = hit.bitangent.z;
+        }
+        out[i] = h;
+    }
     return 0;
 }

@@ -17,9 +17,29 @@
 #include <memory>
 #include <string>
 
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <exception>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <set>
+#include <sstream>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+// The pointwise checks (ref_eval) call Bsdf / Emitter / Medium / Texture objects exactly as csrt::Renderer built them; the
+// renderer keeps them private, so THIS translation unit (test infrastructure, nothing else) reads the class with its
+// members public.  The reference sources themselves are compiled unmodified; the class layout does not change.
+#define private public
+#include "csrt/renderer/renderer.hpp"
+#undef private
 #include "csrt/parser/parser.hpp"
 #include "csrt/renderer/bsdfs/kulla_conty.hpp"
-#include "csrt/renderer/renderer.hpp"
 #include "csrt/rtcore/accel/bvh_builder.hpp"
 #include "csrt/rtcore/scene.hpp"
 
@@ -251,7 +271,7 @@ struct RefScene {
 struct ref_hit {
     float t;             // ray.t_max after the call
     uint32_t valid, inside, id_instance, id_primitive;
-    float position[3], normal[3], texcoord[2];
+    float position[3], normal[3], texcoord[2], tangent[3], bitangent[3];
 };
 
 void *ref_scene_create(const b200pt_scene_desc *desc) {
@@ -290,7 +310,125 @@ int ref_trace(void *handle, uint64_t n, const float *rays, int any_hit, ref_hit 
                 h.position[0] = hit.position.x, h.position[1] = hit.position.y, h.position[2] = hit.position.z;
                 h.normal[0] = hit.normal.x, h.normal[1] = hit.normal.y, h.normal[2] = hit.normal.z;
                 h.texcoord[0] = hit.texcoord.u, h.texcoord[1] = hit.texcoord.v;
+                h.tangent[0] = hit.tangent.x, h.tangent[1] = hit.tangent.y, h.tangent[2] = hit.tangent.z;
+                h.bitangent[0] = hit.bitangent.x, h.bitangent[1] = hit.bitangent.y, h.bitangent[2] = hit.bitangent.z;
             }
+            out[i] = h;
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// ---- pointwise leaf functions: the Bsdf / Emitter / Medium / Texture objects of a csrt::Renderer (as ref_create builds it)
+// at caller-supplied inputs.  Same record layout as b200pt_debug_eval (include/b200pt.h): n x 32 floats in, n x 16 floats out. ----
+int ref_eval(void *renderer_handle, uint32_t what, uint32_t id, uint64_t n, const float *in_all, float *out_all) {
+    try {
+        const csrt::Renderer *r = static_cast<const csrt::Renderer *>(renderer_handle);
+        auto in3 = [](const float *p) { return csrt::Vec3(p[0], p[1], p[2]); };
+        auto out3 = [](float *p, const csrt::Vec3 &v) { p[0] = v.x, p[1] = v.y, p[2] = v.z; };
+        for (uint64_t i = 0; i < n; ++i) {
+            const float *in = in_all + i * B200PT_EVAL_IN;
+            float *out = out_all + i * B200PT_EVAL_OUT;
+            memset(out, 0, sizeof(float) * B200PT_EVAL_OUT);
+            uint32_t seed;
+            memcpy(&seed, in + 18, 4);
+            switch (what) {
+            case B200PT_EVAL_BSDF_EVALUATE:
+            case B200PT_EVAL_BSDF_SAMPLE: {
+                csrt::BsdfSampleRec rec;
+                rec.wi = in3(in), rec.wo = in3(in + 3), rec.normal = in3(in + 6), rec.tangent = in3(in + 9), rec.bitangent = in3(in + 12);
+                rec.texcoord = csrt::Vec2(in[15], in[16]);
+                rec.inside = in[17] != 0.0f;
+                if (what == B200PT_EVAL_BSDF_EVALUATE)
+                    r->bsdfs_[id].Evaluate(&rec);
+                else
+                    r->bsdfs_[id].Sample(&seed, &rec);
+                out[0] = rec.valid, out[1] = rec.pdf;
+                out3(out + 2, rec.attenuation), out3(out + 5, rec.wi);
+                break;
+            }
+            case B200PT_EVAL_EMITTER_SAMPLE: {
+                const csrt::Emitter &e = r->emitters_[id];
+                const csrt::EmitterSampleRec rec = e.Sample(in3(in), in[3], in[4]);
+                out[0] = rec.valid, out[1] = rec.harsh, out[2] = rec.distance;
+                out3(out + 3, rec.wi);
+                if (rec.valid) {
+                    out3(out + 6, e.Evaluate(rec));
+                    out[9] = e.Pdf(-rec.wi);
+                }
+                break;
+            }
+            case B200PT_EVAL_EMITTER_DIR: {
+                const csrt::Emitter &e = r->emitters_[id];
+                out3(out, e.Evaluate(in3(in)));
+                out[3] = e.Pdf(in3(in));
+                break;
+            }
+            case B200PT_EVAL_MEDIUM_SAMPLE:
+            case B200PT_EVAL_MEDIUM_EVALUATE: {
+                csrt::MediumSampleRec rec;
+                if (what == B200PT_EVAL_MEDIUM_SAMPLE) {
+                    r->media_[id].Sample(in[0], &seed, &rec);
+                } else {
+                    rec.distance = in[0];
+                    r->media_[id].Evaluate(&rec);
+                }
+                out[0] = rec.valid, out[1] = rec.scattered, out[2] = rec.pdf, out[3] = rec.distance;
+                out3(out + 4, rec.attenuation);
+                break;
+            }
+            case B200PT_EVAL_PHASE_SAMPLE:
+            case B200PT_EVAL_PHASE_EVALUATE: {
+                csrt::PhaseSampleRec rec;
+                rec.wi = in3(in), rec.wo = in3(in + 3);
+                if (what == B200PT_EVAL_PHASE_SAMPLE)
+                    r->media_[id].SamplePhase(&seed, &rec);
+                else
+                    r->media_[id].EvaluatePhase(&rec);
+                out[0] = rec.valid, out[1] = rec.pdf;
+                out3(out + 2, rec.attenuation), out3(out + 5, rec.wi);
+                break;
+            }
+            case B200PT_EVAL_TEXTURE: {
+                out3(out, r->textures_[id].GetColor(csrt::Vec2(in[0], in[1])));
+                break;
+            }
+            default:
+                g_error = "ref_eval: unknown function";
+                return -1;
+            }
+            memcpy(out + B200PT_EVAL_OUT - 1, &seed, 4);
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// Instance ids with their BSDF, through the renderer's own scene: closest hit with the hit frame as Primitive::Intersect
+// builds it (bump mapping included), for B200PT_EVAL_SURFACE.
+int ref_trace_renderer(void *renderer_handle, uint64_t n, const float *rays, ref_hit *out) {
+    try {
+        const csrt::Renderer *r = static_cast<const csrt::Renderer *>(renderer_handle);
+        const csrt::TLAS *tlas = r->scene_->GetTlas();
+        for (uint64_t i = 0; i < n; ++i) {
+            const float *q = rays + 8 * i;
+            csrt::Ray ray(csrt::Vec3(q[0], q[1], q[2]), csrt::Vec3(q[3], q[4], q[5]));
+            ray.t_min = q[6], ray.t_max = q[7];
+            uint32_t seed = 0;
+            const csrt::Hit hit = tlas->Intersect(r->bsdfs_, r->map_instance_bsdf_, &seed, &ray);
+            ref_hit h{};
+            h.t = ray.t_max;
+            h.valid = hit.valid, h.inside = hit.inside, h.id_instance = hit.id_instance, h.id_primitive = hit.id_primitve;
+            h.position[0] = hit.position.x, h.position[1] = hit.position.y, h.position[2] = hit.position.z;
+            h.normal[0] = hit.normal.x, h.normal[1] = hit.normal.y, h.normal[2] = hit.normal.z;
+            h.texcoord[0] = hit.texcoord.u, h.texcoord[1] = hit.texcoord.v;
+            h.tangent[0] = hit.tangent.x, h.tangent[1] = hit.tangent.y, h.tangent[2] = hit.tangent.z;
+            h.bitangent[0] = hit.bitangent.x, h.bitangent[1] = hit.bitangent.y, h.bitangent[2] = hit.bitangent.z;
             out[i] = h;
         }
         return 0;

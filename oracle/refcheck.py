@@ -78,7 +78,7 @@ class RefHit(ctypes.Structure):
     """struct ref_hit of oracle/ref_glue.cpp."""
     _fields_ = [("t", ctypes.c_float), ("valid", ctypes.c_uint32), ("inside", ctypes.c_uint32), ("id_instance", ctypes.c_uint32),
                 ("id_primitive", ctypes.c_uint32), ("position", ctypes.c_float * 3), ("normal", ctypes.c_float * 3),
-                ("texcoord", ctypes.c_float * 2)]
+                ("texcoord", ctypes.c_float * 2), ("tangent", ctypes.c_float * 3), ("bitangent", ctypes.c_float * 3)]
 
 
 class RefTracer:
@@ -144,6 +144,10 @@ class OracleLib:
         L.oracle_build_bvh.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
         L.oracle_build_bvh.restype = ctypes.c_uint32
 
+    def scene(self, pack_path, watertight=True):
+        """A committed oracle scene for the pointwise entries (oracle_eval / oracle_trace)."""
+        return OracleScene(self, pack_path, watertight)
+
     def render_pack(self, pack_path, width=0, height=0, spp=0, watertight=True, threads=None):
         """Loads the pack with the product's pack reader (data I/O only) and renders it with the C restatement."""
         loader = _pack_loader()
@@ -179,6 +183,49 @@ class OracleLib:
             return frame, srgb
         finally:
             loader.b200pt_scene_free(scene)
+
+
+class OracleScene:
+    """oracle_scene_create + oracle_eval / oracle_trace: the C restatement's leaf functions at caller-supplied inputs."""
+
+    def __init__(self, oracle, pack_path, watertight=True):
+        self.lib = oracle.lib
+        L = self.lib
+        L.oracle_scene_create.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.oracle_scene_create.restype = ctypes.c_void_p
+        L.oracle_scene_destroy.argtypes = [ctypes.c_void_p]
+        L.oracle_scene_destroy.restype = None
+        L.oracle_eval.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_trace.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        self.loader = _pack_loader()
+        self.pack = ctypes.c_void_p()
+        if self.loader.b200pt_scene_load(pack_path.encode(), ctypes.byref(self.pack)) != 0:
+            raise RuntimeError(f"cannot load {pack_path}")
+        self.handle = L.oracle_scene_create(self.loader.b200pt_scene_get_desc(self.pack), 1 if watertight else 0)
+        if not self.handle:
+            raise RuntimeError("oracle_scene_create failed")
+
+    def eval(self, what, index, inputs):
+        inputs = np.ascontiguousarray(inputs, dtype=np.float32).reshape(-1, 32)
+        out = np.zeros((len(inputs), 16), dtype=np.float32)
+        if self.lib.oracle_eval(self.handle, what, index, len(inputs), inputs.ctypes.data, out.ctypes.data) != 0:
+            raise RuntimeError("oracle_eval failed")
+        return out
+
+    def trace(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        out = (RefHit * len(rays))()
+        if self.lib.oracle_trace(self.handle, len(rays), rays.ctypes.data, 1 if any_hit else 0, out) != 0:
+            raise RuntimeError("oracle_trace failed")
+        return np.ctypeslib.as_array(out).copy()
+
+    def close(self):
+        if self.handle:
+            self.lib.oracle_scene_destroy(self.handle)
+            self.handle = None
+        if self.pack:
+            self.loader.b200pt_scene_free(self.pack)
+            self.pack = ctypes.c_void_p()
 
 
 _PACK_LOADER = None
@@ -221,6 +268,27 @@ class RefRenderer:
             raise RuntimeError(ref.error())
         self.build_seconds = b.value
         self.frame = np.zeros((self.height, self.width, 3), dtype=np.float32)
+
+    def eval(self, what, index, inputs):
+        """ref_eval (oracle/ref_glue.cpp): the renderer's own Bsdf / Emitter / Medium / Texture objects at fixed inputs;
+        inputs float32 [n, 32] -> float32 [n, 16], layouts as b200pt_debug_eval (include/b200pt.h)."""
+        L = self.ref.lib
+        L.ref_eval.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+        inputs = np.ascontiguousarray(inputs, dtype=np.float32).reshape(-1, 32)
+        out = np.zeros((len(inputs), 16), dtype=np.float32)
+        if L.ref_eval(self.handle, what, index, len(inputs), inputs.ctypes.data, out.ctypes.data) != 0:
+            raise RuntimeError(self.ref.error())
+        return out
+
+    def trace(self, rays):
+        """Closest hits through the renderer's scene WITH its BSDFs (bump-mapped hit frames): record array of RefHit."""
+        L = self.ref.lib
+        L.ref_trace_renderer.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        out = (RefHit * len(rays))()
+        if L.ref_trace_renderer(self.handle, len(rays), rays.ctypes.data, out) != 0:
+            raise RuntimeError(self.ref.error())
+        return np.ctypeslib.as_array(out).copy()
 
     def draw(self):
         seconds = self.ref.lib.ref_draw(self.handle, self.frame.ctypes.data)

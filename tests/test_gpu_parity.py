@@ -156,7 +156,7 @@ def test_tail_kernel_is_bit_exact(pkg, scene, w, h, spp, monkeypatch):
         st = r.stats()
         assert (st["tail"]["launches"] > 0) == (paths != "0")
         r.close()
-    if scene in ("synthetic_opacity_masks", "synthetic_early_rr"):
+    if scene in ("synthetic_opacity_masks", "synthetic_early_rr", "synthetic_depth_max_below_rr"):
         # two emitters: the two NEE contributions of a vertex are added by atomics in either order in the wavefront path
         assert np.allclose(frames["0"], frames["4096"], rtol=0, atol=1e-6) and np.allclose(frames["0"], frames["16777216"], rtol=0, atol=1e-6)
     else:
