@@ -508,7 +508,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         }
         const uint32_t depth = run.depth;
         auto finish_batch = [&] {
-            launch(kClassOther, [&] { LaunchSettle(la, ar.counters, -1, true, ar.shadow, ar.radiance, capacity); }); // NEE of the last bounce
+            launch(kClassOther, [&] { LaunchSettle(la, ar.counters, -1, true, ar.shadow, ar.radiance, capacity, c->shadow_per_vertex <= 1); }); // NEE of the last bounce
             launch(kClassOther, [&] { LaunchResolve(la, run.bp, ar.radiance, capacity, c->accum.ptr); });
             run.in_batch = false;
             run.sample_begin += run.bp.sample_count;
@@ -521,7 +521,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         // every remaining path in this one launch and the per-bounce kernels below find nothing to do.
         // Settle first: the NEE contributions of the previous bounce are added before anything of this bounce, whichever
         // kernel handles it (the order of float additions per sample is then the same with and without the tail kernel).
-        if (depth > 1) launch(kClassOther, [&] { LaunchSettle(la, ar.counters, run.which ^ 1, true, ar.shadow, ar.radiance, capacity); });
+        if (depth > 1) launch(kClassOther, [&] { LaunchSettle(la, ar.counters, run.which ^ 1, true, ar.shadow, ar.radiance, capacity, c->shadow_per_vertex <= 1); });
         if (depth > 1 && c->tail_paths > 0)
             launch(kClassTail, [&] { LaunchTail(la, c->scene, run.bp, depth, ar.queue[run.which], run.which, ar.radiance, capacity, ar.counters, c->tail_paths); });
         launch(kClassShade, [&] {

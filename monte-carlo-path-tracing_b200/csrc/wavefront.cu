@@ -295,15 +295,24 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_debug_trace
 // k_settle: between two bounces.  Adds the contributions of the NEE rays the last k_trace found unoccluded (marked in place,
 // see k_trace) to their samples — a coalesced pass over the shadow queue — and then, in the last CTA to finish, resets the
 // queue lengths and work counters for the next bounce (what a one-thread launch did before).
+// UNIQUE: the scene sends one NEE ray per vertex, so no two entries of the queue share a sample slot: plain read-modify-write
+// (atomics serialise in the L2: volumetric-caustic spent 51 ms per frame on them).  Otherwise the NEE rays of one vertex (one
+// per emitter + one for the area lights) meet in one slot and are added atomically.
+template <bool UNIQUE>
 __global__ void __launch_bounds__(kThreads) k_settle(Counters *c, int which_queue, bool reset_shadow, ShadowQueue sq, float *radiance, uint32_t capacity) {
     const uint32_t n = c->shadow;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         if (sq.tmax[j] != kShadowUnoccluded) continue;
         const uint32_t slot = sq.slot[j];
-        // several NEE rays of one vertex (one per emitter) may share the slot: atomics; with one emitter the sum has one order
-        atomicAdd(radiance + slot, sq.cr[j]);
-        atomicAdd(radiance + capacity + slot, sq.cg[j]);
-        atomicAdd(radiance + 2 * capacity + slot, sq.cb[j]);
+        if (UNIQUE) {
+            radiance[slot] += sq.cr[j];
+            radiance[capacity + slot] += sq.cg[j];
+            radiance[2 * capacity + slot] += sq.cb[j];
+        } else {
+            atomicAdd(radiance + slot, sq.cr[j]);
+            atomicAdd(radiance + capacity + slot, sq.cg[j]);
+            atomicAdd(radiance + 2 * capacity + slot, sq.cb[j]);
+        }
     }
     __shared__ bool last;
     __syncthreads();
@@ -579,8 +588,11 @@ void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const Bat
 }
 
 void LaunchSettle(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow, ShadowQueue sq, float *radiance,
-                  uint32_t capacity) {
-    k_settle<<<lc.blocks, kThreads, 0, lc.stream>>>(counters, which_queue, reset_shadow, sq, radiance, capacity);
+                  uint32_t capacity, bool unique_slots) {
+    if (unique_slots)
+        k_settle<true><<<lc.blocks, kThreads, 0, lc.stream>>>(counters, which_queue, reset_shadow, sq, radiance, capacity);
+    else
+        k_settle<false><<<lc.blocks, kThreads, 0, lc.stream>>>(counters, which_queue, reset_shadow, sq, radiance, capacity);
 }
 
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum) {

@@ -160,8 +160,9 @@ void LaunchDebugEval(cudaStream_t stream, const DeviceScene &scene, uint32_t wha
 constexpr uint32_t kMaxTailDepth = 4096; // = kMaxRounds of the host loop
 // Adds the contributions of the shadow rays the last k_trace marked unoccluded, then resets queue `which_queue` (>= 0), the
 // shadow queue (reset_shadow) and the traversal work counter for the next bounce.
+// unique_slots: at most one NEE ray per vertex (plain adds instead of atomics).
 void LaunchSettle(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow, ShadowQueue sq, float *radiance,
-                  uint32_t capacity);
+                  uint32_t capacity, bool unique_slots);
 constexpr float kShadowUnoccluded = -1.0f; // written over ShadowQueue::tmax by k_trace (a real tmax is never negative)
 void LaunchResolve(const LaunchConfig &lc, const BatchParams &bp, const float *radiance, uint32_t capacity, float *accum);
 void LaunchFinalize(const LaunchConfig &lc, const BatchParams &bp, uint32_t num_local_pixels, const float *accum,

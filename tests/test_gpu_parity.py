@@ -285,6 +285,72 @@ def test_progressive_preview_entry(pkg, oracle):
     assert abs(a.mean() / golden.mean() - 1.0) < 0.02
 
 
+def test_progressive_preview_pinned_on_the_reference_cuda_build(pkg, oracle):
+    """The only place the reference runs its preview body Renderer::Draw(index_frame, frame, frame_srgb) (renderer.cpp:97-138)
+    is its CUDA backend: oracle/_ref/libcsrt_ref_cuda.so is that backend, unmodified, rebuilt for sm_100a.  Pins, after 64
+    accumulated frames of Cornell 64x64: (1) the C restatement oracle_render_progressive — same per-pixel LCG streams, the two
+    differ only by nvcc-vs-gcc float contraction and argument-evaluation order, the very way the reference's CUDA and CPU backends
+    differ from EACH OTHER on a still frame (tools/ref_cuda_vs_cpu.py: mean ratio 1.0022); (2) b200pt_render_progressive_device."""
+    import ctypes
+    import torch
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libcsrt_ref_cuda.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libcsrt_ref_cuda.so not built (needs /root/reference at build time)")
+    L = ctypes.CDLL(path)
+    L.ref_create_cuda.restype = ctypes.c_void_p
+    L.ref_create_cuda.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    L.ref_draw_progressive_cuda.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+    L.ref_destroy_cuda.argtypes = [ctypes.c_void_p]
+    L.ref_last_error.restype = ctypes.c_char_p
+    w = h = 64
+    frames = 64
+    scene = pkg.Scene(pack("cornell-box"))
+    handle = L.ref_create_cuda(scene.desc, w, h, 1, None)
+    assert handle, L.ref_last_error().decode(errors="replace")
+    ref, ref_srgb = np.zeros((h, w, 3), np.float32), np.zeros((h, w, 3), np.float32)
+    assert L.ref_draw_progressive_cuda(handle, frames, ref.ctypes.data, ref_srgb.ctypes.data) == 0, L.ref_last_error().decode(errors="replace")
+    L.ref_destroy_cuda(handle)
+    port, port_srgb = oracle.render_progressive(pack("cornell-box"), w, h, frames)
+    # (1) restatement vs the reference's own code: same sample positions, same streams
+    assert abs(port.mean() / ref.mean() - 1.0) < 0.006, (port.mean(), ref.mean())
+    assert rel_l2(boxed(port), boxed(ref)) < 0.03 and rel_l2(boxed(port_srgb[::-1]), boxed(ref_srgb[::-1])) < 0.03
+    # (2) the product entry vs the reference's own code
+    r = renderer(pkg, "cornell-box")
+    frame, frame2 = torch.zeros(h * w * 3, dtype=torch.float32, device="cuda"), torch.zeros(h * w * 3, dtype=torch.float32, device="cuda")
+    for k in range(frames):
+        r.draw_progressive_device(frame, None, k, width=w, height=h, seed=5)
+        r.draw_progressive_device(frame2, None, k, width=w, height=h, seed=6)
+    torch.cuda.synchronize()
+    a, b = frame.cpu().numpy().reshape(h, w, 3), frame2.cpu().numpy().reshape(h, w, 3)
+    floor_box = rel_l2(boxed(a), boxed(b))
+    assert abs(a.mean() / ref.mean() - 1.0) < 0.015, (a.mean(), ref.mean())
+    assert rel_l2(boxed(a), boxed(ref)) <= 2.0 * floor_box + 0.005, (rel_l2(boxed(a), boxed(ref)), floor_box)
+
+
+@pytest.mark.parametrize("scene", ["dragon", "matpreview", "volumetric-caustic"])
+def test_full_size_configs_match_reference_frames(pkg, scene):
+    """BASELINE configs C2 / C3 / C4 at their own resolution (1024x1024), PER PIXEL, against frames of the unmodified reference
+    (tests/golden/fullsize_*.npz, made by make_fullsize_golden.py): C2 at its own 256 spp, C3 / C4 at 64 spp on both sides
+    (sample positions depend on spp, renderer.cpp:70).  Tolerances as everywhere: mean within 0.5 %, 8x8-box rel-L2 within
+    2 x the seed-to-seed floor + 0.5 %, per-pixel rel-L2 within 1.5 x the floor + 0.5 %."""
+    g = np.load(os.path.join(GOLDEN, f"fullsize_{scene}.npz"))
+    golden = g["frame"].astype(np.float32)
+    w, h, spp = (int(x) for x in g["size"])
+    r = pkg.Renderer(pkg.Scene(pack(scene)), device=0)   # default capacity: the configuration bench.py measures
+    a = r.Draw(width=w, height=h, spp=spp, seed=31)
+    b = r.Draw(width=w, height=h, spp=spp, seed=32)
+    r.close()
+    assert np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 1.0 + 1e-6
+    floor_pixel, floor_box = rel_l2(a, b), rel_l2(boxed(a), boxed(b))
+    assert abs(a.mean() / golden.mean() - 1.0) < 0.005, (scene, a.mean(), golden.mean())
+    assert rel_l2(boxed(a), boxed(golden)) <= 2.0 * floor_box + 0.005, (scene, rel_l2(boxed(a), boxed(golden)), floor_box)
+    assert rel_l2(a, golden) <= 1.5 * floor_pixel + 0.005, (scene, rel_l2(a, golden), floor_pixel)
+    # where the picture is black in the reference it is black here (coverage, per pixel)
+    if scene == "dragon":
+        lit_ref, lit = golden.max(axis=2) > 0, a.max(axis=2) > 0
+        assert (lit_ref != lit).mean() < 2e-3
+
+
 def test_gpu_lbvh_builder_renders_the_same_scene(pkg):
     """B200PT_CREATE_GPU_LBVH: the tree built on the GPU (Morton sort + Karras radix tree + refit) finds the same closest
     hits as the host SAH tree: identical coverage, statistically identical radiance (a hit exactly on a shared edge may pick
