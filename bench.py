@@ -35,8 +35,13 @@ WORKLOADS = {
     "dragon-1080p-4096spp": ("dragon", 1920, 1080, 4096, "resources/scene/dragon/scene.xml 1920x1080 4096spp (BASELINE configs[4])"),
     "matpreview-1024-512spp": ("matpreview", 1024, 1024, 512, "resources/scene/matpreview/rough_conductor.xml 1024x1024 512spp (configs[2])"),
     "volumetric-1024-2048spp": ("volumetric-caustic", 1024, 1024, 2048, "resources/scene/volumetric-caustic/scene_v0.6.xml 1024x1024 2048spp (configs[3])"),
+    "mercury-256-32spp": ("mercury", 256, 256, 32, "resources/scene/mercury/smooth_diffuse.xml 256x256 32spp (BASELINE configs[0])"),
     "cornell-256-64spp": ("cornell-box", 256, 256, 64, "resources/scene/cornell-box/scene_v0.6.xml 256x256 64spp (smoke)"),
 }
+# (label, workload, timed steps, golden) measured after the headline: N=1 runs the single-GPU configs and C5, N>1 runs C5
+OTHER_CONFIGS_N1 = [("C1", "mercury-256-32spp", 5, "fullsize_mercury.npz"), ("C3", "matpreview-1024-512spp", 3, "fullsize_matpreview.npz"),
+                    ("C4", "volumetric-1024-2048spp", 2, "fullsize_volumetric-caustic.npz"), ("C5", "dragon-1080p-4096spp", 2, "fullsize_dragon-1080p.npz")]
+OTHER_CONFIGS_MULTI = [("C5", "dragon-1080p-4096spp", 3, "fullsize_dragon-1080p.npz")]
 METRIC = "Msamples/sec at 1024^2 256spp (Dragon), 1/2/4/8 B200; per-pixel rel-L2 vs --cpu ref"
 # bytes a cache-less traversal must move per unit of work
 BYTES_PER_NODE_VISIT, BYTES_PER_PRIM_TEST, BYTES_PER_CLOSEST_RAY = 32, 36, 52
@@ -103,15 +108,27 @@ def measured_peak():
 
 
 def cpu_baseline(pack, width, height, spp_sample, spp_full):
-    """The reference's CPU renderer on this box, bounded sample: `spp_sample` of the workload's spp."""
+    """The reference's CPU renderer on this box, bounded sample: `spp_sample` of the workload's spp.  Both builds of the same
+    unmodified sources: the stock one (CMake Release flags) is `value`, the x86-64-v3 unity build ("the fairer
+    comparator") is `fast_build`."""
     import refcheck
-    ref = refcheck.ref_lib("woop")
-    r = refcheck.RefRenderer(ref, pack, width, height, spp_sample)
-    seconds = r.draw()
-    r.close()
-    return {"value": width * height * spp_sample / seconds / 1e6, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference",
-            "sample": f"{width}x{height} at {spp_sample} of {spp_full} spp, one csrt::Renderer::Draw, {seconds:.2f} s "
-                      f"(scene commit {r.build_seconds:.1f} s excluded)"}
+    out = None
+    for variant in ("woop", "fast"):
+        if variant == "fast" and not fast_build_usable():
+            continue
+        r = refcheck.RefRenderer(refcheck.ref_lib(variant), pack, width, height, spp_sample)
+        seconds = r.draw()
+        r.close()
+        rec = {"value": width * height * spp_sample / seconds / 1e6, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference",
+               "sample": f"{width}x{height} at {spp_sample} of {spp_full} spp, one csrt::Renderer::Draw, {seconds:.2f} s "
+                         f"(scene commit {r.build_seconds:.1f} s excluded)"}
+        if variant == "woop":
+            rec["build"] = "g++ -O3 -DNDEBUG (CMake Release), -DWATERTIGHT_TRIANGLES"
+            out = rec
+        else:
+            out["fast_build"] = {"value": rec["value"], "unit": "Msamples/s", "sample": rec["sample"],
+                                 "build": "-O3 -march=x86-64-v3, hot-path sources as one translation unit (oracle/Makefile FAST_OPT)"}
+    return out
 
 
 def reference_gpu_baseline(pack, width, height, spp_sample, spp_full):
@@ -144,7 +161,29 @@ def reference_gpu_baseline(pack, width, height, spp_sample, spp_full):
             "sample": f"{width}x{height} at {spp_sample} of {spp_full} spp, csrt::Renderer::Draw on BackendType::kCuda, best of 2: {min(times):.3f} s"}
 
 
+def host_threads_note():
+    return f"{os.cpu_count()} host threads"
+
+
+def fast_build_usable():
+    """libcsrt_ref_fast.so is compiled for x86-64-v3 (AVX2 + FMA): only load it on a host that has them."""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+    return all(f" {x}" in flags for x in ("avx2", "fma", "bmi2")) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcsrt_ref_fast.so"))
+
+
+def shared_config(desc, width, height, spp):
+    """The part of `config` both arms print identically: the workload both measure."""
+    return {"workload": desc, "width": width, "height": height, "spp": spp,
+            "l2": "b200 arm: 256 MB buffer written between timed steps (L2 flush), and scene + wavefront state exceed the 126 MB L2; reference arm: CPU"}
+
+
 def run_reference(args, workload):
+    """The reference's own CPU renderer (unmodified sources, oracle/_ref), all host threads, bounded spp sample per step.
+    `value` comes from the stock build (CMake Release flags, -O3); the x86-64-v3 unity build of the same sources (BASELINE.md §3.1:
+    "the fairer comparator") is timed beside it and reported in cpu_baseline.fast_build."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -162,16 +201,203 @@ def run_reference(args, workload):
     r.close()
     samples = width * height * REF_SPP_PER_STEP
     value = samples * args.steps / sum(t) / 1e6
+    fast = None
+    if fast_build_usable():
+        try:
+            rf = refcheck.RefRenderer(refcheck.ref_lib("fast"), pack_path(name), width, height, REF_SPP_PER_STEP)
+            rf.draw()
+            tf = [rf.draw() for _ in range(min(3, args.steps))]
+            rf.close()
+            fast = {"value": samples * len(tf) / sum(tf) / 1e6, "unit": "Msamples/s", "build": "-O3 -march=x86-64-v3, hot-path sources as one translation unit (oracle/Makefile FAST_OPT)"}
+        except Exception as e:
+            fast = {"value": None, "note": f"unavailable: {e}"}
     sample = (f"each step = {width}x{height} at {REF_SPP_PER_STEP} of {spp} spp through csrt::Renderer::Draw "
-              f"(renderer.cpp:678), {os.cpu_count()} host threads; scene commit {r.build_seconds:.1f} s excluded")
+              f"(renderer.cpp:678), {host_threads_note()}; scene commit {r.build_seconds:.1f} s excluded; throughput is linear in spp")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(t) / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "reference scene (Dragon), parsed by the reference's XML parser",
-        "config": {"workload": desc, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": sample},
+        "config": shared_config(desc, width, height, spp),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": sample,
+                         "build": "g++ -O3 -DNDEBUG (CMake Release), -DWATERTIGHT_TRIANGLES", "fast_build": fast},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def rel_l2(a, b):
+    import numpy as np
+    return float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)))
+
+
+def boxed(f, box=8):
+    h, w = f.shape[:2]
+    return f[: h // box * box, : w // box * box].reshape(h // box, box, w // box, box, 3).mean(axis=(1, 3))
+
+
+class Job:
+    """One workload on this rank: renderer + the buffers of a step (a frame for N=1; tiles + gather + assemble for N>1)."""
+
+    def __init__(self, pkg, pack, width, height, world, rank, local_rank):
+        import torch
+        self.pkg, self.torch, self.width, self.height, self.world, self.rank = pkg, torch, width, height, world, rank
+        self.scene = pkg.Scene(pack)
+        t0 = time.time()
+        self.renderer = pkg.Renderer(self.scene, device=local_rank)
+        self.create_s = time.time() - t0
+        self.stream = torch.cuda.current_stream()
+        self.frame = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")
+        n = pkg.tile_buffer_floats(width, height, world)
+        self.tiles = torch.zeros(n, dtype=torch.float32, device="cuda") if world > 1 else None
+        self.gathered = torch.zeros(n * world, dtype=torch.float32, device="cuda") if world > 1 else None
+
+    def step(self, spp, seed=1, stats=0, flags=0):
+        """One full frame, result left in HBM (on rank 0 for N>1)."""
+        r, s = self.renderer, self.stream.cuda_stream
+        if self.world == 1:
+            r.draw_device(self.frame, self.width, self.height, spp, seed=seed, stream=s, stats=stats, flags=flags)
+        else:
+            import torch.distributed as dist
+            r.draw_tiles_device(self.tiles, self.rank, self.world, self.width, self.height, spp, seed=seed, stream=s, stats=stats)
+            dist.all_gather_into_tensor(self.gathered, self.tiles)
+            if self.rank == 0:
+                r.assemble_tiles_device(self.gathered, self.frame, self.width, self.height, self.world, stream=s)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed_steps(self, spp, steps, flush):
+        """CUDA events on the launching stream around each step, barrier + synchronize on both sides, L2 flushed in between;
+        returns the total over the steps, max over ranks."""
+        torch = self.torch
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            self.step(spp)
+            e1.record(self.stream)
+            self.barrier()
+            ms.append(e0.elapsed_time(e1))
+        total = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item())
+
+    def frame_host(self):
+        return self.frame.cpu().numpy().reshape(self.height, self.width, 3)
+
+    def parity(self, golden_file):
+        """Frame of this job vs a frame of the UNMODIFIED reference CPU renderer at the same size and spp (tests/golden/fullsize_*.npz,
+        made by tests/golden/make_fullsize_golden.py): whole-image mean ratio, per-pixel and 8x8-box rel-L2, and the same two between
+        two of our own seeds (the Monte Carlo noise floor the comparison cannot go below)."""
+        import numpy as np
+        path = os.path.join(ROOT, "tests", "golden", golden_file)
+        if not os.path.exists(path):
+            return None
+        g = np.load(path)
+        golden = g["frame"].astype(np.float32)
+        w, h, spp = (int(x) for x in g["size"])
+        if (w, h) != (self.width, self.height):
+            return None
+        self.step(spp, seed=31)
+        self.barrier()
+        a = self.frame_host() if self.rank == 0 else None
+        self.step(spp, seed=32)
+        self.barrier()
+        if self.rank != 0:
+            return None
+        b = self.frame_host()
+        return {"against": f"tests/golden/{golden_file}: csrt::Renderer::Draw (reference CPU build), {w}x{h} at {spp} spp on both sides",
+                "mean_ratio": float(a.mean() / golden.mean()), "rel_l2_pixel": rel_l2(a, golden), "rel_l2_box8": rel_l2(boxed(a), boxed(golden)),
+                "noise_floor_pixel": rel_l2(a, b), "noise_floor_box8": rel_l2(boxed(a), boxed(b)),
+                "tolerance": "mean within 0.5 %, box8 <= 2 x floor + 0.5 %, pixel <= 1.5 x floor + 0.5 % (tests/test_gpu_parity.py)"}
+
+    def kernel_split(self, spp):
+        """Per-kernel-class CUDA-event times of one extra step (B200PT_STATS_TIMING renders with ONE arena so that launches are
+        serial), and the traversal counters of another."""
+        self.step(spp, stats=self.pkg.STATS_COUNTERS)
+        self.barrier()
+        counted = self.renderer.stats()
+        self.step(spp, stats=self.pkg.STATS_TIMING)
+        self.barrier()
+        return counted, self.renderer.stats()
+
+    def close(self):
+        self.renderer.close()
+        self.frame = self.tiles = self.gathered = None
+        self.torch.cuda.empty_cache()
+
+
+def algorithmic_bytes(c, closest):
+    return (BYTES_PER_NODE_VISIT * c["node_visits"] + BYTES_PER_PRIM_TEST * c["prim_tests"]
+            + (BYTES_PER_CLOSEST_RAY * c["rays"] if closest else 0))
+
+
+def gbps(nbytes, ms):
+    return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+
+
+def kernel_table(counted, timed):
+    # k_primary traces the camera rays; k_trace traces, in ONE launch per bounce, the bounce rays (closest hit, counted
+    # under "extend") and the NEE rays (any hit, counted under "shadow"); its time is reported under "extend".
+    alg_primary = algorithmic_bytes(counted["primary"], True)
+    alg_trace = algorithmic_bytes(counted["extend"], True) + algorithmic_bytes(counted["shadow"], False)
+    return {
+        "primary": {"ms": timed["primary"]["ms"], "launches": timed["primary"]["launches"], "rays": counted["primary"]["rays"],
+                    "algorithmic_bytes": alg_primary, "GBps": gbps(alg_primary, timed["primary"]["ms"])},
+        "trace": {"ms": timed["extend"]["ms"], "launches": timed["extend"]["launches"], "closest_hit_rays": counted["extend"]["rays"],
+                  "any_hit_rays": counted["shadow"]["rays"], "algorithmic_bytes": alg_trace, "GBps": gbps(alg_trace, timed["extend"]["ms"])},
+        "shade": {"ms": timed["shade"]["ms"], "launches": timed["shade"]["launches"]},
+        "other": {"ms": timed["other"]["ms"], "launches": timed["other"]["launches"]},
+        "tail": {"ms": timed["tail"]["ms"], "launches": timed["tail"]["launches"]},
+    }
+
+
+def ncu_counters(pack, width, height, spp, kernel_prefix):
+    """What ncu measured for this kernel on this workload (committed capture, tools/ncu_counters.py): the bytes that really
+    moved and how busy the issue slots were — the numbers that say what binds, next to the contract's byte formula."""
+    for spp_try in (spp, 256, 128, 64):
+        path = os.path.join(ROOT, "profiles", f"r02_counters_{pack}_{width}x{height}x{spp_try}.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                doc = json.load(f)
+            rows = {k: v for k, v in doc["kernels"].items() if k.startswith(kernel_prefix)}
+            if not rows:
+                return None
+            k, v = max(rows.items(), key=lambda kv: kv[1]["time_ms"])
+            return {"file": os.path.relpath(path, ROOT), "kernel": k, "capture": doc.get("_what", ""), **v}
+    return None
+
+
+def roofline_block(pack, width, height, spp, kernels, render_ms):
+    dominant = max(("primary", "trace"), key=lambda k: kernels[k]["ms"])
+    peak, peak_src = measured_peak()
+    dk = kernels[dominant]
+    block = {"bound": "hbm", "kernel": "k_" + dominant, "achieved": dk["GBps"], "peak": peak, "unit": "GB/s",
+             "frac": dk["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+             "algorithmic_bytes_per_launch": dk["algorithmic_bytes"] / max(1, dk["launches"]),
+             "avg_launch_ms": dk["ms"] / max(1, dk["launches"]), "share_of_step": dk["ms"] / render_ms,
+             "formula": "32 B x child-box tests + 36 B x primitive tests + 52 B x closest-hit rays (SURVEY.md §8d), counted by the kernels themselves"}
+    c = ncu_counters(pack, width, height, spp, "k_" + dominant)
+    if c:
+        dram = c["dram_read_bytes"] + c["dram_write_bytes"]
+        block["traffic"] = dram / max(1, dk["launches"])
+        block.update({"dram_gbs": c["dram_gbs"], "dram_frac": c["dram_gbs"] / peak, "l2_gbs": c["l2_gbs"], "issue_active": c["issue_active"],
+                      "active_lanes": c["active_lanes"], "warps_active": c["warps_active"], "l1_hit": c["l1_hit"], "l2_hit": c["l2_hit"],
+                      "counters_source": f"{c['file']} ({c['kernel']}, {c['launches']} launches, {c['time_ms']:.2f} ms under ncu): "
+                                         "per-frame DRAM bytes / this step's launch count = traffic"})
+        # what the counters say binds: HBM only when the DRAM pipe is actually busy
+        if block["dram_frac"] < 0.5:
+            block["bound"] = "issue/latency"
+            block["bound_note"] = (f"DRAM moves {c['dram_gbs']:.0f} GB/s = {100 * block['dram_frac']:.1f} % of the measured peak while the §8d formula "
+                                   f"counts {dk['GBps']:.0f} GB/s of node and triangle fetches: they are served by L1 ({100 * c['l1_hit']:.0f} % hit) and L2; the kernel "
+                                   f"issues on {100 * c['issue_active']:.0f} % of the cycles with {c['active_lanes']:.1f} of 32 lanes active")
+    return block
 
 
 def run_b200(args, workload):
@@ -191,54 +417,21 @@ def run_b200(args, workload):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    scene = pkg.Scene(pack_path(name))
-    t0 = time.time()
-    renderer = pkg.Renderer(scene, device=local_rank)
-    create_s = time.time() - t0
-    stream = torch.cuda.current_stream()
-    frame = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")
-    tile_floats = pkg.tile_buffer_floats(width, height, world)
-    tiles = torch.zeros(tile_floats, dtype=torch.float32, device="cuda")
-    gathered = torch.zeros(tile_floats * world, dtype=torch.float32, device="cuda") if world > 1 else None
+    job = Job(pkg, pack_path(name), width, height, world, rank, local_rank)
+    renderer, stream, frame = job.renderer, job.stream, job.frame
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    barrier = job.barrier
 
-    def step(stats=0):
-        """One full frame, result left in HBM (on rank 0 for N>1)."""
-        if world == 1:
-            renderer.draw_device(frame, width, height, spp, seed=1, stream=stream.cuda_stream, stats=stats)
-        else:
-            renderer.draw_tiles_device(tiles, rank, world, width, height, spp, seed=1, stream=stream.cuda_stream, stats=stats)
-            dist.all_gather_into_tensor(gathered, tiles)
-            if rank == 0:
-                renderer.assemble_tiles_device(gathered, frame, width, height, world, stream=stream.cuda_stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        job.step(spp)
     barrier()
 
     # ---- timed region: K steps, CUDA events per step on the launching stream, L2 flushed between steps ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    step_ms = []
-    for _ in range(args.steps):
-        flush.zero_()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step()
-        e1.record(stream)
-        barrier()
-        step_ms.append(e0.elapsed_time(e1))
+    total_ms = job.timed_steps(spp, args.steps, flush)
     clocks = sampler.result()
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
     samples_per_step = width * height * spp
     value = samples_per_step * args.steps / total_ms / 1e3
     launches = renderer.stats()["kernel_launches"] * args.steps
@@ -266,7 +459,7 @@ def run_b200(args, workload):
         for _ in range(args.steps):
             barrier()
             t = time.perf_counter()
-            step()
+            job.step(spp)
             if rank == 0:
                 host_pinned.copy_(frame, non_blocking=False)
             barrier()
@@ -287,50 +480,42 @@ def run_b200(args, workload):
             no_cull_ms.append(renderer.stats()["render_ms"])
 
     # ---- roofline of the dominant kernel: one counted + one event-timed step (not part of `value`) ----
-    step(stats=pkg.STATS_COUNTERS)
-    barrier()
-    counted = renderer.stats()
-    step(stats=pkg.STATS_TIMING)
-    barrier()
-    timed = renderer.stats()
-    def algorithmic_bytes(c, closest):
-        return (BYTES_PER_NODE_VISIT * c["node_visits"] + BYTES_PER_PRIM_TEST * c["prim_tests"]
-                + (BYTES_PER_CLOSEST_RAY * c["rays"] if closest else 0))
+    counted, timed = job.kernel_split(spp)
+    kernels = kernel_table(counted, timed)
+    roofline = roofline_block(name, width, height, spp, kernels, timed["render_ms"])
+    roofline["kernels"] = kernels
+    parity = job.parity("fullsize_dragon.npz") if (name, width, height) == ("dragon", 1024, 1024) else None
+    create_s = job.create_s
+    job.close()
 
-    def gbps(nbytes, ms):
-        return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-
-    # k_primary traces the camera rays; k_trace traces, in ONE launch per bounce, the bounce rays (closest hit, counted
-    # under "extend") and the NEE rays (any hit, counted under "shadow"); its time is reported under "extend".
-    alg_primary = algorithmic_bytes(counted["primary"], True)
-    alg_trace = algorithmic_bytes(counted["extend"], True) + algorithmic_bytes(counted["shadow"], False)
-    kernels = {
-        "primary": {"ms": timed["primary"]["ms"], "launches": timed["primary"]["launches"], "rays": counted["primary"]["rays"],
-                    "algorithmic_bytes": alg_primary, "GBps": gbps(alg_primary, timed["primary"]["ms"])},
-        "trace": {"ms": timed["extend"]["ms"], "launches": timed["extend"]["launches"], "closest_hit_rays": counted["extend"]["rays"],
-                  "any_hit_rays": counted["shadow"]["rays"], "algorithmic_bytes": alg_trace, "GBps": gbps(alg_trace, timed["extend"]["ms"])},
-        "shade": {"ms": timed["shade"]["ms"], "launches": timed["shade"]["launches"]},
-        "other": {"ms": timed["other"]["ms"], "launches": timed["other"]["launches"]},
-        "tail": {"ms": timed["tail"]["ms"], "launches": timed["tail"]["launches"]},
-    }
-    dominant = max(("primary", "trace"), key=lambda k: kernels[k]["ms"])
-    peak, peak_src = measured_peak()
-    dk = kernels[dominant]
-    roofline = {"bound": "hbm", "kernel": "k_" + dominant, "achieved": dk["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dk["GBps"] / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dk["algorithmic_bytes"] / max(1, dk["launches"]),
-                "avg_launch_ms": dk["ms"] / max(1, dk["launches"]), "share_of_step": dk["ms"] / timed["render_ms"],
-                "kernels": kernels,
-                "formula": "32 B x child-box tests + 36 B x primitive tests + 52 B x closest-hit rays (SURVEY.md §8d), counted by the kernels themselves"}
-    # DRAM bytes of the dominant kernel from the committed ncu capture of the same frame (tools/gpu_evidence.sh), per launch of
-    # THIS step: the capture's per-frame total over this step's launch count (the capture may run more, smaller launches).
-    traffic_file = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
-    if os.path.exists(traffic_file) and name == "dragon" and (width, height, spp) == (1024, 1024, 256):
-        with open(traffic_file) as f:
-            detail = json.load(f).get("k_" + dominant + "_detail")
-        if detail:
-            roofline["traffic"] = (detail["dram_read_bytes_total"] + detail["dram_write_bytes_total"]) / max(1, dk["launches"])
-            roofline["traffic_source"] = "profiles/r01_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over one frame)"
+    # ---- the other BASELINE configs, same measurement in short form (not part of `value`) ----
+    others = {}
+    if not args.no_other_configs:
+        plan = OTHER_CONFIGS_N1 if world == 1 else OTHER_CONFIGS_MULTI
+        for label, key, steps, golden in plan:
+            if key == args.workload:
+                continue
+            o_name, o_w, o_h, o_spp, o_desc = WORKLOADS[key]
+            if not os.path.exists(pack_path(o_name)):
+                others[label] = {"workload": o_desc, "unavailable": f"scenes/{o_name}.b200scene missing"}
+                continue
+            try:
+                oj = Job(pkg, pack_path(o_name), o_w, o_h, world, rank, local_rank)
+                oj.step(o_spp)
+                oj.barrier()
+                ms = oj.timed_steps(o_spp, steps, flush) / steps
+                o_counted, o_timed = oj.kernel_split(o_spp)
+                o_kernels = kernel_table(o_counted, o_timed)
+                rec = {"workload": o_desc, "n_gpus": world, "Msamples_s": o_w * o_h * o_spp / ms / 1e3, "ms_per_step": ms, "steps": steps, "warmup": 1,
+                       "scene_create_s": oj.create_s, "gpu_launches_per_step": oj.renderer.stats()["kernel_launches"],
+                       "kernel_ms_single_arena": {k: round(v["ms"], 3) for k, v in o_kernels.items()},
+                       "rays": {"primary": o_counted["primary"]["rays"], "closest_hit": o_counted["extend"]["rays"], "any_hit": o_counted["shadow"]["rays"]},
+                       "roofline": roofline_block(o_name, o_w, o_h, o_spp, o_kernels, o_timed["render_ms"]),
+                       "parity": oj.parity(golden) if golden else None}
+                oj.close()
+                others[label] = rec
+            except Exception as e:  # a sub-record must not take the headline down
+                others[label] = {"workload": o_desc, "error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         cpu = None
@@ -342,7 +527,6 @@ def run_b200(args, workload):
         ref_gpu = None
         if not args.no_cpu_baseline and world == 1:
             # in a child process: the comparator is foreign code on the same GPU and must not be able to take this line down
-            renderer.close()
             try:
                 import subprocess
                 probe = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--ref-gpu-probe"],
@@ -350,25 +534,24 @@ def run_b200(args, workload):
                 ref_gpu = json.loads(probe.stdout.strip().splitlines()[-1])
             except Exception as e:
                 ref_gpu = {"value": None, "unit": "Msamples/s", "sample": f"unavailable: {e}"}
-        line = {
-            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "reference scene (Dragon, 831812 triangles) parsed once by the reference's XML parser into scenes/dragon.b200scene",
-            "config": {"workload": desc, "tile_split": f"{world} rank(s), 8x8-pixel tiles dealt round-robin, one NCCL all-gather per step" if world > 1 else "single GPU",
-                       "l2": "256 MB buffer written between timed steps (L2 flush); scene (160 MB) + wavefront state (4 GB) also exceed the 126 MB L2",
+        config = shared_config(desc, width, height, spp)
+        config.update({"tile_split": f"{world} rank(s), 8x8-pixel tiles dealt round-robin, one NCCL all-gather per step" if world > 1 else "single GPU",
                        "rng": "Philox4x32-10 keyed by seed, counter = (pixel, sample, depth)", "scene_create_s": create_s,
                        "tile_visibility_prepass": {
                            "what": "8x8 screen tiles whose camera-ray pyramid provably misses every box of a 384-box BVH cut are not traced "
                                    "(exact: the frame is bit-identical, tests/test_gpu_parity.py); the pre-pass runs inside the timed region",
                            "active_tiles": counted["active_tiles"], "local_tiles": counted["local_tiles"],
-                           "value_with_prepass_off": (samples_per_step / min(no_cull_ms) / 1e3) if no_cull_ms else None}},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "reference_gpu_baseline": ref_gpu,
+                           "value_with_prepass_off": (samples_per_step / min(no_cull_ms) / 1e3) if no_cull_ms else None}})
+        line = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "reference scene (Dragon, 831812 triangles) parsed once by the reference's XML parser into scenes/dragon.b200scene",
+            "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "parity": parity,
+            "cpu_baseline": cpu, "reference_gpu_baseline": ref_gpu, "configs": others,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    renderer.close()
 
 
 def main():
@@ -379,6 +562,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dragon-1024-256spp", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C1 / C3 / C4 / C5 sub-records")
     ap.add_argument("--ref-gpu-probe", action="store_true", help=argparse.SUPPRESS)  # child process of the b200 arm
     args = ap.parse_args()
     workload = WORKLOADS[args.workload]

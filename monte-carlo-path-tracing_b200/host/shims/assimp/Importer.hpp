@@ -1,8 +1,8 @@
 // assimp/Importer.hpp — TEST INFRASTRUCTURE ONLY (oracle build shim, never shipped).
 //
-// The reference loads OBJ meshes through Assimp (src/parser/model_loader.cpp:506-531),
-// which is neither vendored nor installed here.  This is a from-scratch Wavefront-OBJ
-// reader exposing the tiny slice of Assimp::Importer that model_loader.cpp calls:
+// The reference loads OBJ / PLY meshes through Assimp (src/parser/model_loader.cpp:506-531),
+// which is neither vendored nor installed here.  This is a from-scratch Wavefront-OBJ and
+// ASCII-PLY reader exposing the tiny slice of Assimp::Importer that model_loader.cpp calls:
 //   Importer::ReadFile(path, flags) -> const aiScene*,  Importer::GetErrorString().
 // It honours the post-process flags the reference passes (model_loader.cpp:512-520):
 //   Triangulate (fan), GenSmoothNormals (when the file has no `vn`), FlipUVs (v -> 1-v),
@@ -41,11 +41,14 @@ public:
         error_.clear();
         const size_t dot = path.find_last_of('.');
         const std::string suffix = dot == std::string::npos ? "" : path.substr(dot + 1);
-        if (suffix != "obj" && suffix != "OBJ") {
-            error_ = "oracle assimp shim: only Wavefront OBJ is supported ('" + path + "')";
+        if (suffix == "ply" || suffix == "PLY") {
+            if (!LoadPly(path, flags)) return nullptr;
+        } else if (suffix == "obj" || suffix == "OBJ") {
+            if (!LoadObj(path, flags)) return nullptr;
+        } else {
+            error_ = "assimp shim: only Wavefront OBJ and ASCII PLY are supported ('" + path + "')";
             return nullptr;
         }
-        if (!LoadObj(path, flags)) return nullptr;
         Publish();
         return &scene_;
     }
@@ -147,6 +150,98 @@ private:
             }
         }
         fclose(f);
+        return Assemble(path, flags, file_v, file_vn, file_vt, corners);
+    }
+
+    // Stanford PLY, ASCII flavour (resources/scene/box/models/bun_zipper_1.ply): `element vertex` with x y z and optionally
+    // nx ny nz / s t (or u v) among its properties, `element face` as index lists.  Per-vertex attributes: a corner's three
+    // indices coincide.
+    bool LoadPly(const std::string &path, unsigned int flags) {
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) {
+            error_ = "cannot open '" + path + "'";
+            return false;
+        }
+        std::vector<char> line(1 << 16);
+        size_t num_vertices = 0, num_faces = 0;
+        std::vector<std::string> vertex_props;
+        int element = 0; // 1 = vertex, 2 = face, 3 = something else
+        bool ascii = false, header_done = false;
+        std::vector<std::pair<int, size_t>> element_order; // (kind, count) in file order
+        while (fgets(line.data(), static_cast<int>(line.size()), f)) {
+            char word[64] = "", a[64] = "", b[64] = "", c[64] = "";
+            const int n = sscanf(line.data(), "%63s %63s %63s %63s", word, a, b, c);
+            if (n < 1) continue;
+            if (!strcmp(word, "format")) ascii = !strcmp(a, "ascii");
+            else if (!strcmp(word, "element")) {
+                const size_t count = static_cast<size_t>(strtoull(b, nullptr, 10));
+                element = !strcmp(a, "vertex") ? 1 : (!strcmp(a, "face") ? 2 : 3);
+                if (element == 1) num_vertices = count;
+                if (element == 2) num_faces = count;
+                element_order.push_back({element, count});
+            } else if (!strcmp(word, "property") && element == 1 && n >= 3) vertex_props.push_back(b);
+            else if (!strcmp(word, "end_header")) {
+                header_done = true;
+                break;
+            }
+        }
+        if (!header_done || !ascii) {
+            fclose(f);
+            error_ = "assimp shim: '" + path + "' is not an ASCII PLY file";
+            return false;
+        }
+        auto column = [&](const char *name, const char *alt = nullptr) {
+            for (size_t i = 0; i < vertex_props.size(); ++i)
+                if (vertex_props[i] == name || (alt && vertex_props[i] == alt)) return static_cast<int>(i);
+            return -1;
+        };
+        const int cx = column("x"), cy = column("y"), cz = column("z"), cnx = column("nx"), cny = column("ny"), cnz = column("nz"),
+                  cu = column("s", "u"), cv = column("t", "v");
+        if (cx < 0 || cy < 0 || cz < 0) {
+            fclose(f);
+            error_ = "assimp shim: no x / y / z vertex properties in '" + path + "'";
+            return false;
+        }
+        std::vector<V3> file_v, file_vn, file_vt;
+        std::vector<Key> corners;
+        std::vector<float> row(vertex_props.size());
+        for (const auto &el : element_order) {
+            for (size_t i = 0; i < el.second; ++i) {
+                if (!fgets(line.data(), static_cast<int>(line.size()), f)) {
+                    fclose(f);
+                    error_ = "assimp shim: '" + path + "' ends early";
+                    return false;
+                }
+                char *e = line.data();
+                if (el.first == 1) {
+                    for (float &x : row) x = strtof(e, &e);
+                    file_v.push_back({row[cx], row[cy], row[cz]});
+                    if (cnx >= 0 && cny >= 0 && cnz >= 0) file_vn.push_back({row[cnx], row[cny], row[cnz]});
+                    if (cu >= 0 && cv >= 0) file_vt.push_back({row[cu], row[cv], 0.0f});
+                } else if (el.first == 2) {
+                    const long count = strtol(e, &e, 10);
+                    std::vector<int> poly;
+                    for (long k = 0; k < count; ++k) poly.push_back(static_cast<int>(strtol(e, &e, 10)));
+                    for (size_t k = 1; k + 1 < poly.size(); ++k) // aiProcess_Triangulate (fan)
+                        for (int id : {poly[0], poly[k], poly[k + 1]}) {
+                            if (id < 0 || id >= static_cast<int>(num_vertices)) {
+                                fclose(f);
+                                error_ = "bad vertex index in '" + path + "'";
+                                return false;
+                            }
+                            corners.push_back({id, file_vt.empty() ? -1 : id, file_vn.empty() ? -1 : id});
+                        }
+                }
+            }
+        }
+        fclose(f);
+        (void)num_faces;
+        return Assemble(path, flags, file_v, file_vn, file_vt, corners);
+    }
+
+    // The post-process steps the reference asks for (model_loader.cpp:512-520), shared by both readers.
+    bool Assemble(const std::string &path, unsigned int flags, const std::vector<V3> &file_v, const std::vector<V3> &file_vn,
+                  const std::vector<V3> &file_vt, const std::vector<Key> &corners) {
         if (corners.empty()) {
             error_ = "no faces in '" + path + "'";
             return false;

@@ -21,6 +21,13 @@ SCENES = {
     "mercury": ("mercury/smooth_diffuse.xml", 256, 256, 32),               # C1
     "matpreview": ("matpreview/rough_conductor.xml", 1024, 1024, 512),     # C3
     "volumetric-caustic": ("volumetric-caustic/scene_v0.6.xml", 1024, 1024, 2048),  # C4
+    # the remaining scenes of resources/scene (XML's own size and spp)
+    "box": ("box/scene_v0.6.xml", 0, 0, 0),
+    "classroom": ("classroom/scene_v0.6.xml", 0, 0, 0),
+    "dining-room": ("dining-room/scene_v0.6.xml", 0, 0, 0),
+    "lte-orb-silver": ("lte-orb/silver.xml", 0, 0, 0),
+    "lte-orb-rough-glass": ("lte-orb/rough_glass.xml", 0, 0, 0),
+    "material-testball": ("material-testball/scene_v0.6.xml", 0, 0, 0),
 }
 
 

@@ -3,8 +3,9 @@
 
 Run once in a container that has /root/reference (after `python -c "import __graft_entry__ as g; g.build()"`):
 
-    python tests/golden/make_golden.py [--synthetic NAME ... | --kats]   (--synthetic: only (re)make the named synthetic scenes;
-                                                                       --kats: only the known answers of leaf functions)
+    python tests/golden/make_golden.py [--synthetic NAME ... | --scenes NAME ... | --kats]
+        --synthetic: only (re)make the named synthetic scenes;  --scenes: only the named reference scenes (scenes/NAME.b200scene);
+        --kats: only the known answers of leaf functions
 
 Outputs (all produced by reference code, none by the oracle restatement or the CUDA path):
   kats.json                      known answers of reference leaf functions (Tea<4>, LCG, VdC, MisWeight, cos-hemisphere, LBVH)
@@ -27,10 +28,15 @@ import refcheck  # noqa: E402
 EXACT = {  # scene -> (w, h, spp)
     "cornell-box": (24, 24, 4), "dragon": (32, 32, 2), "mercury": (24, 24, 4), "matpreview": (24, 24, 2),
     "volumetric-caustic": (24, 24, 4),
+    # the other scenes the reference ships (resources/scene/*)
+    "box": (24, 24, 4), "classroom": (24, 24, 4), "dining-room": (24, 24, 4), "lte-orb-silver": (24, 24, 4),
+    "lte-orb-rough-glass": (24, 24, 4), "material-testball": (24, 24, 4),
 }
 CONVERGED = {  # scene -> (w, h, spp)
     "cornell-box": (64, 64, 1024), "dragon": (64, 64, 1024), "mercury": (64, 64, 256), "matpreview": (64, 64, 512),
     "volumetric-caustic": (64, 64, 1024),
+    "box": (64, 64, 1024), "classroom": (64, 64, 512), "dining-room": (64, 64, 1024), "lte-orb-silver": (64, 64, 512),
+    "lte-orb-rough-glass": (64, 64, 1024), "material-testball": (64, 64, 512),
 }
 
 
@@ -38,6 +44,14 @@ def main():
     woop, mt = refcheck.ref_lib("woop"), refcheck.ref_lib("mt")
     L = woop.lib
     only_synthetic = sys.argv[2:] if len(sys.argv) > 2 and sys.argv[1] == "--synthetic" else None
+    if len(sys.argv) > 2 and sys.argv[1] == "--scenes":
+        make_reference_frames(woop, mt, sys.argv[2:])
+        settings_path = os.path.join(HERE, "settings.json")
+        settings = json.load(open(settings_path))
+        settings["exact"], settings["converged"] = EXACT, CONVERGED
+        with open(settings_path, "w") as f:
+            json.dump(settings, f, indent=1)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--kats":  # only the known answers of the leaf functions (no renders)
         make_kats(L)
         return
@@ -93,14 +107,18 @@ def make_kats(L):
     np.savez_compressed(os.path.join(HERE, "kulla_conty.npz"), brdf_avg=brdf, albedo_avg=albedo)
 
 
-def make_reference_frames(woop, mt):
+def make_reference_frames(woop, mt, only=None):
     for name, (w, h, spp) in EXACT.items():
+        if only is not None and name not in only:
+            continue
         pack = os.path.join(ROOT, "scenes", name + ".b200scene")
         for variant, ref in (("woop", woop), ("mt", mt)):
             frame, _, _ = ref.render_pack(pack, w, h, spp)
             np.save(os.path.join(HERE, f"exact_{name}_{variant}.npy"), frame)
             print("exact", name, variant, frame.mean())
     for name, (w, h, spp) in CONVERGED.items():
+        if only is not None and name not in only:
+            continue
         pack = os.path.join(ROOT, "scenes", name + ".b200scene")
         frame, _, seconds = woop.render_pack(pack, w, h, spp)
         np.save(os.path.join(HERE, f"converged_{name}.npy"), frame.astype(np.float32))

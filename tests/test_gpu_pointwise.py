@@ -216,8 +216,10 @@ def test_hit_attributes(pkg, scene_name):
     inp[:, 3:9] = rays[:, 0:6]
     inp[:, 9] = t[hit]
     out = ours.debug_eval(pkg.EVAL_SURFACE, 0, inp)
+    # ours is o + t d with the t both sides agree on to 1e-5 (the filter above): the bar scales with the distance travelled
     scale = np.maximum(np.abs(href["position"]).max(), 1.0)
-    assert np.abs(out[:, 0:3] - href["position"]).max() <= 2e-5 * scale, "hit position"
+    err = np.abs(out[:, 0:3] - href["position"]).max(axis=1)
+    assert (err <= 2e-5 * scale + 1.5e-5 * t[hit]).all(), f"hit position: worst {err.max():.3e} (scene scale {scale:.1f}, t up to {t[hit].max():.1f})"
     assert np.array_equal(out[:, 14] != 0, href["inside"] != 0), "hit side"
     assert np.array_equal(out[:, 15].view(np.uint32), href["id_instance"]), "hit instance"
     # a bump map perturbs the normal by texture differences over 1e-4-wide steps (bsdf.cpp:238-254): float noise is amplified
