@@ -312,6 +312,7 @@ typedef struct b200pt_debug_hit {
 } b200pt_debug_hit;
 #define B200PT_DEBUG_ANY_HIT 1u      /* TLAS::IntersectAny (tlas.cpp:44-76): prim = 0 if occluded, 0xFFFFFFFF if not */
 #define B200PT_DEBUG_PER_LANE_LOOP 2u /* the tail kernel's one-ray-per-lane loop instead of the persistent loop */
+#define B200PT_DEBUG_PACKET_LOOP 8u  /* the warp-packet loop of the camera / first-vertex NEE rays (binary tree only): 32 consecutive rays walk together */
 #define B200PT_DEBUG_RAW_PRIM 4u      /* prim as the kernels store it (leaf-order triangle index): input of B200PT_EVAL_SURFACE */
 /* rays_host / hits_host: n elements each, HOST memory.  Runs the product's traversal kernels on the scene's tree. */
 int b200pt_debug_trace(b200pt_handle h, const b200pt_debug_ray *rays_host, uint64_t n, uint32_t flags, b200pt_debug_hit *hits_host);

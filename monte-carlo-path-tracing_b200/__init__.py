@@ -54,6 +54,7 @@ CREATE_BVH8 = 2          # B200PT_CREATE_BVH8
 DEBUG_ANY_HIT = 1        # B200PT_DEBUG_ANY_HIT
 DEBUG_PER_LANE_LOOP = 2  # B200PT_DEBUG_PER_LANE_LOOP
 DEBUG_RAW_PRIM = 4       # B200PT_DEBUG_RAW_PRIM
+DEBUG_PACKET_LOOP = 8    # B200PT_DEBUG_PACKET_LOOP
 (EVAL_BSDF_EVALUATE, EVAL_BSDF_SAMPLE, EVAL_EMITTER_SAMPLE, EVAL_EMITTER_DIR, EVAL_MEDIUM_SAMPLE, EVAL_MEDIUM_EVALUATE,
  EVAL_PHASE_SAMPLE, EVAL_PHASE_EVALUATE, EVAL_TEXTURE, EVAL_SURFACE) = range(10)
 EVAL_IN, EVAL_OUT = 32, 16
@@ -199,12 +200,12 @@ class Renderer:
         _check(lib().b200pt_assemble_tiles_device(self._h, width, height, tile_world, gathered_tensor.data_ptr(),
                                                   frame_tensor.data_ptr(), stream), self._h)
 
-    def debug_trace(self, rays, any_hit=False, per_lane_loop=False, raw_prim=False):
+    def debug_trace(self, rays, any_hit=False, per_lane_loop=False, raw_prim=False, packet_loop=False):
         """Test hook (b200pt_debug_trace): rays = float32 [n, 8] (origin, direction, tmin, tmax) through the traversal kernels.
         Returns (t [n] float32, prim [n] uint32, uv [n, 2] float32)."""
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
         out = np.zeros((len(rays), 4), dtype=np.float32)
-        flags = (DEBUG_ANY_HIT if any_hit else 0) | (DEBUG_PER_LANE_LOOP if per_lane_loop else 0) | (DEBUG_RAW_PRIM if raw_prim else 0)
+        flags = (DEBUG_ANY_HIT if any_hit else 0) | (DEBUG_PER_LANE_LOOP if per_lane_loop else 0) | (DEBUG_RAW_PRIM if raw_prim else 0) | (DEBUG_PACKET_LOOP if packet_loop else 0)
         _check(lib().b200pt_debug_trace(self._h, rays.ctypes.data, len(rays), flags, out.ctypes.data), self._h)
         return out[:, 0].copy(), out[:, 1].copy().view(np.uint32), out[:, 2:4].copy()
 

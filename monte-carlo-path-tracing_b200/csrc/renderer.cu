@@ -122,6 +122,10 @@ struct b200pt_context {
     int num_sms = 148;
     // launch tunables (overridable through the environment for experiments: B200PT_TOP_NODES, B200PT_REFILL, B200PT_CTAS_PER_SM)
     int top_nodes = 0, refill = 20, ctas_per_sm = 4, min_inner = 8; // top_nodes = 0: no shared-memory staging (profiles/r01_sweep_sel3_topnodes.log)
+    // B200PT_PACKETS (bit mask): 1 = camera rays as warp packets, 2 = first-vertex NEE rays towards a single delta light as warp
+    // packets, 4 = NEE packets whatever the emitters are, 8 = NEE packets at every depth (4 / 8: experiments)
+    int packets = 3;
+    bool nee_coherent = false;    // one emitter, of a delta kind, and no area lights: the NEE rays of neighbouring hits run in parallel
     int tri_min = 8;              // B200PT_TRI_MIN: triangle postponing threshold of the wide traversal (LaunchConfig::tri_min)
     uint32_t wide_top_nodes = 0;  // nodes at the head of the wide node array that were laid out breadth-first
     // B200PT_STATS_TIMING: (class, begin, end) per launch, resolved in b200pt_get_stats
@@ -238,6 +242,13 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
             only = type;
         }
         c->shade_only = (mixed || getenv("B200PT_GENERIC_SHADE")) ? -1 : only;
+    }
+    {
+        const DIntegrator &ig = s.integrator;
+        bool delta = ig.num_emitters == 1 && ig.num_area_lights == 0;
+        for (const DEmitter &e : h.emitters)
+            if (e.type != B200PT_EMIT_POINT && e.type != B200PT_EMIT_SPOT && e.type != B200PT_EMIT_DIRECTIONAL && e.type != B200PT_EMIT_SUN) delta = false;
+        c->nee_coherent = delta;
     }
     c->stats.num_bvh_nodes = h.wide_nodes.empty() ? h.nodes.size() : h.wide_nodes.size();
     c->stats.bvh_width = h.wide_nodes.empty() ? 2u : 8u;
@@ -390,6 +401,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     lc.tri_min = c->tri_min;
     lc.blocks = c->num_sms * c->ctas_per_sm;
     lc.shade_only = c->shade_only;
+    lc.packets = c->packets & kPacketsPrimary;
 
     uint64_t launches = 0;
     c->timed.clear();
@@ -533,6 +545,8 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         run.which ^= 1;
         // One traversal launch per bounce: closest hits of the survivors (queue `which`) + occlusion of the NEE rays.
         auto trace = [&](int extend_queue) {
+            const bool nee_packets = (c->packets & kPacketsShadow) && (c->nee_coherent || (c->packets & 4)) && (depth == 1 || (c->packets & 8));
+            la.packets = nee_packets ? kPacketsShadow : 0;
             launch(kClassExtend, [&] {
                 const int n = LaunchTrace(la, c->scene, run.bp, depth, ar.queue[run.which], extend_queue, bins, ar.shadow, ar.radiance, capacity, ar.counters);
                 launches += n - 1;
@@ -628,6 +642,7 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     c->ctas_per_sm = env_int("B200PT_CTAS_PER_SM", c->ctas_per_sm, 1, 16);
     c->tile_cull = env_int("B200PT_TILE_CULL", 1, 0, 1) != 0;
     c->tail_paths = static_cast<uint32_t>(env_int("B200PT_TAIL_PATHS", static_cast<int>(c->tail_paths), 0, 1 << 24));
+    c->packets = env_int("B200PT_PACKETS", c->packets, 0, 15);
 
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();
@@ -635,12 +650,17 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     const bool gpu_lbvh = builder_env ? std::string(builder_env) == "lbvh" : (opts && (opts->flags & B200PT_CREATE_GPU_LBVH));
     const char *layout_env = getenv("B200PT_BVH_LAYOUT");   // "2" / "8": overrides the create option (experiments)
     const bool bvh8 = layout_env ? atoi(layout_env) == 8 : (opts && (opts->flags & B200PT_CREATE_BVH8));
+    const bool verbose = getenv("B200PT_VERBOSE_CREATE") != nullptr; // wall time of the phases of b200pt_create on stderr
+    auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     if (!BuildHostScene(*scene, opts ? opts->max_leaf_size : 0, gpu_lbvh, bvh8, &c->host, &err)) {
         // same prefix as renderer.cpp:343-346
         return SetGlobalError(B200PT_EINVAL, "error when commit renderer.\n\t" + err);
     }
+    if (verbose) fprintf(stderr, "[b200pt create] %-28s %8.1f ms\n", "BuildHostScene (total)", since(t0));
+    const auto t_upload = std::chrono::steady_clock::now();
     int rc = UploadScene(c.get(), *scene);
     if (rc != B200PT_OK) return rc;
+    if (verbose) fprintf(stderr, "[b200pt create] %-28s %8.1f ms\n", "UploadScene", since(t_upload));
     uint64_t capacity = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : kDefaultPathsInFlight;
     capacity = std::max<uint64_t>(capacity, 1024);
     c->max_capacity = std::min<uint64_t>(capacity, 1ull << 28);
@@ -790,7 +810,7 @@ int b200pt_debug_trace(b200pt_handle h, const b200pt_debug_ray *rays_host, uint6
     lc.blocks = h->num_sms * h->ctas_per_sm, lc.threads = 256, lc.stream = h->stream, lc.stats = false;
     lc.top_nodes = 0, lc.refill = h->refill, lc.min_inner = h->min_inner, lc.tri_min = h->tri_min;
     LaunchDebugTrace(lc, h->scene, rays.ptr, static_cast<uint32_t>(n), (flags & B200PT_DEBUG_ANY_HIT) != 0, (flags & B200PT_DEBUG_PER_LANE_LOOP) != 0,
-                     (flags & B200PT_DEBUG_RAW_PRIM) != 0, hits.ptr, counter.ptr);
+                     (flags & B200PT_DEBUG_RAW_PRIM) != 0, (flags & B200PT_DEBUG_PACKET_LOOP) != 0, hits.ptr, counter.ptr);
     CU_CHECK(h, cudaGetLastError());
     CU_CHECK(h, cudaMemcpyAsync(hits_host, hits.ptr, n * sizeof(b200pt_debug_hit), cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->stream));

@@ -16,11 +16,17 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "bvh_gpu.hpp"
 #include "bvh_wide.hpp"
@@ -147,6 +153,46 @@ F3 ToF3(V3 v) { return {v.x, v.y, v.z}; }
 // ---------------------------------------------------------------------------------------------
 // Geometry
 // ---------------------------------------------------------------------------------------------
+// Runs fn(t, num_threads) on num_threads threads (the calling thread is thread 0).
+template <typename Fn>
+void ParallelRun(unsigned num_threads, Fn fn) {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < num_threads; ++t) pool.emplace_back([&fn, t, num_threads] { fn(t, num_threads); });
+    fn(0u, num_threads);
+    for (std::thread &th : pool) th.join();
+}
+
+// B200PT_VERBOSE_CREATE=1: wall time of every phase of BuildHostScene on stderr.
+struct PhaseTimer {
+    std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    bool on = getenv("B200PT_VERBOSE_CREATE") != nullptr;
+    void operator()(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b200pt create] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+    }
+};
+
+unsigned BuildThreads() {
+    static const unsigned threads = [] {
+        const char *env = getenv("B200PT_BUILD_THREADS"); // experiments
+        const unsigned want = env ? static_cast<unsigned>(atoi(env)) : std::thread::hardware_concurrency();
+        return std::max(1u, std::min(32u, want));
+    }();
+    return threads;
+}
+
+// fn(i) for i in [0, n), in contiguous chunks over the build threads.
+template <typename Fn>
+void ParallelFor(size_t n, Fn fn) {
+    const unsigned threads = n < 8192 ? 1u : BuildThreads();
+    ParallelRun(threads, [&](unsigned t, unsigned nt) {
+        const size_t b = n * t / nt, e = n * (t + 1) / nt;
+        for (size_t i = b; i < e; ++i) fn(i);
+    });
+}
+
 struct RawTriangle {
     V3 p[3], n[3], t[3];
     float uv[3][2];
@@ -190,33 +236,32 @@ bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::ve
     }
     const uint64_t nv = mesh.num_vertices;
     std::vector<V3> pos(nv), nrm, tan, bit;
-    for (uint64_t i = 0; i < nv; ++i) pos[i] = TransformPoint(to_world, Load3(mesh.positions + 3 * i));
+    ParallelFor(nv, [&](size_t i) { pos[i] = TransformPoint(to_world, Load3(mesh.positions + 3 * i)); });
     if (mesh.normals) {
         const M4 normal_to_world = Inverse(Transpose(to_world));
         nrm.resize(nv);
-        for (uint64_t i = 0; i < nv; ++i) nrm[i] = TransformVector(normal_to_world, Load3(mesh.normals + 3 * i));
+        ParallelFor(nv, [&](size_t i) { nrm[i] = TransformVector(normal_to_world, Load3(mesh.normals + 3 * i)); });
     }
     if (mesh.tangents) {
         tan.resize(nv);
-        for (uint64_t i = 0; i < nv; ++i) tan[i] = TransformVector(to_world, Load3(mesh.tangents + 3 * i));
+        ParallelFor(nv, [&](size_t i) { tan[i] = TransformVector(to_world, Load3(mesh.tangents + 3 * i)); });
     }
     if (mesh.bitangents) {
         bit.resize(nv);
-        for (uint64_t i = 0; i < nv; ++i) bit[i] = TransformVector(to_world, Load3(mesh.bitangents + 3 * i));
+        ParallelFor(nv, [&](size_t i) { bit[i] = TransformVector(to_world, Load3(mesh.bitangents + 3 * i)); });
     }
-    float area_total = 0.0f;
-    tris->reserve(tris->size() + mesh.num_triangles);
-    for (uint64_t f = 0; f < mesh.num_triangles; ++f) {
+    for (uint64_t k = 0; k < 3 * mesh.num_triangles; ++k)
+        if (mesh.indices[k] >= nv) {
+            *error = "mesh index out of range.";
+            return false;
+        }
+    const size_t first_triangle = tris->size();
+    tris->resize(first_triangle + mesh.num_triangles);
+    ParallelFor(mesh.num_triangles, [&](size_t f) {
         RawTriangle tri;
         tri.inst = inst;
         uint32_t idx[3];
-        for (int j = 0; j < 3; ++j) {
-            idx[j] = mesh.indices[3 * f + j];
-            if (idx[j] >= nv) {
-                *error = "mesh index out of range.";
-                return false;
-            }
-        }
+        for (int j = 0; j < 3; ++j) idx[j] = mesh.indices[3 * f + j];
         if (!mesh.texcoords) {
             tri.uv[0][0] = 0, tri.uv[0][1] = 0, tri.uv[1][0] = 1, tri.uv[1][1] = 0, tri.uv[2][0] = 1, tri.uv[2][1] = 1;
         } else {
@@ -226,7 +271,6 @@ bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::ve
         const V3 v0v1 = tri.p[1] - tri.p[0], v0v2 = tri.p[2] - tri.p[0];
         const V3 normal_geom = Cross(v0v1, v0v2);
         tri.area = Length(normal_geom);
-        area_total += tri.area;
         if (nrm.empty()) {
             const V3 n = Normalize(normal_geom);
             for (int j = 0; j < 3; ++j) tri.n[j] = n;
@@ -250,8 +294,10 @@ bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::ve
                 tri.t[j] = Normalize(Cross(b, tri.n[j]));
             }
         }
-        tris->push_back(tri);
-    }
+        (*tris)[first_triangle + f] = tri;
+    });
+    float area_total = 0.0f; // summed in triangle order, as scene.cpp:48-49 does (Q3: the float sum is what the pdf uses)
+    for (uint64_t f = 0; f < mesh.num_triangles; ++f) area_total += (*tris)[first_triangle + f].area;
     *area_sum = area_total;
     return true;
 }
@@ -269,118 +315,353 @@ struct Box {
     }
 };
 
+// Four floats in one SSE register (plain loops elsewhere): the builder's inner loop is min / max of box corners.
+#if defined(__SSE2__)
+struct alignas(16) F4 {
+    float v[4];
+};
+inline F4 Min4(const F4 &a, const F4 &b) {
+    F4 r;
+    _mm_store_ps(r.v, _mm_min_ps(_mm_load_ps(a.v), _mm_load_ps(b.v)));
+    return r;
+}
+inline F4 Max4(const F4 &a, const F4 &b) {
+    F4 r;
+    _mm_store_ps(r.v, _mm_max_ps(_mm_load_ps(a.v), _mm_load_ps(b.v)));
+    return r;
+}
+#else
+struct alignas(16) F4 {
+    float v[4];
+};
+inline F4 Min4(const F4 &a, const F4 &b) {
+    F4 r;
+    for (int k = 0; k < 4; ++k) r.v[k] = a.v[k] < b.v[k] ? a.v[k] : b.v[k];
+    return r;
+}
+inline F4 Max4(const F4 &a, const F4 &b) {
+    F4 r;
+    for (int k = 0; k < 4; ++k) r.v[k] = a.v[k] > b.v[k] ? a.v[k] : b.v[k];
+    return r;
+}
+#endif
+constexpr F4 kF4Max{{kFltMax, kFltMax, kFltMax, kFltMax}}, kF4Lowest{{-kFltMax, -kFltMax, -kFltMax, -kFltMax}};
+
 struct BuildNode {
     Box box;
     int32_t left = -1, right = -1; // children (BuildNode indices) or -1 for leaf
     uint32_t first = 0, count = 0; // leaf range in the permuted triangle order
 };
 
+// Binned SAH (32 bins per axis, all three axes in one pass over the node's references).  The references are kept in an
+// array that is partitioned in place, so every pass is a sequential scan; the bins also carry the bounds of the centres,
+// so a child's box and centre box come out of the parent's bins and no node is scanned twice.  Large nodes are binned and
+// partitioned by all threads together (the first levels of the tree hold most of the work), the subtrees below
+// kParallelNode references are then built one per thread.
 class BvhBuilder {
 public:
     BvhBuilder(const std::vector<Box> &boxes, const std::vector<V3> &centers, uint32_t max_leaf, float traversal_cost)
-        : boxes_(boxes), centers_(centers), max_leaf_(max_leaf), traversal_cost_(traversal_cost) {
-        order_.resize(boxes.size());
-        std::iota(order_.begin(), order_.end(), 0u);
-        nodes_.resize(boxes.size() * 2 + 1); // a binary tree over n leaves has at most 2n-1 nodes
+        : max_leaf_(max_leaf), traversal_cost_(traversal_cost) {
+        const size_t n = boxes.size();
+        refs_.resize(n);
+        (void)centers; // = (lo + hi) * 0.5f, recomputed with the same rounding where needed (Ref::Centre)
+        ParallelFor(n, [&](size_t i) {
+            Ref r;
+            const uint32_t id = static_cast<uint32_t>(i);
+            r.lo = F4{{boxes[i].lo.x, boxes[i].lo.y, boxes[i].lo.z, 0.0f}}, r.hi = F4{{boxes[i].hi.x, boxes[i].hi.y, boxes[i].hi.z, 0.0f}};
+            memcpy(&r.lo.v[3], &id, 4);
+            refs_[i] = r;
+        });
+        nodes_.resize(n * 2 + 1); // a binary tree over n leaves has at most 2n-1 nodes
     }
 
-    int32_t Build() { return Recurse(0, static_cast<uint32_t>(order_.size()), 0); }
+    int32_t Build() {
+        const uint32_t n = static_cast<uint32_t>(refs_.size());
+        const unsigned threads = BuildThreads();
+        // bounds of the root
+        std::vector<Box> part_box(threads), part_cbox(threads);
+        ParallelRun(threads, [&](unsigned t, unsigned nt) {
+            const size_t b = static_cast<size_t>(n) * t / nt, e = static_cast<size_t>(n) * (t + 1) / nt;
+            for (size_t i = b; i < e; ++i) {
+                const Ref &rf = refs_[i];
+                part_box[t].Grow(Box{{rf.lo.v[0], rf.lo.v[1], rf.lo.v[2]}, {rf.hi.v[0], rf.hi.v[1], rf.hi.v[2]}});
+                part_cbox[t].Grow(V3{rf.Centre(0), rf.Centre(1), rf.Centre(2)});
+            }
+        });
+        Task root{0, n, 0, Box(), Box(), next_node_.fetch_add(1)};
+        for (unsigned t = 0; t < threads; ++t) root.box.Grow(part_box[t]), root.cbox.Grow(part_cbox[t]);
+        const int32_t root_id = root.id;
+        PhaseTimer phase;
+        phase("  root bounds");
+        // large nodes: one at a time, all threads on each
+        std::vector<Task> large{root}, small;
+        scratch_.resize(threads > 1 ? n : 0);
+        while (!large.empty()) {
+            const Task task = large.back();
+            large.pop_back();
+            if (threads == 1 || task.end - task.begin < kParallelNode) {
+                small.push_back(task);
+                continue;
+            }
+            Task l, r;
+            if (SplitNode(task, threads, &l, &r)) large.push_back(l), large.push_back(r);
+        }
+        phase("  large nodes");
+        // the subtrees below: biggest first, one per thread
+        std::sort(small.begin(), small.end(), [](const Task &a, const Task &b) { return a.end - a.begin > b.end - b.begin; });
+        std::atomic<size_t> next{0};
+        ParallelRun(std::min<size_t>(threads, std::max<size_t>(small.size(), 1)), [&](unsigned, unsigned) {
+            std::unique_ptr<Bins> bins(new Bins());
+            for (size_t k = next.fetch_add(1); k < small.size(); k = next.fetch_add(1)) Recurse(small[k], *bins);
+        });
+        phase("  subtrees");
+        scratch_.clear();
+        scratch_.shrink_to_fit();
+        order_.resize(n);
+        ParallelFor(n, [&](size_t i) { order_[i] = refs_[i].id(); });
+        return root_id;
+    }
     const std::vector<BuildNode> &nodes() const { return nodes_; }
     const std::vector<uint32_t> &order() const { return order_; }
 
 private:
     static constexpr int kBins = 32;
     static constexpr int kMedianSplitDepth = 32; // + ceil(log2(2^28 triangles)) = 60 levels at most < kStackSize (64)
+    static constexpr uint32_t kParallelNode = 1u << 16;
 
-    // Sub-ranges of order_ are disjoint, node slots come from an atomic counter: large subtrees build on their own thread.
-    int32_t Recurse(uint32_t begin, uint32_t end, int depth) {
-        const int32_t id = next_node_.fetch_add(1);
-        Box box, cbox;
-        for (uint32_t i = begin; i < end; ++i) {
-            box.Grow(boxes_[order_[i]]);
-            cbox.Grow(centers_[order_[i]]);
+    struct Ref {   // 32 bytes: box corners padded to four floats, the triangle's index in the pad of `lo`
+        F4 lo, hi;
+        uint32_t id() const {
+            uint32_t i;
+            memcpy(&i, &lo.v[3], 4);
+            return i;
         }
-        nodes_[id].box = box;
-        const uint32_t n = end - begin;
-        auto make_leaf = [&]() {
-            nodes_[id].first = begin;
-            nodes_[id].count = n;
-            return id;
-        };
-        if (n == 1) return make_leaf();
-
-        const V3 ext = cbox.hi - cbox.lo;
-        float best_cost = kFltMax;
-        int best_axis = -1, best_bin = -1;
-        for (int axis = 0; axis < 3; ++axis) {
-            const float lo = (&cbox.lo.x)[axis], e = (&ext.x)[axis];
-            if (!(e > 0.0f)) continue;
-            Box bin_box[kBins];
-            uint32_t bin_cnt[kBins] = {};
-            const float scale = kBins / e;
-            for (uint32_t i = begin; i < end; ++i) {
-                const uint32_t t = order_[i];
-                int b = static_cast<int>(((&centers_[t].x)[axis] - lo) * scale);
-                b = std::min(std::max(b, 0), kBins - 1);
-                bin_box[b].Grow(boxes_[t]);
-                ++bin_cnt[b];
-            }
-            float right_area[kBins];
-            uint32_t right_cnt[kBins];
-            Box acc;
-            uint32_t cnt = 0;
-            for (int b = kBins - 1; b > 0; --b) {
-                acc.Grow(bin_box[b]);
-                cnt += bin_cnt[b];
-                right_area[b] = cnt ? acc.HalfArea() : 0.0f;
-                right_cnt[b] = cnt;
-            }
-            acc = Box();
-            cnt = 0;
-            for (int b = 0; b < kBins - 1; ++b) {
-                acc.Grow(bin_box[b]);
-                cnt += bin_cnt[b];
-                if (cnt == 0 || right_cnt[b + 1] == 0) continue;
-                const float cost = acc.HalfArea() * cnt + right_area[b + 1] * right_cnt[b + 1];
-                if (cost < best_cost) best_cost = cost, best_axis = axis, best_bin = b;
+        float Centre(int axis) const { return (lo.v[axis] + hi.v[axis]) * 0.5f; } // = centers[i] of the caller, same rounding
+    };
+    struct Task {
+        uint32_t begin, end;
+        int depth;
+        Box box, cbox; // bounds of the boxes / of the centres of [begin, end)
+        int32_t id;    // node slot
+    };
+    struct Bin {
+        F4 lo = kF4Max, hi = kF4Lowest;   // box of the member boxes
+        F4 clo = kF4Max, chi = kF4Lowest; // box of the member centres
+        Box box() const { return Box{{lo.v[0], lo.v[1], lo.v[2]}, {hi.v[0], hi.v[1], hi.v[2]}}; }
+        Box cbox() const { return Box{{clo.v[0], clo.v[1], clo.v[2]}, {chi.v[0], chi.v[1], chi.v[2]}}; }
+    };
+    struct Bins {
+        Bin b[3][kBins];
+        uint32_t count[3][kBins] = {};
+        uint32_t mask[3] = {0, 0, 0}; // non-empty bins per axis: small nodes touch a few of the 96 bins, and only those are swept / reset
+        void Merge(const Bins &o) {
+            for (int a = 0; a < 3; ++a) {
+                for (int k = 0; k < kBins; ++k) {
+                    b[a][k].lo = Min4(b[a][k].lo, o.b[a][k].lo), b[a][k].hi = Max4(b[a][k].hi, o.b[a][k].hi);
+                    b[a][k].clo = Min4(b[a][k].clo, o.b[a][k].clo), b[a][k].chi = Max4(b[a][k].chi, o.b[a][k].chi);
+                    count[a][k] += o.count[a][k];
+                }
+                mask[a] |= o.mask[a];
             }
         }
-        const float leaf_cost = box.HalfArea() * n;
-        // SAH: splitting costs one traversal step (traversal_cost_ triangle tests) on top of the children's expected tests
-        if (n <= max_leaf_ && (best_axis < 0 || best_cost + traversal_cost_ * box.HalfArea() >= leaf_cost)) return make_leaf();
+        void Reset() {
+            for (int a = 0; a < 3; ++a) {
+                for (uint32_t m = mask[a]; m != 0; m &= m - 1) {
+                    const int k = __builtin_ctz(m);
+                    b[a][k] = Bin();
+                    count[a][k] = 0;
+                }
+                mask[a] = 0;
+            }
+        }
+    };
+    struct Split {
+        int axis = -1, bin = -1;
+        float cost = kFltMax;
+    };
 
-        uint32_t mid;
-        if (best_axis < 0 || depth >= kMedianSplitDepth) {
-            // all centroids coincide, or the tree is getting deep (peeling off a sliver per level): split the list in halves,
-            // which bounds the depth by kMedianSplitDepth + log2(n) and keeps the traversal stacks (traverse.cuh) safe
-        } else {
-            const float lo = (&cbox.lo.x)[best_axis], scale = kBins / (&ext.x)[best_axis];
-            auto it = std::partition(order_.begin() + begin, order_.begin() + end, [&](uint32_t t) {
-                int b = static_cast<int>(((&centers_[t].x)[best_axis] - lo) * scale);
-                b = std::min(std::max(b, 0), kBins - 1);
-                return b <= best_bin;
-            });
-            mid = static_cast<uint32_t>(it - order_.begin());
-            if (mid == begin || mid == end) mid = begin + n / 2;
-        }
-        int32_t l, r;
-        if (depth < 5 && n > 32768) {
-            std::thread left([&]() { l = Recurse(begin, mid, depth + 1); });
-            r = Recurse(mid, end, depth + 1);
-            left.join();
-        } else {
-            l = Recurse(begin, mid, depth + 1);
-            r = Recurse(mid, end, depth + 1);
-        }
-        nodes_[id].left = l;
-        nodes_[id].right = r;
-        return id;
+    static int BinOf(float c, float lo, float scale) {
+        const int b = static_cast<int>((c - lo) * scale);
+        return std::min(std::max(b, 0), kBins - 1);
     }
 
-    const std::vector<Box> &boxes_;
-    const std::vector<V3> &centers_;
+    void BinRange(const Task &t, uint32_t begin, uint32_t end, Bins *bins) const {
+        const V3 ext = t.cbox.hi - t.cbox.lo;
+        float lo[3], scale[3];
+        bool use[3];
+        for (int a = 0; a < 3; ++a) {
+            const float e = (&ext.x)[a];
+            use[a] = e > 0.0f;
+            lo[a] = (&t.cbox.lo.x)[a], scale[a] = use[a] ? kBins / e : 0.0f;
+        }
+        for (uint32_t i = begin; i < end; ++i) {
+            const Ref &r = refs_[i];
+            F4 c; // lane 3 of `lo` holds the index bits (a denormal as a float: arithmetic on it would trap to microcode)
+            for (int k = 0; k < 3; ++k) c.v[k] = (r.lo.v[k] + r.hi.v[k]) * 0.5f;
+            c.v[3] = 0.0f;
+            for (int a = 0; a < 3; ++a) {
+                if (!use[a]) continue;
+                const int k = BinOf(c.v[a], lo[a], scale[a]);
+                Bin &bin = bins->b[a][k];
+                bin.lo = Min4(bin.lo, r.lo), bin.hi = Max4(bin.hi, r.hi);
+                bin.clo = Min4(bin.clo, c), bin.chi = Max4(bin.chi, c);
+                ++bins->count[a][k];
+                bins->mask[a] |= 1u << k;
+            }
+        }
+    }
+
+    // Cheapest of the 3 x 31 bin boundaries.  Only boundaries right after a NON-EMPTY bin are evaluated: the boundaries inside a
+    // run of empty bins separate the same two sets at the same cost, and the first of them (the one evaluated here) is the
+    // one a sweep over all 31 would keep.
+    Split BestSplit(const Task &t, const Bins &bins) const {
+        const V3 ext = t.cbox.hi - t.cbox.lo;
+        Split best;
+        for (int axis = 0; axis < 3; ++axis) {
+            if (!((&ext.x)[axis] > 0.0f)) continue;
+            float right_area[kBins];
+            uint32_t right_cnt[kBins];
+            auto half_area = [](const F4 &lo, const F4 &hi) { // Box::HalfArea, same expression
+                const float dx = hi.v[0] - lo.v[0], dy = hi.v[1] - lo.v[1], dz = hi.v[2] - lo.v[2];
+                return dx * dy + dy * dz + dz * dx;
+            };
+            F4 lo = kF4Max, hi = kF4Lowest;
+            uint32_t cnt = 0;
+            for (uint32_t m = bins.mask[axis]; m != 0;) { // suffixes, from the last non-empty bin down
+                const int b = 31 - __builtin_clz(m);
+                m &= ~(1u << b);
+                lo = Min4(lo, bins.b[axis][b].lo), hi = Max4(hi, bins.b[axis][b].hi);
+                cnt += bins.count[axis][b];
+                right_area[b] = half_area(lo, hi);
+                right_cnt[b] = cnt;
+            }
+            lo = kF4Max, hi = kF4Lowest;
+            cnt = 0;
+            for (uint32_t m = bins.mask[axis]; m != 0;) {
+                const int b = __builtin_ctz(m);
+                m &= m - 1;
+                if (m == 0) break; // the last non-empty bin: nothing to its right
+                const int next = __builtin_ctz(m);
+                lo = Min4(lo, bins.b[axis][b].lo), hi = Max4(hi, bins.b[axis][b].hi);
+                cnt += bins.count[axis][b];
+                const float cost = half_area(lo, hi) * cnt + right_area[next] * right_cnt[next];
+                if (cost < best.cost) best.cost = cost, best.axis = axis, best.bin = b;
+            }
+        }
+        return best;
+    }
+
+    // Leaf or split?  Returns true with the split to use (axis < 0: halve the list), false for a leaf.
+    bool Decide(const Task &t, const Bins &bins, Split *split) {
+        const uint32_t n = t.end - t.begin;
+        nodes_[t.id].box = t.box;
+        *split = n > 1 ? BestSplit(t, bins) : Split();
+        const float leaf_cost = t.box.HalfArea() * n;
+        // SAH: splitting costs one traversal step (traversal_cost_ triangle tests) on top of the children's expected tests
+        if (n == 1 || (n <= max_leaf_ && (split->axis < 0 || split->cost + traversal_cost_ * t.box.HalfArea() >= leaf_cost))) {
+            nodes_[t.id].first = t.begin;
+            nodes_[t.id].count = n;
+            return false;
+        }
+        // all centroids coincide, or the tree is getting deep (peeling off a sliver per level): split the list in halves,
+        // which bounds the depth by kMedianSplitDepth + log2(n) and keeps the traversal stacks (traverse.cuh) safe
+        if (t.depth >= kMedianSplitDepth) split->axis = -1;
+        return true;
+    }
+
+    void ChildTasks(const Task &t, const Split &split, const Bins &bins, uint32_t mid, Task *l, Task *r) {
+        *l = Task{t.begin, mid, t.depth + 1, Box(), Box(), next_node_.fetch_add(1)};
+        *r = Task{mid, t.end, t.depth + 1, Box(), Box(), next_node_.fetch_add(1)};
+        if (split.axis >= 0) {
+            for (uint32_t m = bins.mask[split.axis]; m != 0; m &= m - 1) {
+                const int b = __builtin_ctz(m);
+                Task *side = b <= split.bin ? l : r;
+                side->box.Grow(bins.b[split.axis][b].box()), side->cbox.Grow(bins.b[split.axis][b].cbox());
+            }
+        } else {
+            for (uint32_t i = t.begin; i < t.end; ++i) {
+                Task *side = i < mid ? l : r;
+                const Ref &rf = refs_[i];
+                side->box.Grow(Box{{rf.lo.v[0], rf.lo.v[1], rf.lo.v[2]}, {rf.hi.v[0], rf.hi.v[1], rf.hi.v[2]}});
+                side->cbox.Grow(V3{rf.Centre(0), rf.Centre(1), rf.Centre(2)});
+            }
+        }
+        nodes_[t.id].left = l->id;
+        nodes_[t.id].right = r->id;
+    }
+
+    // One large node with all threads: false when it became a leaf.
+    bool SplitNode(const Task &t, unsigned threads, Task *l, Task *r) {
+        const uint32_t n = t.end - t.begin;
+        std::vector<Bins> part(threads);
+        ParallelRun(threads, [&](unsigned k, unsigned nt) {
+            BinRange(t, t.begin + static_cast<uint32_t>(static_cast<uint64_t>(n) * k / nt), t.begin + static_cast<uint32_t>(static_cast<uint64_t>(n) * (k + 1) / nt), &part[k]);
+        });
+        for (unsigned k = 1; k < threads; ++k) part[0].Merge(part[k]);
+        Split split;
+        if (!Decide(t, part[0], &split)) return false;
+        uint32_t mid = t.begin + n / 2;
+        if (split.axis >= 0) {
+            // stable parallel partition through the scratch array: count per chunk, then scatter
+            const float lo = (&t.cbox.lo.x)[split.axis], sc = kBins / ((&t.cbox.hi.x)[split.axis] - lo);
+            std::vector<uint32_t> left_count(threads + 1, 0);
+            auto chunk = [&](unsigned k, unsigned nt, uint32_t *b, uint32_t *en) {
+                *b = t.begin + static_cast<uint32_t>(static_cast<uint64_t>(n) * k / nt);
+                *en = t.begin + static_cast<uint32_t>(static_cast<uint64_t>(n) * (k + 1) / nt);
+            };
+            ParallelRun(threads, [&](unsigned k, unsigned nt) {
+                uint32_t b, en, c = 0;
+                chunk(k, nt, &b, &en);
+                for (uint32_t i = b; i < en; ++i) c += BinOf(refs_[i].Centre(split.axis), lo, sc) <= split.bin;
+                left_count[k + 1] = c;
+            });
+            for (unsigned k = 0; k < threads; ++k) left_count[k + 1] += left_count[k];
+            mid = t.begin + left_count[threads];
+            ParallelRun(threads, [&](unsigned k, unsigned nt) {
+                uint32_t b, en;
+                chunk(k, nt, &b, &en);
+                uint32_t lpos = t.begin + left_count[k], rpos = mid + (b - t.begin) - left_count[k];
+                for (uint32_t i = b; i < en; ++i) {
+                    if (BinOf(refs_[i].Centre(split.axis), lo, sc) <= split.bin) scratch_[lpos++] = refs_[i];
+                    else scratch_[rpos++] = refs_[i];
+                }
+            });
+            ParallelRun(threads, [&](unsigned k, unsigned nt) {
+                uint32_t b, en;
+                chunk(k, nt, &b, &en);
+                std::copy(scratch_.begin() + b, scratch_.begin() + en, refs_.begin() + b);
+            });
+        }
+        ChildTasks(t, split, part[0], mid, l, r);
+        return true;
+    }
+
+    // `bins`: this thread's scratch, all empty on entry and on return.
+    void Recurse(const Task &t, Bins &bins) {
+        if (t.end - t.begin > 1) BinRange(t, t.begin, t.end, &bins);
+        Split split;
+        if (!Decide(t, bins, &split)) {
+            bins.Reset();
+            return;
+        }
+        const uint32_t n = t.end - t.begin;
+        uint32_t mid = t.begin + n / 2;
+        if (split.axis >= 0) {
+            const float lo = (&t.cbox.lo.x)[split.axis], sc = kBins / ((&t.cbox.hi.x)[split.axis] - lo);
+            auto it = std::partition(refs_.begin() + t.begin, refs_.begin() + t.end,
+                                     [&](const Ref &r) { return BinOf(r.Centre(split.axis), lo, sc) <= split.bin; });
+            mid = static_cast<uint32_t>(it - refs_.begin());
+        }
+        Task l, r;
+        ChildTasks(t, split, bins, mid, &l, &r);
+        bins.Reset();
+        Recurse(l, bins);
+        Recurse(r, bins);
+    }
+
     uint32_t max_leaf_;
     float traversal_cost_;
+    std::vector<Ref> refs_, scratch_;
     std::vector<uint32_t> order_;
     std::vector<BuildNode> nodes_;
     std::atomic<int32_t> next_node_{0};
@@ -620,7 +901,20 @@ float IntegrateAlbedo(V3 V, float roughness, float brdf) {
 
 } // namespace
 
+// The tables depend on nothing but the constants above: computed once per process (0.1-0.4 s), copied afterwards.
+void ComputeKullaContyTablesOnce(float *brdf_avg, float *albedo_avg);
 void ComputeKullaContyTables(float *brdf_avg, float *albedo_avg) {
+    static std::once_flag once;
+    static std::vector<float> brdf, albedo;
+    std::call_once(once, [] {
+        brdf.assign(kLutResolution * kLutResolution, 0.0f), albedo.assign(kLutResolution, 0.0f);
+        ComputeKullaContyTablesOnce(brdf.data(), albedo.data());
+    });
+    std::copy(brdf.begin(), brdf.end(), brdf_avg);
+    std::copy(albedo.begin(), albedo.end(), albedo_avg);
+}
+
+void ComputeKullaContyTablesOnce(float *brdf_avg, float *albedo_avg) {
     const float step = 1.0f / kLutResolution;
     auto row = [&](int i) {
         float albedo_accum = 0.0f;
@@ -634,13 +928,9 @@ void ComputeKullaContyTables(float *brdf_avg, float *albedo_avg) {
         }
         albedo_avg[i] = albedo_accum * step;
     };
-    const unsigned num_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < num_threads; ++t)
-        pool.emplace_back([&, t]() {
-            for (int i = static_cast<int>(t); i < kLutResolution; i += static_cast<int>(num_threads)) row(i);
-        });
-    for (std::thread &th : pool) th.join();
+    ParallelRun(BuildThreads(), [&](unsigned t, unsigned num_threads) {
+        for (int i = static_cast<int>(t); i < kLutResolution; i += static_cast<int>(num_threads)) row(i);
+    });
 }
 
 DCamera MakeCamera(const b200pt_camera &cam, uint32_t width, uint32_t height) {
@@ -668,6 +958,7 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
     max_leaf_size = std::min(max_leaf_size, 8u);
     hs->camera = d.camera;
 
+    PhaseTimer whole;
     // ---- textures ----
     for (uint64_t i = 0; i < d.num_textures; ++i) {
         const b200pt_texture &t = d.textures[i];
@@ -904,6 +1195,7 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
         o.pdf_area = 1.0f / inst_area[i];
     }
 
+    whole("textures .. geometry");
     // ---- area lights (renderer.cpp:271-304) ----
     hs->cdf_area_light.assign(1, 0.0f);
     for (uint64_t i = 0; i < d.num_instances; ++i) {
@@ -916,15 +1208,17 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
     }
 
     // ---- BVH over all triangles ----
+    PhaseTimer phase;
     const auto t0 = std::chrono::steady_clock::now();
     const size_t nt = tris.size();
     std::vector<Box> boxes(nt);
     std::vector<V3> centers(nt);
-    for (size_t i = 0; i < nt; ++i) {
+    ParallelFor(nt, [&](size_t i) {
         for (int j = 0; j < 3; ++j) boxes[i].Grow(tris[i].p[j]);
         centers[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
-        scene_box.Grow(boxes[i]);
-    }
+    });
+    for (size_t i = 0; i < nt; ++i) scene_box.Grow(boxes[i]);
+    phase("triangle boxes");
     std::vector<uint32_t> order;
     std::vector<Bvh2Node> binary; // the SAH tree as handed to the wide collapse / the cull-box cut
     int32_t binary_root = -1;
@@ -954,8 +1248,10 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             const char *ct_env = getenv("B200PT_SAH_TRAVERSAL_COST"); // tuning knob, default 1 triangle test per node step
             BvhBuilder builder(boxes, centers, wide ? std::min(max_leaf_size, kWideMaxLeaf) : max_leaf_size,
                                ct_env ? static_cast<float>(atof(ct_env)) : 1.0f);
+            phase("builder setup");
             binary_root = builder.Build();
             order = builder.order();
+            phase("SAH build");
             if (wide) {
                 const std::vector<BuildNode> &bn = builder.nodes();
                 binary.resize(bn.size());
@@ -971,6 +1267,7 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
                 hs->wide_depth = info.depth, hs->wide_top_nodes = info.top_nodes;
             } else {
                 FlattenBvh(builder.nodes(), binary_root, 1024, &hs->nodes);
+                phase("flatten");
                 if (FlatBvhDepth(hs->nodes) >= kBvh2StackSize) {
                     *error = "BVH too deep for the traversal stack.";
                     return false;
@@ -978,9 +1275,10 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             }
         }
     }
+    phase("tree done");
     hs->tri_verts.resize(nt);
     hs->tri_shade.resize(nt);
-    for (size_t i = 0; i < nt; ++i) {
+    ParallelFor(nt, [&](size_t i) {
         const RawTriangle &t = tris[order[i]];
         TriVerts &v = hs->tri_verts[i];
         float inst_bits;
@@ -998,7 +1296,8 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             s.uv[j][0] = t.uv[j][0], s.uv[j][1] = t.uv[j][1];
         }
         s.inst = t.inst;
-    }
+    });
+    phase("attribute permutation");
     hs->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     memcpy(hs->scene_bmin, &scene_box.lo, 12);
     memcpy(hs->scene_bmax, &scene_box.hi, 12);
@@ -1170,10 +1469,12 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
     for (const DInstance &in : hs->instances)
         if (in.id_bsdf != kInvalid && hs->bsdfs[in.id_bsdf].id_opacity != kInvalid) ig.has_opacity = 1;
 
+    whole("BVH .. integrator");
     // ---- Kulla-Conty LUTs (renderer.cpp:311-314); only read by conductor/dielectric BSDFs ----
     hs->kc_brdf_avg.assign(kLutResolution * kLutResolution, 0.0f);
     hs->kc_albedo_avg.assign(kLutResolution, 0.0f);
     if (need_kulla_conty) ComputeKullaContyTables(hs->kc_brdf_avg.data(), hs->kc_albedo_avg.data());
+    whole("Kulla-Conty tables");
     return true;
 }
 

@@ -13,6 +13,7 @@
 
 #include "shade_kernel.cuh"
 #include "shading.cuh"
+#include "traverse_packet.cuh"
 #include "traverse_wide.cuh"
 #include "wavefront.cuh"
 
@@ -130,7 +131,7 @@ template <bool STATS, bool OPACITY, int LAYOUT>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(const __grid_constant__ DeviceScene scene,
                                                       const __grid_constant__ BatchParams bp, PathQueue q,
                                                       float *radiance, uint32_t capacity, Counters *counters, int max_top,
-                                                      int refill, int phase_lanes) {
+                                                      int refill, int phase_lanes, int packets) {
     extern __shared__ uint4 top[];
     __shared__ uint64_t bar;
     const uint32_t num_top = LAYOUT == kLayoutWideTop ? min(scene.num_wide_nodes, static_cast<uint32_t>(max_top)) : 0u;
@@ -177,6 +178,18 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(con
         }
         q.hit[idx] = hit;
     };
+    if constexpr (LAYOUT == kLayoutBinary) {
+        // 32 consecutive slots are 32 samples of one pixel (slot = pixel * sample_count + sample): one warp packet
+        if (packets & kPacketsPrimary) {
+            __shared__ int packet_stack[kThreads / 32][kPacketStack];
+            TraversePacket<false, STATS, OPACITY>(
+                scene, 0u, nslots, &counters->work_primary, bp.key, packet_stack[threadIdx.x >> 5],
+                [&](uint32_t slot, Ray *ray, uint3 *ctr) { return fetch(slot, ray, ctr, nullptr); },
+                [&](uint32_t slot, const HitRec &hit, bool found) { finish(slot, hit, found, false); }, &tc[0], &rays[0]);
+            FlushCounters(STATS, tc[0], rays[0], kClassPrimary, counters);
+            return;
+        }
+    }
     TraverseLayout<false, STATS, OPACITY, LAYOUT>(scene, top, num_top, nslots, &counters->work_primary, refill, phase_lanes, bp.key, fetch, finish, tc, rays);
     FlushCounters(STATS, tc[0], rays[0], kClassPrimary, counters);
 }
@@ -194,7 +207,7 @@ template <bool STATS, bool OPACITY, int LAYOUT>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const __grid_constant__ DeviceScene scene,
                                                     const __grid_constant__ BatchParams bp, uint32_t depth, PathQueue q, int which,
                                                     ShadowQueue sq, float *radiance, uint32_t capacity, Counters *counters,
-                                                    int max_top, int refill, int phase_lanes) {
+                                                    int max_top, int refill, int phase_lanes, int packets) {
     extern __shared__ uint4 top[];
     __shared__ uint64_t bar;
     const uint32_t n_extend = which >= 0 ? counters->queue[which] : 0u, n_shadow = counters->shadow;
@@ -235,6 +248,25 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const
             sq.tmax[i - n_extend] = kShadowUnoccluded;
         }
     };
+    if constexpr (LAYOUT == kLayoutBinary) {
+        // Coherent NEE rays (the host says when: first vertex, delta lights) go first, as warp packets; the persistent loop then
+        // only has the bounce rays left.  One launch all the same: a warp that finds no packet left moves on to the bounce rays.
+        if ((packets & kPacketsShadow) && n_shadow > 0) {
+            __shared__ int packet_stack[kThreads / 32][kPacketStack];
+            TraversePacket<true, STATS, OPACITY>(
+                scene, n_extend, n_shadow, &counters->work_packets, bp.key, packet_stack[threadIdx.x >> 5],
+                [&](uint32_t i, Ray *ray, uint3 *ctr) {
+                    bool any;
+                    return fetch(i, ray, ctr, &any);
+                },
+                [&](uint32_t i, const HitRec &hit, bool found) { finish(i, hit, found, true); }, &tc[1], &rays[1]);
+            if (n_extend > 0)
+                TraversePersistent<false, STATS, OPACITY, false>(scene, nullptr, 0, n_extend, &counters->work_trace, refill, phase_lanes, bp.key, fetch, finish, tc, rays);
+            FlushCounters(STATS, tc[0], rays[0], kClassExtend, counters);
+            FlushCounters(STATS, tc[1], rays[1], kClassShadow, counters);
+            return;
+        }
+    }
     TraverseLayout<true, STATS, OPACITY, LAYOUT>(scene, top, num_top, n, &counters->work_trace, refill, phase_lanes, bp.key, fetch, finish, tc, rays);
     FlushCounters(STATS, tc[0], rays[0], kClassExtend, counters);
     FlushCounters(STATS, tc[1], rays[1], kClassShadow, counters);
@@ -247,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const
 // ---------------------------------------------------------------------------------------------
 template <int LAYOUT>
 __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_debug_trace(const __grid_constant__ DeviceScene scene, const b200pt_debug_ray *rays_in,
-                                                                                uint32_t n, bool any_hit, bool single, bool raw_prim,
+                                                                                uint32_t n, bool any_hit, bool single, bool raw_prim, bool packet,
                                                                                 b200pt_debug_hit *out, uint32_t *work_counter, int refill, int phase_lanes) {
     auto report = [&](uint32_t i, const HitRec &hit, bool found, bool any) {
         b200pt_debug_hit h;
@@ -281,6 +313,22 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_debug_trace
     extern __shared__ uint4 top[];
     TraversalCounters tc[2];
     uint32_t traced[2] = {0, 0};
+    if constexpr (LAYOUT == kLayoutBinary) {
+        if (packet) { // 32 consecutive caller rays per warp packet (traverse_packet.cuh)
+            __shared__ int packet_stack[kThreads / 32][kPacketStack];
+            auto fetch3 = [&](uint32_t i, Ray *ray, uint3 *) {
+                load(i, ray);
+                return true;
+            };
+            if (any_hit)
+                TraversePacket<true, false, false>(scene, 0u, n, work_counter, make_uint2(0u, 0u), packet_stack[threadIdx.x >> 5], fetch3,
+                                                   [&](uint32_t i, const HitRec &hit, bool found) { report(i, hit, found, true); }, &tc[0], &traced[0]);
+            else
+                TraversePacket<false, false, false>(scene, 0u, n, work_counter, make_uint2(0u, 0u), packet_stack[threadIdx.x >> 5], fetch3,
+                                                    [&](uint32_t i, const HitRec &hit, bool found) { report(i, hit, found, false); }, &tc[0], &traced[0]);
+            return;
+        }
+    }
     auto fetch = [&](uint32_t i, Ray *ray, uint3 *, bool *any) {
         load(i, ray);
         *any = any_hit;
@@ -325,6 +373,7 @@ __global__ void __launch_bounds__(kThreads) k_settle(Counters *c, int which_queu
         }
         if (reset_shadow) c->shadow = 0;
         c->work_trace = 0;
+        c->work_packets = 0;
         c->settle_ticket = 0;
     }
 }
@@ -511,7 +560,7 @@ void EnableSmem(K kernel, size_t bytes) {
         const int phase_lanes = wide ? lc.tri_min : lc.min_inner;                                                     \
         auto go = [&](auto k) {                                                                                       \
             EnableSmem(k, smem);                                                                                      \
-            k<<<lc.blocks, kThreads, smem, lc.stream>>>(__VA_ARGS__, lc.top_nodes, lc.refill, phase_lanes);           \
+            k<<<lc.blocks, kThreads, smem, lc.stream>>>(__VA_ARGS__, lc.top_nodes, lc.refill, phase_lanes, lc.packets); \
         };                                                                                                            \
         auto pick_layout = [&](auto binary, auto wide_plain, auto wide_top) {                                         \
             if (!wide) go(binary);                                                                                    \
@@ -572,11 +621,11 @@ int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
 }
 
 void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b200pt_debug_ray *rays, uint32_t n, bool any_hit, bool single,
-                      bool raw_prim, b200pt_debug_hit *out, uint32_t *work_counter) {
+                      bool raw_prim, bool packet, b200pt_debug_hit *out, uint32_t *work_counter) {
     if (scene.num_wide_nodes > 0)
-        k_debug_trace<kLayoutWide><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, raw_prim, out, work_counter, lc.refill, lc.tri_min);
+        k_debug_trace<kLayoutWide><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, raw_prim, false, out, work_counter, lc.refill, lc.tri_min);
     else
-        k_debug_trace<kLayoutBinary><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, raw_prim, out, work_counter, lc.refill, lc.min_inner);
+        k_debug_trace<kLayoutBinary><<<lc.blocks, kThreads, 0, lc.stream>>>(scene, rays, n, any_hit, single, raw_prim, packet, out, work_counter, lc.refill, lc.min_inner);
 }
 
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,

@@ -70,10 +70,11 @@ struct Counters {             // device-resident
     uint32_t work_tail;       // next unclaimed entry of the tail kernel
     uint32_t tail_taken;      // != 0 once k_tail has taken over the batch's remaining paths (depth of the take-over + 1)
     uint32_t settle_ticket;   // CTAs of k_settle that have finished (the last one resets the counters)
+    uint32_t work_packets;    // next unclaimed NEE ray of k_trace's packet loop (coherent shadow rays, traverse_packet.cuh)
     uint32_t bin_count[2][kNumShadeBins]; // entries of path queue 0 / 1 per shading bin (scenes with several BSDF models)
     ClassCounters cls[3];     // primary / extend / shadow traversal statistics (zeroed per render)
 };
-constexpr size_t kCountersPerBatchBytes = 32 + 2 * kNumShadeBins * sizeof(uint32_t); // the part of Counters that is zeroed for every batch
+constexpr size_t kCountersPerBatchBytes = 36 + 2 * kNumShadeBins * sizeof(uint32_t); // the part of Counters that is zeroed for every batch
 
 struct BatchParams {
     DCamera camera;
@@ -130,7 +131,11 @@ struct LaunchConfig {
     int min_inner;            // binary layout: lanes still walking inner nodes below which a warp switches to its pending leaves
     int tri_min;              // wide layout: lanes holding triangles below which they are postponed in favour of inner nodes
     int shade_only;           // the one BSDF type every scattering surface of the scene has, or -1 (generic shading kernel)
+    int packets;              // kPackets* bits: which ray sets of this launch walk the binary tree as warp packets
 };
+// Warp-packet traversal (traverse_packet.cuh) of the ray sets that are coherent by construction.
+constexpr int kPacketsPrimary = 1;  // camera rays: 32 consecutive sample slots belong to one pixel
+constexpr int kPacketsShadow = 2;   // NEE rays of this launch (first vertex, towards delta lights: neighbouring origins, one direction)
 
 // kernel launchers (wavefront.cu)
 // LaunchPrimary / LaunchTrace also file the traced queue's hits into the shading bins when `bins.lists` is set (one
@@ -154,7 +159,7 @@ void LaunchTail(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
                 float *radiance, uint32_t capacity, Counters *counters, uint32_t threshold);
 // Test hook (b200pt_debug_trace): rays[0..n) through the persistent traversal loop (or the per-lane one) of the scene's tree.
 void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b200pt_debug_ray *rays, uint32_t n, bool any_hit, bool single,
-                      bool raw_prim, b200pt_debug_hit *out, uint32_t *work_counter);
+                      bool raw_prim, bool packet, b200pt_debug_hit *out, uint32_t *work_counter);
 // Test hook (b200pt_debug_eval, debug_eval.cu): leaf functions of the shading stage at caller-supplied inputs.
 void LaunchDebugEval(cudaStream_t stream, const DeviceScene &scene, uint32_t what, uint32_t id, uint32_t n, const float *in, float *out);
 constexpr uint32_t kMaxTailDepth = 4096; // = kMaxRounds of the host loop

@@ -220,12 +220,29 @@ def test_hit_attributes(pkg, scene_name):
     scale = np.maximum(np.abs(href["position"]).max(), 1.0)
     err = np.abs(out[:, 0:3] - href["position"]).max(axis=1)
     assert (err <= 2e-5 * scale + 1.5e-5 * t[hit]).all(), f"hit position: worst {err.max():.3e} (scene scale {scale:.1f}, t up to {t[hit].max():.1f})"
-    assert np.array_equal(out[:, 14] != 0, href["inside"] != 0), "hit side"
+    import ctypes
+    import scene_builder as sb
+    d, _ = counts(scene)
+    inst_type = np.array([ctypes.cast(d.instances, ctypes.POINTER(sb.Instance))[i].type for i in range(d.num_instances)])
+    kind = inst_type[href["id_instance"]]
     assert np.array_equal(out[:, 15].view(np.uint32), href["id_instance"]), "hit instance"
+    # `inside` of a sphere / cylinder is the sign of c = |o|^2 - r^2 in float (sphere.cpp:49, cylinder.cpp:61): origins within
+    # rounding of the surface may fall on either side of it with another contraction of the products
+    side_differs = (out[:, 14] != 0) != (href["inside"] != 0)
+    assert side_differs.mean() <= 0.002, f"hit side differs on {side_differs.sum()} of {len(side_differs)} hits (instance types {np.unique(kind[side_differs])})"
     # a bump map perturbs the normal by texture differences over 1e-4-wide steps (bsdf.cpp:238-254): float noise is amplified
     tol = 3e-3 if "bump" in scene_name else 2e-4
+    # The tangent frame of a DISK hangs on phi = atan2(z, x) of a point whose local z is rounding noise around 0
+    # (disk.cpp:38-60 with the y-up CartesianToSpherical, math.cpp:102-119): phi jumps between 0 / pi / -pi with the sign of that
+    # noise, and `flip_tangent = phi' > pi` with it.  The frame is compared up to that sign there; normals are not affected.
+    disk = kind == sb.INST_DISK
+    same_side = ~side_differs
     for cols, field in (((3, 6), "normal"), ((6, 9), "tangent"), ((9, 12), "bitangent")):
-        err = np.abs(out[:, cols[0]:cols[1]] - href[field]).max(axis=1)
-        assert (err > tol).mean() <= 0.002, f"{field}: {(err > tol).sum()} of {len(err)} differ (worst {err.max():.3e})"
+        a, b = out[:, cols[0]:cols[1]], href[field]
+        err = np.abs(a - b).max(axis=1)
+        if field != "normal":
+            err = np.where(disk, np.minimum(err, np.abs(a + b).max(axis=1)), err)
+        err = err[same_side]
+        assert (err > tol).mean() <= 0.002, f"{field}: {(err > tol).sum()} of {len(err)} differ (worst {err.max():.3e}; instance types {np.unique(kind[same_side][err > tol])})"
     err = np.abs(out[:, 12:14] - href["texcoord"]).max(axis=1)
     assert (err > 2e-5).mean() <= 0.002, f"texcoord: worst {err.max():.3e}"

@@ -83,10 +83,12 @@ def check_against_reference(r, tracer, table, rays, name, allow_prim_ties, exact
             # does any BVH whose boxes end exactly on the lattice lines — ours included (same test, other rounding).  The
             # watertightness Woop's test guarantees is per TRIANGLE PAIR, and that is what must hold: whenever the boxes let
             # the ray through to the triangles it is hit, at the distance of its target.  Leaks are reported and bounded.
-            leaks, ref_leaks = exact_targets & ~hit, exact_targets & ~ref_hit
+            # (a ray that slips through the first sheet and meets the second one has leaked just the same)
+            through = lambda h, tt: exact_targets & (~h | (tt > expected_t * np.float32(1.001)))
+            leaks, ref_leaks = through(hit, t), through(ref_hit, ref["t"])
             assert leaks.sum() <= max(2 * ref_leaks.sum(), 0.08 * exact_targets.sum()), \
                 f"{name}: {leaks.sum()} of {exact_targets.sum()} rays leaked at a shared vertex / edge (the reference leaks {ref_leaks.sum()})"
-            found = exact_targets & hit
+            found = exact_targets & hit & ~leaks
             # the target's distance, to what float Woop arithmetic gives at grazing incidence (the eye 2 degrees above the sheet
             # loses a factor 1 / sin(2 deg) = 28); the second sheet would be off by percents.  Where the reference hits too the
             # BITS are compared below.
@@ -111,7 +113,14 @@ def check_against_reference(r, tracer, table, rays, name, allow_prim_ties, exact
             f"{name}: another triangle on {ties.sum()} of {len(rays)} rays (instance differs on {(ties & (inst != ref['id_instance'])).sum()}); " \
             f"first ours {list(zip(inst[ties][:4], local[ties][:4]))} vs reference {list(zip(ref['id_instance'][ties][:4], ref['id_primitive'][ties][:4]))}"
         if ties.any():
-            off = ties & (np.abs(t / np.where(ref_hit, ref["t"], 1) - 1) >= 1e-6)
+            # (1e-6 of the distance or of the scene's own scale: a ray that starts a millimetre above two coplanar faces)
+            off = ties & (np.abs(t - ref["t"]) >= 1e-6 * np.maximum(np.maximum(np.abs(t), np.abs(rays[:, 0:3]).max(axis=1)), 1.0))
+            # a silhouette ray of a sphere / cylinder (discriminant or cap test within rounding of zero) may pass on one side and
+            # hit on the other, and then meets whatever lies behind: a handful in 10^5, never a pattern
+            ref_analytic = np.array([table[i][2] >= 0 for i in ref["id_instance"].clip(0, len(table) - 1)]) & ref_hit
+            silhouette = off & ref_analytic
+            assert silhouette.sum() <= max(2, 1e-4 * len(rays)), f"{name}: {silhouette.sum()} rays miss an analytic primitive the reference hits"
+            off &= ~silhouette
             first = [(rays[k].tolist(), float(t[k]), int(inst[k]), int(local[k]), float(ref["t"][k]), int(ref["id_instance"][k]), int(ref["id_primitive"][k]))
                      for k in np.flatnonzero(off)[:3]]
             assert not off.any(), f"{name} per_lane={per_lane}: a different triangle AND a different distance on {off.sum()} rays: (ray, t, inst, prim, ref t, ref inst, ref prim) {first}"
@@ -241,3 +250,65 @@ def test_wide_and_binary_trees_render_the_same_frame(pkg, scene, w, h, spp):
     differing = np.any(a != b, axis=2).mean()
     assert differing < 0.02, f"{scene}: {differing:.4f} of the pixels differ between the wide and the binary tree"
     assert abs(a.mean() / b.mean() - 1.0) < 2e-3
+
+
+@pytest.mark.parametrize("scene", ["dragon", "cornell-box", "matpreview", "synthetic_dielectrics_conductor_cylinder"])
+def test_warp_packets_find_the_same_hits(pkg, scene):
+    """traverse_packet.cuh (camera rays and first-vertex NEE rays on the binary tree): 32 consecutive rays walk the tree with one
+    shared node pointer and stack, each lane testing its own ray.  Same closest hit as the per-ray loop BIT FOR BIT (a tie
+    between two triangles at one t may name the other triangle), same occlusion verdict — for coherent bundles (a pinhole
+    camera, parallel shadow rays) AND for incoherent rays, where packets are slow but must still be right."""
+    path = os.path.join(GOLDEN, scene + ".b200scene") if scene.startswith("synthetic_") else pack(scene)
+    sc = pkg.Scene(path)
+    r = pkg.Renderer(sc, device=0)
+    rng = np.random.RandomState(17)
+    far = make_rays(rng.randn(20000, 3) * 50.0, rng.randn(20000, 3))
+    far[:, 3:6] = -far[:, 0:3] / np.linalg.norm(far[:, 0:3], axis=1, keepdims=True)
+    t, prim, _ = r.debug_trace(far)
+    pts = (far[:, 0:3] + t[:, None] * far[:, 3:6])[prim != 0xFFFFFFFF]
+    lo, hi = (pts.min(axis=0), pts.max(axis=0)) if len(pts) > 16 else (np.full(3, -5.0), np.full(3, 5.0))
+    centre, size = (lo + hi) / 2, np.linalg.norm(hi - lo)
+    # a pinhole camera: 96 x 96 pixels x 32 sub-pixel samples, consecutive rays = one pixel
+    eye = centre + np.float32([0.3, 0.5, 1.0]) * size
+    px = np.stack(np.meshgrid(np.arange(96), np.arange(96), indexing="ij"), axis=-1).reshape(-1, 1, 2) + rng.rand(96 * 96, 32, 2)
+    u, v = (px[..., 0] / 96 - 0.5).ravel(), (px[..., 1] / 96 - 0.5).ravel()
+    front = (centre - eye) / np.linalg.norm(centre - eye)
+    right = np.cross(front, [0, 1, 0]); right /= np.linalg.norm(right)
+    up = np.cross(right, front)
+    camera = make_rays(np.tile(eye, (len(u), 1)), front + 0.9 * (u[:, None] * right + v[:, None] * up))
+    # parallel shadow rays from the camera's hit points towards one light, in camera order
+    tc, pc, _ = r.debug_trace(camera)
+    hit = pc != 0xFFFFFFFF
+    origins = camera[hit, 0:3] + (tc[hit] * np.float32(0.999))[:, None] * camera[hit, 3:6]
+    shadow = make_rays(origins, np.tile(np.float32([0.4, 1.0, 0.2]), (len(origins), 1)), tmin=1e-4, tmax=np.float32(4.0) * size)
+    incoherent = random_rays(lo, hi, 40000, rng)
+    for name, rays in (("camera", camera), ("shadow", shadow), ("incoherent", incoherent)):
+        t0, p0, uv0 = r.debug_trace(rays)
+        t1, p1, uv1 = r.debug_trace(rays, packet_loop=True)
+        assert np.array_equal(p0 == 0xFFFFFFFF, p1 == 0xFFFFFFFF), f"{scene}/{name}: hit / miss differs on {((p0 == 0xFFFFFFFF) != (p1 == 0xFFFFFFFF)).sum()} rays"
+        same = p0 == p1
+        assert np.array_equal(t0[same].view(np.uint32), t1[same].view(np.uint32)) and np.array_equal(uv0[same], uv1[same]), f"{scene}/{name}: same primitive, other t"
+        assert (~same).mean() < 0.01, f"{scene}/{name}: {(~same).sum()} of {len(rays)} rays report another primitive"
+        if (~same).any():
+            assert np.abs(t0[~same] / t1[~same] - 1).max() < 1e-6, f"{scene}/{name}: another primitive at another distance"
+        o0 = r.debug_trace(rays, any_hit=True)[1] == 0
+        o1 = r.debug_trace(rays, any_hit=True, packet_loop=True)[1] == 0
+        assert np.array_equal(o0, o1), f"{scene}/{name}: occlusion differs on {(o0 != o1).sum()} rays"
+    r.close()
+
+
+@pytest.mark.parametrize("scene,w,h,spp", [("dragon", 160, 160, 64), ("cornell-box", 96, 96, 64), ("synthetic_opacity_masks", 64, 64, 64)])
+def test_frames_with_and_without_warp_packets(pkg, scene, w, h, spp, monkeypatch):
+    """B200PT_PACKETS=0 (every ray through the per-lane replacement loop) and the default render the same frame up to ties."""
+    path = os.path.join(GOLDEN, scene + ".b200scene") if scene.startswith("synthetic_") else pack(scene)
+    sc = pkg.Scene(path)
+    frames = []
+    for packets in ("0", "3", "15"):
+        monkeypatch.setenv("B200PT_PACKETS", packets)
+        r = pkg.Renderer(sc, device=0, max_paths_in_flight=1 << 22)
+        frames.append(r.Draw(width=w, height=h, spp=spp, seed=5))
+        r.close()
+    for f in frames[1:]:
+        differing = np.any(f != frames[0], axis=2).mean()
+        assert differing < 0.02, f"{scene}: {differing:.4f} of the pixels differ with warp packets"
+        assert abs(f.mean() / frames[0].mean() - 1.0) < 2e-3
