@@ -31,6 +31,8 @@ namespace {
 constexpr uint64_t kDefaultPathsInFlight = 1ull << 28;
 constexpr uint32_t kMaxRounds = 4096;                  // hard stop for max_depth = -1 scenes (RR ends paths long before)
 
+double g_upload_alloc_ms = 0.0, g_upload_copy_ms = 0.0; // B200PT_VERBOSE_CREATE: where UploadScene's time goes
+
 template <typename T>
 struct DeviceArray {
     T *ptr = nullptr;
@@ -48,9 +50,14 @@ struct DeviceArray {
         return cudaMalloc(&ptr, n * sizeof(T));
     }
     cudaError_t Upload(const std::vector<T> &src) {
+        const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = Alloc(src.size());
+        const auto t1 = std::chrono::steady_clock::now();
         if (e != cudaSuccess || src.empty()) return e;
-        return cudaMemcpy(ptr, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+        e = cudaMemcpy(ptr, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+        g_upload_alloc_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        g_upload_copy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+        return e;
     }
 };
 
@@ -66,7 +73,7 @@ constexpr uint32_t kFirstPollDepth = 4;
 struct Arena {
     PathQueue queue[2]{};
     ShadowQueue shadow{};
-    float *radiance = nullptr;       // 3 planes of `capacity` floats
+    float *radiance = nullptr;       // one float4 (r, g, b, unused) per sample slot (RadianceAdd, wavefront.cuh)
     uint32_t *bin_lists = nullptr;   // shading bins (scenes with several BSDF models): `capacity` entries per bin in use
     Counters *counters = nullptr;
     cudaStream_t stream = nullptr;   // owned side stream (a single-arena render runs on the caller's stream instead)
@@ -122,9 +129,11 @@ struct b200pt_context {
     int num_sms = 148;
     // launch tunables (overridable through the environment for experiments: B200PT_TOP_NODES, B200PT_REFILL, B200PT_CTAS_PER_SM)
     int top_nodes = 0, refill = 20, ctas_per_sm = 4, min_inner = 8; // top_nodes = 0: no shared-memory staging (profiles/r01_sweep_sel3_topnodes.log)
-    // B200PT_PACKETS (bit mask): 1 = camera rays as warp packets, 2 = first-vertex NEE rays towards a single delta light as warp
-    // packets, 4 = NEE packets whatever the emitters are, 8 = NEE packets at every depth (4 / 8: experiments)
-    int packets = 3;
+    // B200PT_PACKETS (bit mask): 1 = camera rays as warp packets (default: Dragon 38.96 -> 37.45 ms, 1080p 257 -> 249 ms),
+    // 2 = first-vertex NEE rays towards a single delta light as warp packets, 4 = NEE packets whatever the emitters are,
+    // 8 = NEE packets at every depth.  2 / 4 / 8 are measured variants, all slower than per-lane ray replacement (Dragon k_trace
+    // 28.4 -> 31.0 ms with 2: the NEE rays of neighbouring hits are not coherent enough, profiles/r02_sweep_packets.log).
+    int packets = 1;
     bool nee_coherent = false;    // one emitter, of a delta kind, and no area lights: the NEE rays of neighbouring hits run in parallel
     int tri_min = 8;              // B200PT_TRI_MIN: triangle postponing threshold of the wide traversal (LaunchConfig::tri_min)
     uint32_t wide_top_nodes = 0;  // nodes at the head of the wide node array that were laid out breadth-first
@@ -271,7 +280,7 @@ uint64_t WordsPerSlot(const b200pt_context *c) {
     const bool vol = c->scene.integrator.type == B200PT_INTEGRATOR_VOLPATH;
     const uint32_t shadow_per_vertex = c->scene.integrator.num_emitters + (c->scene.integrator.num_area_lights ? 1u : 0u);
     const uint64_t words_per_queue = 11 + (vol ? 4 : 0) + 4; // 10 floats + slot (+ medium, wo) + HitRec
-    return 2 * words_per_queue + 11 * std::max(1u, shadow_per_vertex) + 3 + __builtin_popcount(c->scene.integrator.shade_bins);
+    return 2 * words_per_queue + 11 * std::max(1u, shadow_per_vertex) + 4 + __builtin_popcount(c->scene.integrator.shade_bins);
 }
 
 // Carve the SoA queues of `arenas` arenas out of one allocation; each arena gets `wanted_per_arena` sample slots, or
@@ -319,7 +328,7 @@ int CarveWavefront(b200pt_context *c, uint64_t wanted_per_arena, int arenas) {
         sq.tmax = take(shadow_cap);
         sq.cr = take(shadow_cap), sq.cg = take(shadow_cap), sq.cb = take(shadow_cap);
         sq.slot = reinterpret_cast<uint32_t *>(take(shadow_cap));
-        ar.radiance = take(3 * capacity);
+        ar.radiance = take(4 * capacity); // 16-byte aligned: every array before it is a multiple of `capacity` (x 1024) floats
         const int bins_in_use = __builtin_popcount(c->scene.integrator.shade_bins);
         ar.bin_lists = bins_in_use ? reinterpret_cast<uint32_t *>(take(static_cast<uint64_t>(bins_in_use) * capacity)) : nullptr;
         ar.counters = c->counters.ptr + a;
@@ -505,8 +514,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
             run.bp.sample_begin = run.sample_begin + (ro.progressive ? ro.frame_index : 0u);
             run.bp.sample_count = std::min(samples_per_batch, ro.spp - run.sample_begin);
             const uint64_t nslots = static_cast<uint64_t>(run.bp.pixel_count) * run.bp.sample_count;
-            for (int ch = 0; ch < 3; ++ch)
-                check(cudaMemsetAsync(ar.radiance + static_cast<uint64_t>(ch) * capacity, 0, nslots * sizeof(float), la.stream));
+            check(cudaMemsetAsync(ar.radiance, 0, nslots * 4 * sizeof(float), la.stream));
             check(cudaMemsetAsync(ar.counters, 0, kCountersPerBatchBytes, la.stream)); // queue lengths + work counters
             launch(kClassPrimary, [&] {
                 const int n = LaunchPrimary(la, c->scene, run.bp, ar.queue[0], bins, ar.radiance, capacity, ar.counters);
@@ -660,7 +668,9 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     const auto t_upload = std::chrono::steady_clock::now();
     int rc = UploadScene(c.get(), *scene);
     if (rc != B200PT_OK) return rc;
-    if (verbose) fprintf(stderr, "[b200pt create] %-28s %8.1f ms\n", "UploadScene", since(t_upload));
+    if (verbose)
+        fprintf(stderr, "[b200pt create] %-28s %8.1f ms (cudaMalloc %.1f ms, cudaMemcpy %.1f ms, all creates of this process)\n", "UploadScene", since(t_upload),
+                g_upload_alloc_ms, g_upload_copy_ms);
     uint64_t capacity = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : kDefaultPathsInFlight;
     capacity = std::max<uint64_t>(capacity, 1024);
     c->max_capacity = std::min<uint64_t>(capacity, 1ull << 28);

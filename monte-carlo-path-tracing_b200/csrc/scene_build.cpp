@@ -22,6 +22,7 @@
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <numeric>
 #include <thread>
 #if defined(__SSE2__)
@@ -256,7 +257,7 @@ bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::ve
             return false;
         }
     const size_t first_triangle = tris->size();
-    tris->resize(first_triangle + mesh.num_triangles);
+    tris->resize(first_triangle + mesh.num_triangles); // within the capacity BuildHostScene reserved
     ParallelFor(mesh.num_triangles, [&](size_t f) {
         RawTriangle tri;
         tri.inst = inst;
@@ -358,10 +359,32 @@ struct BuildNode {
 // so a child's box and centre box come out of the parent's bins and no node is scanned twice.  Large nodes are binned and
 // partitioned by all threads together (the first levels of the tree hold most of the work), the subtrees below
 // kParallelNode references are then built one per thread.
+// Storage for up to `capacity` BuildNodes that is NOT touched until a node is handed out (a binary tree over n triangles may
+// need 2n - 1 nodes, a SAH tree with 2-4 triangles per leaf uses about half: 66 MB of page faults and constructors on Dragon).
+class BuildNodePool {
+public:
+    explicit BuildNodePool(size_t capacity) : data_(static_cast<BuildNode *>(malloc(std::max<size_t>(capacity, 1) * sizeof(BuildNode)))) {}
+    ~BuildNodePool() { free(data_); }
+    BuildNodePool(const BuildNodePool &) = delete;
+    BuildNodePool &operator=(const BuildNodePool &) = delete;
+    int32_t Allocate() {
+        const int32_t id = used_.fetch_add(1);
+        new (data_ + id) BuildNode();
+        return id;
+    }
+    BuildNode &operator[](size_t i) { return data_[i]; }
+    const BuildNode &operator[](size_t i) const { return data_[i]; }
+    size_t size() const { return static_cast<size_t>(used_.load()); }
+
+private:
+    BuildNode *data_;
+    std::atomic<int32_t> used_{0};
+};
+
 class BvhBuilder {
 public:
     BvhBuilder(const std::vector<Box> &boxes, const std::vector<V3> &centers, uint32_t max_leaf, float traversal_cost)
-        : max_leaf_(max_leaf), traversal_cost_(traversal_cost) {
+        : max_leaf_(max_leaf), traversal_cost_(traversal_cost), nodes_(boxes.size() * 2 + 1) { // at most 2n-1 nodes over n leaves
         const size_t n = boxes.size();
         refs_.resize(n);
         (void)centers; // = (lo + hi) * 0.5f, recomputed with the same rounding where needed (Ref::Centre)
@@ -372,7 +395,6 @@ public:
             memcpy(&r.lo.v[3], &id, 4);
             refs_[i] = r;
         });
-        nodes_.resize(n * 2 + 1); // a binary tree over n leaves has at most 2n-1 nodes
     }
 
     int32_t Build() {
@@ -388,7 +410,7 @@ public:
                 part_cbox[t].Grow(V3{rf.Centre(0), rf.Centre(1), rf.Centre(2)});
             }
         });
-        Task root{0, n, 0, Box(), Box(), next_node_.fetch_add(1)};
+        Task root{0, n, 0, Box(), Box(), nodes_.Allocate()};
         for (unsigned t = 0; t < threads; ++t) root.box.Grow(part_box[t]), root.cbox.Grow(part_cbox[t]);
         const int32_t root_id = root.id;
         PhaseTimer phase;
@@ -421,7 +443,7 @@ public:
         ParallelFor(n, [&](size_t i) { order_[i] = refs_[i].id(); });
         return root_id;
     }
-    const std::vector<BuildNode> &nodes() const { return nodes_; }
+    const BuildNodePool &nodes() const { return nodes_; }
     const std::vector<uint32_t> &order() const { return order_; }
 
 private:
@@ -570,8 +592,8 @@ private:
     }
 
     void ChildTasks(const Task &t, const Split &split, const Bins &bins, uint32_t mid, Task *l, Task *r) {
-        *l = Task{t.begin, mid, t.depth + 1, Box(), Box(), next_node_.fetch_add(1)};
-        *r = Task{mid, t.end, t.depth + 1, Box(), Box(), next_node_.fetch_add(1)};
+        *l = Task{t.begin, mid, t.depth + 1, Box(), Box(), nodes_.Allocate()};
+        *r = Task{mid, t.end, t.depth + 1, Box(), Box(), nodes_.Allocate()};
         if (split.axis >= 0) {
             for (uint32_t m = bins.mask[split.axis]; m != 0; m &= m - 1) {
                 const int b = __builtin_ctz(m);
@@ -663,8 +685,7 @@ private:
     float traversal_cost_;
     std::vector<Ref> refs_, scratch_;
     std::vector<uint32_t> order_;
-    std::vector<BuildNode> nodes_;
-    std::atomic<int32_t> next_node_{0};
+    BuildNodePool nodes_;
 };
 
 int32_t EncodeLeaf(uint32_t first, uint32_t count) { return ~static_cast<int32_t>((first << 3) | (count - 1)); }
@@ -680,7 +701,7 @@ void SetChildBox(BvhNode *node, int which, const Box &b) {
 }
 
 // Leaves with more than 8 triangles cannot be encoded; the builder never makes them for max_leaf <= 8.
-void FlattenBvh(const std::vector<BuildNode> &bn, int32_t root, uint32_t top_nodes, std::vector<BvhNode> *out) {
+void FlattenBvh(const BuildNodePool &bn, int32_t root, uint32_t top_nodes, std::vector<BvhNode> *out) {
     out->clear();
     if (root < 0) return;
     const Box empty; // inverted box: never hit
@@ -1073,6 +1094,12 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
 
     // ---- instances + geometry ----
     std::vector<RawTriangle> tris;
+    {
+        uint64_t total = 0; // one allocation for all meshes (176 B per triangle: growing by doubling copies it all again and again)
+        for (uint64_t i = 0; i < d.num_instances; ++i)
+            total += d.instances[i].type == B200PT_INST_MESHES ? d.instances[i].num_triangles : (d.instances[i].type == B200PT_INST_CUBE ? 12u : 2u);
+        tris.reserve(total);
+    }
     std::vector<float> inst_area(d.num_instances, 0.0f);
     hs->instances.resize(d.num_instances);
     Box scene_box;
@@ -1253,7 +1280,7 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             order = builder.order();
             phase("SAH build");
             if (wide) {
-                const std::vector<BuildNode> &bn = builder.nodes();
+                const BuildNodePool &bn = builder.nodes();
                 binary.resize(bn.size());
                 for (size_t i = 0; i < bn.size(); ++i) {
                     memcpy(binary[i].lo, &bn[i].box.lo, 12), memcpy(binary[i].hi, &bn[i].box.hi, 12);

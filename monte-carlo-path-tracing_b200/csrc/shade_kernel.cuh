@@ -415,9 +415,7 @@ __global__ void __launch_bounds__(kShadeThreads, B200PT_SHADE_MIN_CTAS(VOL, ONLY
             }
         }
         if (active && (Ladd.x != 0.0f || Ladd.y != 0.0f || Ladd.z != 0.0f)) {
-            radiance[slot] += Ladd.x;
-            radiance[capacity + slot] += Ladd.y;
-            radiance[2 * capacity + slot] += Ladd.z;
+            RadianceAdd(radiance, slot, Ladd.x, Ladd.y, Ladd.z);
         }
     }
 }

@@ -43,14 +43,18 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const __grid_constant__ D
     const uint32_t lane = threadIdx.x & 31u;
     TraversalCounters tc[2];
     uint32_t rays[2] = {0, 0};
+    // The paths are spread over ALL warps of the launch, as few per warp as that allows: the tail is bound by latency, not by
+    // lanes, and a warp walks the code of every one of its paths (traversal steps, leaves, shading) one after the other.
+    const uint32_t total_warps = gridDim.x * (kTailThreads / 32);
+    const uint32_t per_warp = min(32u, max(1u, (n + total_warps - 1u) / total_warps));
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&counters->work_tail, 32u);
+        if (lane == 0) base = atomicAdd(&counters->work_tail, per_warp);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + lane;
         PathVertex v;
-        bool alive = LoadPathVertex<VOL>(scene, q, i, i < n, &v);
+        bool alive = LoadPathVertex<VOL>(scene, q, i, lane < per_warp && i < n, &v);
         const uint32_t slot = v.slot;
         for (uint32_t depth = depth0; __any_sync(0xffffffffu, alive); ++depth) {
             PathNext next;
@@ -70,16 +74,12 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const __grid_constant__ D
                     HitRec unused;
                     ++rays[1];
                     if (!TraceSingle(scene, ray, true, opacity, Rng(ctr.x, ctr.y, ctr.z, bp.key, kRngDomainShadow), &unused, stats, &tc[1])) {
-                        radiance[slot] += sc.c.x;
-                        radiance[capacity + slot] += sc.c.y;
-                        radiance[2 * capacity + slot] += sc.c.z;
+                        RadianceAdd(radiance, slot, sc.c.x, sc.c.y, sc.c.z);
                     }
                 },
                 &next, &Ladd);
             if (was_alive && (Ladd.x != 0.0f || Ladd.y != 0.0f || Ladd.z != 0.0f)) {
-                radiance[slot] += Ladd.x;
-                radiance[capacity + slot] += Ladd.y;
-                radiance[2 * capacity + slot] += Ladd.z;
+                RadianceAdd(radiance, slot, Ladd.x, Ladd.y, Ladd.z);
             }
             if (depth >= kMaxTailDepth) alive = false; // the host loop's hard stop (renderer.cu: kMaxRounds)
             if (alive) { // extend the path: closest hit of the sampled direction
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const __grid_constant__ D
 
 void LaunchTail(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
                 float *radiance, uint32_t capacity, Counters *counters, uint32_t threshold) {
-    // enough CTAs for `threshold` paths at one path per lane, capped at a full machine
-    const int blocks = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(lc.blocks) * 2u, (threshold + kTailThreads - 1) / kTailThreads));
+    // enough CTAs for `threshold` paths at one path per WARP, capped at two waves of a full machine
+    const int blocks = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(lc.blocks) * 2u, (threshold + kTailThreads / 32 - 1) / (kTailThreads / 32)));
     if (scene.integrator.type == B200PT_INTEGRATOR_VOLPATH)
         k_tail<true><<<std::max(blocks, 1), kTailThreads, 0, lc.stream>>>(scene, bp, depth, q, which, radiance, capacity, counters, threshold, lc.stats);
     else

@@ -82,29 +82,58 @@ __device__ __forceinline__ uint32_t ShadeBinOfHit(const DeviceScene &scene, uint
 }
 
 // k_bin_hits: files every entry of a freshly traced path queue under the shading bin of its closest hit (one coalesced
-// pass over the hit records, one atomic per warp and bin).  Doing this inside the traversal kernels costs one atomic
-// per RAY, because rays finish one lane at a time there (volumetric-caustic: +50 % traversal time).
+// pass over the hit records).  Doing this inside the traversal kernels costs one atomic per RAY, because rays finish one
+// lane at a time there (volumetric-caustic: +50 % traversal time).
+// A CTA takes kBinChunk entries at a time: every thread loads its kBinPerThread hit records up front (independent loads in
+// flight), ranks them per bin with warp votes and SHARED-memory counters, and the CTA reserves its slice of each bin list with
+// ONE global atomic per bin and chunk.  (One global atomic per warp and bin — the first version — ran at the rate the L2
+// serialises adds to the same three or four addresses: 41 ms per 256-spp volumetric-caustic frame at 6 % issue utilisation,
+// profiles/r02_counters_volumetric-caustic_1024x1024x256.json.)
+constexpr int kBinPerThread = 8;
+constexpr uint32_t kBinChunk = kThreads * kBinPerThread;
 __global__ void __launch_bounds__(kThreads) k_bin_hits(const __grid_constant__ DeviceScene scene, const HitRec *hits, int which,
                                                        ShadeBins bins, Counters *counters) {
+    __shared__ uint32_t s_count[kNumShadeBins], s_base[kNumShadeBins];
     const uint32_t n = counters->queue[which];
     const uint32_t in_use = scene.integrator.shade_bins;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (uint32_t i0 = tid - lane; i0 < n; i0 += stride) {
-        const uint32_t i = i0 + lane;
-        uint32_t bin = kNumShadeBins; // none
-        if (i < n) {
-            const uint32_t prim = hits[i].prim;
-            // an escaped ray with nothing left to do (no environment map, no medium) is dropped here
-            if (prim != kPrimMiss || (in_use & 1u)) bin = ShadeBinOfHit(scene, prim);
+    for (uint32_t chunk = blockIdx.x * kBinChunk; chunk < n; chunk += gridDim.x * kBinChunk) {
+        if (threadIdx.x < kNumShadeBins) s_count[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t prim[kBinPerThread];
+#pragma unroll
+        for (int k = 0; k < kBinPerThread; ++k) {
+            const uint32_t i = chunk + k * kThreads + threadIdx.x;
+            prim[k] = i < n ? hits[i].prim : kPrimMiss;
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, bin);
-        if (bin == kNumShadeBins) continue;
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (static_cast<int>(lane) == leader) base = atomicAdd(&counters->bin_count[which][bin], __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        bins.lists[static_cast<uint64_t>(BinListIndex(in_use, bin)) * bins.capacity + base + __popc(peers & ((1u << lane) - 1u))] = i;
+        uint32_t packed_bin = 0, offset[kBinPerThread]; // 4 bits per entry
+#pragma unroll
+        for (int k = 0; k < kBinPerThread; ++k) {
+            const uint32_t i = chunk + k * kThreads + threadIdx.x;
+            uint32_t bin = kNumShadeBins; // none
+            // an escaped ray with nothing left to do (no environment map, no medium) is dropped here
+            if (i < n && (prim[k] != kPrimMiss || (in_use & 1u))) bin = ShadeBinOfHit(scene, prim[k]);
+            packed_bin |= bin << (4 * k);
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            offset[k] = 0;
+            if (bin != kNumShadeBins) {
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (static_cast<int>(lane) == leader) base = atomicAdd(&s_count[bin], __popc(peers));
+                offset[k] = __shfl_sync(peers, base, leader) + __popc(peers & ((1u << lane) - 1u));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kNumShadeBins && s_count[threadIdx.x] != 0)
+            s_base[threadIdx.x] = atomicAdd(&counters->bin_count[which][threadIdx.x], s_count[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kBinPerThread; ++k) {
+            const uint32_t bin = (packed_bin >> (4 * k)) & 15u;
+            if (bin != kNumShadeBins)
+                bins.lists[static_cast<uint64_t>(BinListIndex(in_use, bin)) * bins.capacity + s_base[bin] + offset[k]] = chunk + k * kThreads + threadIdx.x;
+        }
+        __syncthreads();
     }
 }
 
@@ -160,9 +189,7 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(con
             if (scene.integrator.id_envmap != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_envmap], cam.d);
             if (scene.integrator.id_sun != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[scene.integrator.id_sun], cam.d);
             if (L.x != 0.0f || L.y != 0.0f || L.z != 0.0f) {
-                radiance[slot] = L.x;
-                radiance[capacity + slot] = L.y;
-                radiance[2 * capacity + slot] = L.z;
+                RadianceSet(radiance, slot, L.x, L.y, L.z);
             }
             return;
         }
@@ -352,15 +379,10 @@ __global__ void __launch_bounds__(kThreads) k_settle(Counters *c, int which_queu
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         if (sq.tmax[j] != kShadowUnoccluded) continue;
         const uint32_t slot = sq.slot[j];
-        if (UNIQUE) {
-            radiance[slot] += sq.cr[j];
-            radiance[capacity + slot] += sq.cg[j];
-            radiance[2 * capacity + slot] += sq.cb[j];
-        } else {
-            atomicAdd(radiance + slot, sq.cr[j]);
-            atomicAdd(radiance + capacity + slot, sq.cg[j]);
-            atomicAdd(radiance + 2 * capacity + slot, sq.cb[j]);
-        }
+        if (UNIQUE)
+            RadianceAdd(radiance, slot, sq.cr[j], sq.cg[j], sq.cb[j]);
+        else
+            RadianceAtomicAdd(radiance, slot, sq.cr[j], sq.cg[j], sq.cb[j]);
     }
     __shared__ bool last;
     __syncthreads();
@@ -467,9 +489,10 @@ __global__ void __launch_bounds__(kThreads) k_resolve(const __grid_constant__ Ba
         float r = 0.0f, g = 0.0f, b = 0.0f;
         const uint32_t base = p * bp.sample_count;
         for (uint32_t s = lane; s < bp.sample_count; s += 32) {
-            r += fminf(radiance[base + s], 1.0f);
-            g += fminf(radiance[capacity + base + s], 1.0f);
-            b += fminf(radiance[2 * capacity + base + s], 1.0f);
+            const float4 v = reinterpret_cast<const float4 *>(radiance)[base + s];
+            r += fminf(v.x, 1.0f);
+            g += fminf(v.y, 1.0f);
+            b += fminf(v.z, 1.0f);
         }
         for (int o = 16; o > 0; o >>= 1) {
             r += __shfl_down_sync(0xffffffffu, r, o);

@@ -62,6 +62,26 @@ struct ClassCounters {
     unsigned long long rays, node_visits, prim_tests;
 };
 
+// Per-sample radiance: ONE float4 (r, g, b, unused) per sample slot.  The adds are scattered (a path's slot has nothing to do
+// with its queue position after the first bounce), and DRAM moves 32-byte sectors: three planes cost three sectors read and
+// written per add (volumetric-caustic: k_settle 47 ms per 256-spp frame at 190 B of DRAM traffic per NEE ray,
+// profiles/r02_counters_volumetric-caustic_1024x1024x256.json), one float4 costs one.
+#ifdef __CUDACC__
+__device__ __forceinline__ void RadianceAdd(float *radiance, uint32_t slot, float r, float g, float b) {
+    float4 *p = reinterpret_cast<float4 *>(radiance) + slot;
+    float4 v = *p;
+    v.x += r, v.y += g, v.z += b;
+    *p = v;
+}
+__device__ __forceinline__ void RadianceSet(float *radiance, uint32_t slot, float r, float g, float b) {
+    reinterpret_cast<float4 *>(radiance)[slot] = make_float4(r, g, b, 0.0f);
+}
+__device__ __forceinline__ void RadianceAtomicAdd(float *radiance, uint32_t slot, float r, float g, float b) {
+    float *p = radiance + 4ull * slot;
+    atomicAdd(p, r), atomicAdd(p + 1, g), atomicAdd(p + 2, b);
+}
+#endif
+
 struct Counters {             // device-resident
     uint32_t queue[2];        // entries in path queue 0 / 1 (zeroed per batch)
     uint32_t shadow;          // entries in the shadow queue

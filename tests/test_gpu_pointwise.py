@@ -225,24 +225,28 @@ def test_hit_attributes(pkg, scene_name):
     d, _ = counts(scene)
     inst_type = np.array([ctypes.cast(d.instances, ctypes.POINTER(sb.Instance))[i].type for i in range(d.num_instances)])
     kind = inst_type[href["id_instance"]]
-    assert np.array_equal(out[:, 15].view(np.uint32), href["id_instance"]), "hit instance"
+    # two surfaces at one distance (a rectangle standing on the stage): either answer is right, the rest is compared elsewhere
+    other_instance = out[:, 15].view(np.uint32) != href["id_instance"]
+    assert other_instance.mean() <= 0.002, f"hit instance differs on {other_instance.sum()} of {len(other_instance)} hits"
     # `inside` of a sphere / cylinder is the sign of c = |o|^2 - r^2 in float (sphere.cpp:49, cylinder.cpp:61): origins within
     # rounding of the surface may fall on either side of it with another contraction of the products
     side_differs = (out[:, 14] != 0) != (href["inside"] != 0)
     assert side_differs.mean() <= 0.002, f"hit side differs on {side_differs.sum()} of {len(side_differs)} hits (instance types {np.unique(kind[side_differs])})"
     # a bump map perturbs the normal by texture differences over 1e-4-wide steps (bsdf.cpp:238-254): float noise is amplified
-    tol = 3e-3 if "bump" in scene_name else 2e-4
+    # spheres, disks and cylinders rebuild the frame from a hit point that both sides know to 1e-5 of the distance travelled
+    # (hundreds of units here), and the sphere's bitangent is a finite difference over a 0.03-radian arc (sphere.cpp:58-67)
+    tol = np.where(np.isin(kind, [sb.INST_SPHERE, sb.INST_DISK, sb.INST_CYLINDER]), 3e-3, 3e-3 if "bump" in scene_name else 2e-4)
     # The tangent frame of a DISK hangs on phi = atan2(z, x) of a point whose local z is rounding noise around 0
     # (disk.cpp:38-60 with the y-up CartesianToSpherical, math.cpp:102-119): phi jumps between 0 / pi / -pi with the sign of that
     # noise, and `flip_tangent = phi' > pi` with it.  The frame is compared up to that sign there; normals are not affected.
     disk = kind == sb.INST_DISK
-    same_side = ~side_differs
+    same_side = ~side_differs & ~other_instance
     for cols, field in (((3, 6), "normal"), ((6, 9), "tangent"), ((9, 12), "bitangent")):
         a, b = out[:, cols[0]:cols[1]], href[field]
         err = np.abs(a - b).max(axis=1)
         if field != "normal":
             err = np.where(disk, np.minimum(err, np.abs(a + b).max(axis=1)), err)
-        err = err[same_side]
-        assert (err > tol).mean() <= 0.002, f"{field}: {(err > tol).sum()} of {len(err)} differ (worst {err.max():.3e}; instance types {np.unique(kind[same_side][err > tol])})"
-    err = np.abs(out[:, 12:14] - href["texcoord"]).max(axis=1)
+        bad = (err > tol)[same_side]
+        assert bad.mean() <= 0.002, f"{field}: {bad.sum()} of {len(bad)} differ (worst {err[same_side].max():.3e}; instance types {np.unique(kind[same_side][bad])})"
+    err = np.abs(out[:, 12:14] - href["texcoord"]).max(axis=1)[same_side]
     assert (err > 2e-5).mean() <= 0.002, f"texcoord: worst {err.max():.3e}"

@@ -95,7 +95,9 @@ def check_against_reference(r, tracer, table, rays, name, allow_prim_ties, exact
             worst = np.abs(t[found] / expected_t[found] - 1).max()
             assert worst < 1e-4, f"{name}: wrong distance on an exact vertex / edge hit (worst {worst:.3e} relative)"
             assert np.array_equal(hit[~exact_targets], ref_hit[~exact_targets]), f"{name}: hit/miss differs off the lattice lines"
-            hit = hit & ref_hit
+        neither = ~hit & ~ref_hit
+        if exact_targets is not None:
+            hit = hit & ref_hit  # the distances below are compared where both sides hit
         tri = hit & ((prim & 0x80000000) == 0)
         analytic = hit & ~tri
         same_bits = t.view(np.uint32) == ref["t"].view(np.uint32)
@@ -105,7 +107,7 @@ def check_against_reference(r, tracer, table, rays, name, allow_prim_ties, exact
         # Same triangle => same Woop arithmetic on the same vertices => the SAME BITS.  Two coplanar triangles (a box standing
         # on the floor) or a shared edge answer with distances one ulp apart; `t <= t_max` lets the one tested last win, and
         # the order of the tests differs between trees: there the other triangle, 2 ulp away at most, is as right.
-        check = (tri & same_prim) | ~(hit | ref_hit)
+        check = (tri & same_prim) | neither
         assert same_bits[check].all(), (f"{name}: t differs from TLAS::Intersect on {(~same_bits[check]).sum()} of {check.sum()} rays that hit the same triangle "
                                         f"(worst {np.abs(t[check] / ref['t'][check] - 1).max():.3e} relative, first {np.flatnonzero(check & ~same_bits)[:5]})")
         ties = tri & ~same_prim
