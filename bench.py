@@ -349,9 +349,13 @@ def kernel_table(counted, timed):
     alg_trace = algorithmic_bytes(counted["extend"], True) + algorithmic_bytes(counted["shadow"], False)
     return {
         "primary": {"ms": timed["primary"]["ms"], "launches": timed["primary"]["launches"], "rays": counted["primary"]["rays"],
+                    "box_tests": counted["primary"]["node_visits"], "primitive_tests": counted["primary"]["prim_tests"],
                     "algorithmic_bytes": alg_primary, "GBps": gbps(alg_primary, timed["primary"]["ms"])},
         "trace": {"ms": timed["extend"]["ms"], "launches": timed["extend"]["launches"], "closest_hit_rays": counted["extend"]["rays"],
-                  "any_hit_rays": counted["shadow"]["rays"], "algorithmic_bytes": alg_trace, "GBps": gbps(alg_trace, timed["extend"]["ms"])},
+                  "any_hit_rays": counted["shadow"]["rays"],
+                  "box_tests": {"closest_hit": counted["extend"]["node_visits"], "any_hit": counted["shadow"]["node_visits"]},
+                  "primitive_tests": {"closest_hit": counted["extend"]["prim_tests"], "any_hit": counted["shadow"]["prim_tests"]},
+                  "algorithmic_bytes": alg_trace, "GBps": gbps(alg_trace, timed["extend"]["ms"])},
         "shade": {"ms": timed["shade"]["ms"], "launches": timed["shade"]["launches"]},
         "other": {"ms": timed["other"]["ms"], "launches": timed["other"]["launches"]},
         "tail": {"ms": timed["tail"]["ms"], "launches": timed["tail"]["launches"]},

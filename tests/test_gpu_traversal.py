@@ -97,7 +97,7 @@ def check_against_reference(r, tracer, table, rays, name, allow_prim_ties, exact
             assert np.array_equal(hit[~exact_targets], ref_hit[~exact_targets]), f"{name}: hit/miss differs off the lattice lines"
         neither = ~hit & ~ref_hit
         if exact_targets is not None:
-            hit = hit & ref_hit  # the distances below are compared where both sides hit
+            hit = hit & ref_hit & ~leaks & ~ref_leaks  # the distances below are compared where both sides met the first sheet
         tri = hit & ((prim & 0x80000000) == 0)
         analytic = hit & ~tri
         same_bits = t.view(np.uint32) == ref["t"].view(np.uint32)
