@@ -90,7 +90,7 @@ struct b200pt_context {
     DeviceScene scene{};
     b200pt_stats stats{};
 
-    DeviceArray<uint8_t> tree;       // binary nodes, then triangle vertices: ONE allocation (one L2 access-policy window covers both)
+    DeviceArray<uint8_t> tree;       // binary nodes, then triangle vertices, in one allocation
     DeviceArray<WideNode> wide_nodes;
     DeviceArray<TriShade> tri_shade;
     DeviceArray<uint8_t> tri_bsdf_type;
@@ -133,12 +133,7 @@ struct b200pt_context {
     // 8 = NEE packets at every depth.  2 / 4 / 8 are measured variants, all slower than per-lane ray replacement (Dragon k_trace
     // 28.4 -> 31.0 ms with 2: the NEE rays of neighbouring hits are not coherent enough, profiles/r02_sweep_packets.log).
     int packets = 1;
-    // B200PT_L2_PERSIST_MB: the first so many MB of the tree (nodes, then triangle vertices: one allocation) are marked as
-    // persisting in L2 for the render streams (cudaAccessPolicyWindow), so that the streaming traffic of the ray queues does
-    // not evict them.  0 = off.
-    int l2_persist_mb = 0;
-    void *l2_window_base = nullptr;
-    size_t l2_window_bytes = 0;
+
     bool nee_coherent = false;    // one emitter, of a delta kind, and no area lights: the NEE rays of neighbouring hits run in parallel
     int tri_min = 8;              // B200PT_TRI_MIN: triangle postponing threshold of the wide traversal (LaunchConfig::tri_min)
     uint32_t wide_top_nodes = 0;  // nodes at the head of the wide node array that were laid out breadth-first
@@ -202,8 +197,6 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     CU_CHECK(c, c->tree.Alloc(node_bytes + vert_bytes));
     if (!h.nodes.empty()) CU_CHECK(c, cudaMemcpy(c->tree.ptr, h.nodes.data(), h.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
     if (vert_bytes) CU_CHECK(c, cudaMemcpy(c->tree.ptr + node_bytes, h.tri_verts.data(), vert_bytes, cudaMemcpyHostToDevice));
-    c->l2_window_base = c->tree.ptr;
-    c->l2_window_bytes = node_bytes + vert_bytes;
     CU_CHECK(c, c->wide_nodes.Upload(h.wide_nodes));
     CU_CHECK(c, c->tri_shade.Upload(h.tri_shade));
     CU_CHECK(c, c->tri_bsdf_type.Upload(h.tri_bsdf_type));
@@ -288,7 +281,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
 uint64_t WordsPerSlot(const b200pt_context *c) {
     const bool vol = c->scene.integrator.type == B200PT_INTEGRATOR_VOLPATH;
     const uint32_t shadow_per_vertex = c->scene.integrator.num_emitters + (c->scene.integrator.num_area_lights ? 1u : 0u);
-    const uint64_t words_per_queue = 11 + (vol ? 4 : 0) + 4; // 10 floats + slot (+ medium, wo) + HitRec
+    const uint64_t words_per_queue = 12 + (vol ? 4 : 0) + 4; // three float4 (+ wo) + HitRec
     return 2 * words_per_queue + 11 * std::max(1u, shadow_per_vertex) + 4 + __builtin_popcount(c->scene.integrator.shade_bins);
 }
 
@@ -320,16 +313,10 @@ int CarveWavefront(b200pt_context *c, uint64_t wanted_per_arena, int arenas) {
         for (int k = 0; k < 2; ++k) {
             PathQueue &q = ar.queue[k];
             q.hit = reinterpret_cast<HitRec *>(take(4 * capacity)); // first: keeps 16-byte alignment
-            q.ox = take(capacity), q.oy = take(capacity), q.oz = take(capacity);
-            q.dx = take(capacity), q.dy = take(capacity), q.dz = take(capacity);
-            q.tr = take(capacity), q.tg = take(capacity), q.tb = take(capacity);
-            q.pdf = take(capacity);
-            q.slot = reinterpret_cast<uint32_t *>(take(capacity));
-            q.medium = nullptr, q.wx = q.wy = q.wz = nullptr;
-            if (vol) {
-                q.medium = reinterpret_cast<uint32_t *>(take(capacity));
-                q.wx = take(capacity), q.wy = take(capacity), q.wz = take(capacity);
-            }
+            q.o_pdf = reinterpret_cast<float4 *>(take(4 * capacity));
+            q.d_slot = reinterpret_cast<float4 *>(take(4 * capacity));
+            q.t_medium = reinterpret_cast<float4 *>(take(4 * capacity));
+            q.wo = vol ? reinterpret_cast<float4 *>(take(4 * capacity)) : nullptr;
         }
         ShadowQueue &sq = ar.shadow;
         sq.ox = take(shadow_cap), sq.oy = take(shadow_cap), sq.oz = take(shadow_cap);
@@ -344,19 +331,6 @@ int CarveWavefront(b200pt_context *c, uint64_t wanted_per_arena, int arenas) {
     }
     c->capacity = capacity;
     return B200PT_OK;
-}
-
-// Marks the head of the tree allocation as persisting in L2 for work submitted to `stream` (no-op when the knob is off).
-void ApplyL2Window(b200pt_context *c, cudaStream_t stream) {
-    if (c->l2_persist_mb <= 0 || c->l2_window_base == nullptr || c->l2_window_bytes == 0) return;
-    cudaStreamAttrValue attr{};
-    attr.accessPolicyWindow.base_ptr = c->l2_window_base;
-    attr.accessPolicyWindow.num_bytes = std::min<size_t>(c->l2_window_bytes, static_cast<size_t>(c->l2_persist_mb) << 20);
-    attr.accessPolicyWindow.hitRatio = 1.0f;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr); // best effort: an unsupported window is not an error
-    cudaGetLastError();
 }
 
 struct ResolvedOpts {
@@ -438,7 +412,6 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     c->timed.clear();
     c->events_used = 0;
     for (uint64_t &n : c->class_launches) n = 0;
-    ApplyL2Window(c, stream);
     CU_CHECK(c, cudaEventRecord(c->ev_begin, stream));
 
     // Visibility pre-pass: which of this rank's tiles can see geometry at all.  Escaped camera rays only carry radiance
@@ -502,10 +475,7 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     for (int a = 0; a < S; ++a) {
         runs[a].stream = S > 1 ? c->arenas[a].stream : stream;
         runs[a].bp = bp;
-        if (S > 1) {
-            ApplyL2Window(c, runs[a].stream);
-            CU_CHECK(c, cudaStreamWaitEvent(runs[a].stream, c->ev_fork, 0));
-        }
+        if (S > 1) CU_CHECK(c, cudaStreamWaitEvent(runs[a].stream, c->ev_fork, 0));
     }
     cudaError_t issue_error = cudaSuccess;
     // Issues the next piece of work of arena `a` (the start of a batch, or one bounce of the batch in flight);
@@ -677,12 +647,6 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
     c->tile_cull = env_int("B200PT_TILE_CULL", 1, 0, 1) != 0;
     c->tail_paths = static_cast<uint32_t>(env_int("B200PT_TAIL_PATHS", static_cast<int>(c->tail_paths), 0, 1 << 24));
     c->packets = env_int("B200PT_PACKETS", c->packets, 0, 15);
-    if (env_int("B200PT_PUSH_PREFETCH", 0, 0, 1)) c->min_inner |= 0x100; // measured variant, see TraversePersistent
-    c->l2_persist_mb = env_int("B200PT_L2_PERSIST_MB", c->l2_persist_mb, 0, 4096);
-    if (c->l2_persist_mb > 0) {
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(c->l2_persist_mb) << 20); // clamped by the driver to what the device allows
-        cudaGetLastError();
-    }
 
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();

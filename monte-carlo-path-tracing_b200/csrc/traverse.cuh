@@ -252,9 +252,6 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                                                    TraversalCounters *counters, uint32_t *rays_traced) {
     int stack[kStackSize];
     int sp = 0, cur = kSentinel;
-    // measured variant (B200PT_PUSH_PREFETCH, bit 8 of the argument): a node that goes on the stack is prefetched into L1
-    const bool push_prefetch = (min_inner_lanes & 0x100) != 0;
-    min_inner_lanes &= 0xff;
 #if B200PT_SPECULATIVE
     int postponed = 0; // a leaf link (< 0) waiting to be intersected, 0 = none
 #endif
@@ -332,14 +329,8 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                     cur = sp > 0 ? stack[--sp] : kSentinel;
                 } else if (hit0 && hit1) {
                     const bool swap = c1min < c0min;
-                    const int far_child = swap ? child0 : child1;
-                    stack[sp++] = far_child;
+                    stack[sp++] = swap ? child0 : child1;
                     cur = swap ? child1 : child0;
-                    if (push_prefetch) {
-                        const void *target = far_child >= 0 ? static_cast<const void *>(scene.nodes + far_child)
-                                                            : static_cast<const void *>(scene.tri_verts + (static_cast<uint32_t>(~far_child) >> 3));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(target));
-                    }
                 } else {
                     cur = hit0 ? child0 : child1;
                 }
