@@ -281,7 +281,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
 uint64_t WordsPerSlot(const b200pt_context *c) {
     const bool vol = c->scene.integrator.type == B200PT_INTEGRATOR_VOLPATH;
     const uint32_t shadow_per_vertex = c->scene.integrator.num_emitters + (c->scene.integrator.num_area_lights ? 1u : 0u);
-    const uint64_t words_per_queue = 12 + (vol ? 4 : 0) + 4; // three float4 (+ wo) + HitRec
+    const uint64_t words_per_queue = 11 + (vol ? 4 : 0) + 4; // 10 floats + slot (+ medium, wo) + HitRec
     return 2 * words_per_queue + 11 * std::max(1u, shadow_per_vertex) + 4 + __builtin_popcount(c->scene.integrator.shade_bins);
 }
 
@@ -313,10 +313,16 @@ int CarveWavefront(b200pt_context *c, uint64_t wanted_per_arena, int arenas) {
         for (int k = 0; k < 2; ++k) {
             PathQueue &q = ar.queue[k];
             q.hit = reinterpret_cast<HitRec *>(take(4 * capacity)); // first: keeps 16-byte alignment
-            q.o_pdf = reinterpret_cast<float4 *>(take(4 * capacity));
-            q.d_slot = reinterpret_cast<float4 *>(take(4 * capacity));
-            q.t_medium = reinterpret_cast<float4 *>(take(4 * capacity));
-            q.wo = vol ? reinterpret_cast<float4 *>(take(4 * capacity)) : nullptr;
+            q.ox = take(capacity), q.oy = take(capacity), q.oz = take(capacity);
+            q.dx = take(capacity), q.dy = take(capacity), q.dz = take(capacity);
+            q.tr = take(capacity), q.tg = take(capacity), q.tb = take(capacity);
+            q.pdf = take(capacity);
+            q.slot = reinterpret_cast<uint32_t *>(take(capacity));
+            q.medium = nullptr, q.wx = q.wy = q.wz = nullptr;
+            if (vol) {
+                q.medium = reinterpret_cast<uint32_t *>(take(capacity));
+                q.wx = take(capacity), q.wy = take(capacity), q.wz = take(capacity);
+            }
         }
         ShadowQueue &sq = ar.shadow;
         sq.ox = take(shadow_cap), sq.oy = take(shadow_cap), sq.oz = take(shadow_cap);

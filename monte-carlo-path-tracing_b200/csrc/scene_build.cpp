@@ -739,7 +739,7 @@ void FlattenBvh(const BuildNodePool &bn, int32_t root, uint32_t top_nodes, std::
         if (bn[bn[id].left].left >= 0) stack.push_back(bn[id].left);
     }
     out->resize(order.size());
-    for (size_t i = 0; i < order.size(); ++i) {
+    ParallelFor(order.size(), [&](size_t i) {
         const BuildNode &src = bn[order[i]];
         BvhNode n{};
         const BuildNode &l = bn[src.left], &r = bn[src.right];
@@ -748,7 +748,7 @@ void FlattenBvh(const BuildNodePool &bn, int32_t root, uint32_t top_nodes, std::
         n.child0 = l.left >= 0 ? out_index[src.left] : EncodeLeaf(l.first, l.count);
         n.child1 = r.left >= 0 ? out_index[src.right] : EncodeLeaf(r.first, r.count);
         (*out)[i] = n;
-    }
+    });
 }
 
 // Number of inner-node levels of a flattened tree = the most entries a traversal can have on its stack, plus one.

@@ -333,16 +333,14 @@ __device__ __forceinline__ bool LoadPathVertex(const DeviceScene &scene, const P
         if (!VOL && v->hit.prim == kPrimMiss && scene.integrator.id_envmap == kInvalid) alive = false;
     }
     if (alive) {
-        const float4 o = qin.o_pdf[i], d = qin.d_slot[i], t = qin.t_medium[i];
-        v->ray.o = mk3(o.x, o.y, o.z);
-        v->ray.d = mk3(d.x, d.y, d.z);
-        v->att = mk3(t.x, t.y, t.z);
-        v->pdf_sample = o.w;
-        v->slot = __float_as_uint(d.w);
+        v->ray.o = mk3(qin.ox[i], qin.oy[i], qin.oz[i]);
+        v->ray.d = mk3(qin.dx[i], qin.dy[i], qin.dz[i]);
+        v->att = mk3(qin.tr[i], qin.tg[i], qin.tb[i]);
+        v->pdf_sample = qin.pdf[i];
+        v->slot = qin.slot[i];
         if (VOL) {
-            const float4 w = qin.wo[i];
-            v->ray_medium = __float_as_uint(t.w);
-            v->wo_prev = mk3(w.x, w.y, w.z);
+            v->ray_medium = qin.medium[i];
+            v->wo_prev = mk3(qin.wx[i], qin.wy[i], qin.wz[i]);
         }
     }
     return alive;
@@ -406,10 +404,15 @@ __global__ void __launch_bounds__(kShadeThreads, B200PT_SHADE_MIN_CTAS(VOL, ONLY
         alive = ShadeVertex<VOL, ONLY>(scene, bp, depth, alive, v, [&](const ShadowCandidate &sc) { PushShadow(sc, slot, sq, counters); }, &next, &Ladd);
         const uint32_t out = WarpAppend(alive, &counters->queue[which_in ^ 1]);
         if (alive) {
-            qout.o_pdf[out] = make_float4(next.o.x, next.o.y, next.o.z, next.pdf);
-            qout.d_slot[out] = make_float4(next.d.x, next.d.y, next.d.z, __uint_as_float(slot));
-            qout.t_medium[out] = make_float4(next.att.x, next.att.y, next.att.z, __uint_as_float(VOL ? next.medium : kInvalid));
-            if (VOL) qout.wo[out] = make_float4(next.wo.x, next.wo.y, next.wo.z, 0.0f);
+            qout.ox[out] = next.o.x, qout.oy[out] = next.o.y, qout.oz[out] = next.o.z;
+            qout.dx[out] = next.d.x, qout.dy[out] = next.d.y, qout.dz[out] = next.d.z;
+            qout.tr[out] = next.att.x, qout.tg[out] = next.att.y, qout.tb[out] = next.att.z;
+            qout.pdf[out] = next.pdf;
+            qout.slot[out] = slot;
+            if (VOL) {
+                qout.medium[out] = next.medium;
+                qout.wx[out] = next.wo.x, qout.wy[out] = next.wo.y, qout.wz[out] = next.wo.z;
+            }
         }
         if (active && (Ladd.x != 0.0f || Ladd.y != 0.0f || Ladd.z != 0.0f)) {
             RadianceAdd(radiance, slot, Ladd.x, Ladd.y, Ladd.z);

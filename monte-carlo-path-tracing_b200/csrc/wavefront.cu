@@ -194,10 +194,15 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_primary(con
             return;
         }
         const uint32_t idx = AppendCoalesced(&counters->queue[0]);
-        q.o_pdf[idx] = make_float4(cam.o.x, cam.o.y, cam.o.z, 0.0f);
-        q.d_slot[idx] = make_float4(cam.d.x, cam.d.y, cam.d.z, __uint_as_float(slot));
-        q.t_medium[idx] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(kInvalid));
-        if (q.wo != nullptr) q.wo[idx] = make_float4(-cam.d.x, -cam.d.y, -cam.d.z, 0.0f);
+        q.ox[idx] = cam.o.x, q.oy[idx] = cam.o.y, q.oz[idx] = cam.o.z;
+        q.dx[idx] = cam.d.x, q.dy[idx] = cam.d.y, q.dz[idx] = cam.d.z;
+        q.tr[idx] = 1.0f, q.tg[idx] = 1.0f, q.tb[idx] = 1.0f;
+        q.pdf[idx] = 0.0f;
+        q.slot[idx] = slot;
+        if (q.medium != nullptr) {
+            q.medium[idx] = kInvalid;
+            q.wx[idx] = -cam.d.x, q.wy[idx] = -cam.d.y, q.wz[idx] = -cam.d.z;
+        }
         q.hit[idx] = hit;
     };
     if constexpr (LAYOUT == kLayoutBinary) {
@@ -242,12 +247,11 @@ __global__ void __launch_bounds__(kThreads, B200PT_TRACE_MIN_CTAS) k_trace(const
     auto fetch = [&](uint32_t i, Ray *ray, uint3 *ctr, bool *any) {
         ray->tmin = kEpsilonDistance;
         if (i < n_extend) {
-            const float4 o = q.o_pdf[i], d = q.d_slot[i];
-            ray->o = mk3(o.x, o.y, o.z);
-            ray->d = mk3(d.x, d.y, d.z);
+            ray->o = mk3(q.ox[i], q.oy[i], q.oz[i]);
+            ray->d = mk3(q.dx[i], q.dy[i], q.dz[i]);
             ray->tmax = kMaxFloat;
             *any = false;
-            if (OPACITY) *ctr = SlotCounter(bp, __float_as_uint(d.w), depth);
+            if (OPACITY) *ctr = SlotCounter(bp, q.slot[i], depth);
         } else {
             const uint32_t j = i - n_extend;
             ray->o = mk3(sq.ox[j], sq.oy[j], sq.oz[j]);

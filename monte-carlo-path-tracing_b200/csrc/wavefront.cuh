@@ -24,15 +24,14 @@ constexpr int kTileSize = 8;                  // pixels; tiles are dealt round-r
 constexpr int kTilePixels = kTileSize * kTileSize;
 
 // One path segment waiting for its closest hit / shading.  Arrays of `capacity` elements.
-// Structure of arrays of 16-BYTE records: a warp that walks the queue in order still moves full 128-byte lines per load, and
-// a warp that GATHERS entries (the shading kernels of binned scenes read them through per-BSDF index lists, every shading
-// kernel skips dead entries) touches 4-5 sectors per entry instead of one per scalar — 19 with one array per float
-// (volumetric-caustic: k_shade at 20 % L2 hit rate, profiles/r02_counters_volumetric-caustic_1024x1024x256.json).
 struct PathQueue {
-    float4 *o_pdf;            // ray origin, pdf of the direction sample that produced this ray (MIS at the next vertex)
-    float4 *d_slot;           // ray direction (unit), sample slot inside the batch (bits)
-    float4 *t_medium;         // path throughput ("attenuation" in path.cpp); volpath: medium the ray was scattered in (bits), or kInvalid
-    float4 *wo;               // volpath only: `wo` of the last surface vertex (stale-wo behaviour of volpath.cpp)
+    float *ox, *oy, *oz;      // ray origin
+    float *dx, *dy, *dz;      // ray direction (unit)
+    float *tr, *tg, *tb;      // path throughput ("attenuation" in path.cpp)
+    float *pdf;               // pdf of the direction sample that produced this ray (MIS at the next vertex)
+    uint32_t *slot;           // sample slot inside the batch
+    uint32_t *medium;         // volpath: medium the ray was scattered in, or kInvalid if it left a surface
+    float *wx, *wy, *wz;      // volpath: `wo` of the last surface vertex (stale-wo behaviour of volpath.cpp)
     HitRec *hit;              // closest hit, written by k_primary / k_trace
 };
 
