@@ -250,8 +250,23 @@ template <bool MIXED, bool STATS, bool OPACITY, bool TOP, typename Fetch, typena
 __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, const float4 *top, int num_top, uint32_t num_rays,
                                                    uint32_t *work_counter, int refill_threshold, int min_inner_lanes, uint2 key, Fetch fetch, Finish finish,
                                                    TraversalCounters *counters, uint32_t *rays_traced) {
-    int stack[kStackSize];
-    int sp = 0, cur = kSentinel;
+    // The top of the traversal stack lives in a register: a pop hands `tos` over at once and re-loads the next one in the
+    // background, so the local-memory load is off the chain  pop -> node address -> node fetch  that bounds a step.
+    // stack[0] is a permanent sentinel, stack[1 + i] holds entry i below the top (Pop / Push below).
+    int stack[kStackSize + 1];
+    int sp = 0, cur = kSentinel, tos = kSentinel;
+    stack[0] = kSentinel;
+    auto Push = [&](int node) {
+        stack[sp] = tos; // sp == 0: rewrites the sentinel with itself
+        tos = node;
+        ++sp;
+    };
+    auto Pop = [&]() {
+        const int node = tos; // kSentinel when the stack is empty
+        sp = max(sp - 1, 0);
+        tos = stack[sp];
+        return node;
+    };
 #if B200PT_SPECULATIVE
     int postponed = 0; // a leaf link (< 0) waiting to be intersected, 0 = none
 #endif
@@ -281,7 +296,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                 hit.t = ray.tmax, hit.prim = kPrimMiss, hit.u = hit.v = 0.0f;
                 found = false;
                 has = true;
-                sp = 0;
+                sp = 0, tos = kSentinel;
                 cur = scene.num_nodes ? 0 : kSentinel;
                 ++rays_traced[any];
                 // Analytic primitives (spheres, disks, cylinders) are few: tested linearly up front.
@@ -325,14 +340,16 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                 const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), ray.tmin));
                 const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), ray.tmax));
                 const bool hit0 = c0min <= c0max, hit1 = c1min <= c1max;
-                if (!hit0 && !hit1) {
-                    cur = sp > 0 ? stack[--sp] : kSentinel;
-                } else if (hit0 && hit1) {
-                    const bool swap = c1min < c0min;
-                    stack[sp++] = swap ? child0 : child1;
-                    cur = swap ? child1 : child0;
-                } else {
-                    cur = hit0 ? child0 : child1;
+                // Straight-line selection of the next node (three short predicated groups, no three-way branch: the lanes that
+                // missed both boxes used to pop in a pass of their own at 2.6 active lanes, profiles/r02_k_trace_source.csv.gz).
+                const bool both = hit0 && hit1, none = !(hit0 || hit1);
+                const bool swap = c1min < c0min;
+                if (both) Push(swap ? child0 : child1);
+                const int next = (hit1 && (swap || !hit0)) ? child1 : child0; // the nearer of two hits, or the only one
+                cur = none ? tos : next;
+                if (none) {
+                    sp = max(sp - 1, 0);
+                    tos = stack[sp];
                 }
                 // Most lanes of an incoherent warp reach their next leaf within a few steps while a few stragglers
                 // keep descending; once fewer than `min_inner_lanes` lanes are still walking inner nodes the warp
@@ -342,7 +359,7 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                 // inner nodes with the rest of the warp; it only waits once it holds a second one.
                 if (cur < 0 && postponed == 0) {
                     postponed = cur;
-                    cur = sp > 0 ? stack[--sp] : kSentinel;
+                    cur = Pop();
                 }
 #endif
                 if (__popc(__activemask()) < min_inner_lanes) break;
@@ -387,14 +404,14 @@ __device__ __forceinline__ void TraversePersistent(const DeviceScene &scene, con
                     postponed = 0;
                 } else if (cur < 0) {
                     link = cur;
-                    cur = sp > 0 ? stack[--sp] : kSentinel;
+                    cur = Pop();
                 }
                 if (link < 0) process_leaf(link);
             }
 #else
             if (cur < 0) {
                 const int link = cur;
-                cur = sp > 0 ? stack[--sp] : kSentinel;
+                cur = Pop();
                 process_leaf(link);
             }
 #endif
