@@ -542,9 +542,10 @@ def run_b200(args, workload):
         config.update({"tile_split": f"{world} rank(s), 8x8-pixel tiles dealt round-robin, one NCCL all-gather per step" if world > 1 else "single GPU",
                        "rng": "Philox4x32-10 keyed by seed, counter = (pixel, sample, depth)", "scene_create_s": create_s,
                        "tile_visibility_prepass": {
-                           "what": "8x8 screen tiles whose camera-ray pyramid provably misses every box of a 384-box BVH cut are not traced "
+                           "what": "8x8 screen tiles whose camera-ray pyramid provably misses every box of a 384-box BVH cut, and pixels whose "
+                                   "pyramid misses every box of a 4096-box cut, are not traced "
                                    "(exact: the frame is bit-identical, tests/test_gpu_parity.py); the pre-pass runs inside the timed region",
-                           "active_tiles": counted["active_tiles"], "local_tiles": counted["local_tiles"],
+                           "active_tiles": counted["active_tiles"], "local_tiles": counted["local_tiles"], "active_pixels": counted["active_pixels"],
                            "value_with_prepass_off": (samples_per_step / min(no_cull_ms) / 1e3) if no_cull_ms else None}})
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,

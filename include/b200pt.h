@@ -245,7 +245,8 @@ typedef struct b200pt_stats {
     uint64_t num_bvh_nodes, num_triangles, num_prims;
     uint32_t bvh_width;          /* 2 = binary layout (64-byte nodes, default), 8 = compressed wide layout (80-byte nodes) */
     uint32_t bvh_depth;          /* levels of the wide tree (0 for the binary layout) */
-    uint64_t local_tiles, active_tiles; /* 8x8 tiles owned by this rank / those that passed the visibility pre-pass */
+    uint64_t local_tiles, active_tiles; /* 8x8 tiles owned by this rank / those with a pixel that passed the visibility pre-pass */
+    uint64_t active_pixels;      /* pixels of this rank that passed the visibility pre-pass (= the pixels camera rays are traced for) */
     b200pt_kernel_stats primary; /* k_primary: ray-gen + closest hit of camera rays */
     b200pt_kernel_stats extend;  /* k_trace  : closest hit of bounce rays + any-hit of NEE rays in ONE launch per bounce;
                                     ms / launches cover the whole launch, the counters only the bounce rays */

@@ -65,7 +65,7 @@ class Stats(ctypes.Structure):
                 ("bvh_gpu_ms", ctypes.c_double), ("samples", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
                 ("num_bvh_nodes", ctypes.c_uint64), ("num_triangles", ctypes.c_uint64), ("num_prims", ctypes.c_uint64),
                 ("bvh_width", ctypes.c_uint32), ("bvh_depth", ctypes.c_uint32),
-                ("local_tiles", ctypes.c_uint64), ("active_tiles", ctypes.c_uint64),
+                ("local_tiles", ctypes.c_uint64), ("active_tiles", ctypes.c_uint64), ("active_pixels", ctypes.c_uint64),
                 ("primary", KernelStats), ("extend", KernelStats), ("shadow", KernelStats), ("shade", KernelStats),
                 ("other", KernelStats), ("tail", KernelStats)]
 

@@ -169,6 +169,7 @@ struct DeviceScene {
     // A cut through the top of the BVH (plus the boxes of the analytic primitives): min.xyz max.xyz per box, together
     // they cover all geometry.  Screen tiles whose pyramid of camera rays misses every box trace nothing (k_cull_tiles).
     const float *cull_boxes;     uint32_t num_cull_boxes;
+    const float *fine_cull_boxes; uint32_t num_fine_cull_boxes;
     DIntegrator integrator;
 };
 

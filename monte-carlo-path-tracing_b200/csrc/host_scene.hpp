@@ -31,7 +31,8 @@ struct HostScene {
     std::vector<float> light_tri_cdf;
     std::vector<uint32_t> light_tri_ids;
     float scene_bmin[3], scene_bmax[3];
-    std::vector<float> cull_boxes;   // 6 floats per box (DeviceScene::cull_boxes)
+    std::vector<float> cull_boxes;   // 6 floats per box (DeviceScene::cull_boxes): coarse cover, rejects whole screen tiles
+    std::vector<float> fine_cull_boxes; // finer cover (<= 4096 boxes + analytic primitives): rejects single pixels
     DIntegrator integrator{};
     b200pt_camera camera{};
     double bvh_build_ms = 0.0;  // whole BVH stage (boxes, build, flatten)

@@ -104,7 +104,9 @@ struct b200pt_context {
     DeviceArray<float> envmap_tables, kc_brdf, kc_albedo, cdf_area_light, light_tri_cdf;
     DeviceArray<uint32_t> map_area_light_instance, light_tri_ids;
     DeviceArray<float> cull_boxes;
-    DeviceArray<uint32_t> tile_flags, tile_list; // visibility pre-pass: per local tile flag; ascending active list + count
+    DeviceArray<float> fine_cull_boxes;
+    DeviceArray<unsigned long long> tile_masks;  // visibility pre-pass: per local tile, the pixels that can see geometry
+    DeviceArray<uint32_t> pixel_list;            // ... their local indices in ascending order, followed by {pixels, non-empty tiles}
     bool tile_cull = true;        // B200PT_TILE_CULL=0 turns the pre-pass off
     int shade_only = -1;          // see LaunchConfig::shade_only
     uint32_t tail_paths = 32768;  // B200PT_TAIL_PATHS: survivor count below which k_tail finishes a batch's paths (0 = never);
@@ -125,6 +127,7 @@ struct b200pt_context {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_fork = nullptr;
     bool timing_pending = false;
+    bool rendered_once = false;   // ev_end has been recorded at least once
     int num_sms = 148;
     // launch tunables (overridable through the environment for experiments: B200PT_TOP_NODES, B200PT_REFILL, B200PT_CTAS_PER_SM)
     int top_nodes = 0, refill = 20, ctas_per_sm = 4, min_inner = 8; // top_nodes = 0: no shared-memory staging (profiles/r01_sweep_sel3_topnodes.log)
@@ -214,6 +217,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     CU_CHECK(c, c->light_tri_cdf.Upload(h.light_tri_cdf));
     CU_CHECK(c, c->light_tri_ids.Upload(h.light_tri_ids));
     CU_CHECK(c, c->cull_boxes.Upload(h.cull_boxes));
+    CU_CHECK(c, c->fine_cull_boxes.Upload(h.fine_cull_boxes));
     CU_CHECK(c, c->pixels.Alloc(desc.num_pixels));
     if (desc.num_pixels)
         CU_CHECK(c, cudaMemcpy(c->pixels.ptr, desc.pixels, desc.num_pixels * sizeof(float), cudaMemcpyHostToDevice));
@@ -238,6 +242,8 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     s.light_tri_cdf = c->light_tri_cdf.ptr, s.light_tri_ids = c->light_tri_ids.ptr;
     memcpy(s.scene_bmin, h.scene_bmin, 12), memcpy(s.scene_bmax, h.scene_bmax, 12);
     s.cull_boxes = c->cull_boxes.ptr, s.num_cull_boxes = static_cast<uint32_t>(h.cull_boxes.size() / 6);
+    s.fine_cull_boxes = c->fine_cull_boxes.ptr, s.num_fine_cull_boxes = static_cast<uint32_t>(h.fine_cull_boxes.size() / 6);
+    if (getenv("B200PT_PIXEL_CULL") && atoi(getenv("B200PT_PIXEL_CULL")) == 0) s.num_fine_cull_boxes = 0; // experiments: tiles only
     s.integrator = h.integrator;
 
     // One BSDF type on every scattering surface (area lights and BSDF-less surfaces aside)?  Then the shading kernel
@@ -418,28 +424,34 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
     c->timed.clear();
     c->events_used = 0;
     for (uint64_t &n : c->class_launches) n = 0;
+    // One render in flight per handle: accum, the arenas and the counters are shared state, so work submitted on ANOTHER
+    // stream is ordered after the previous render of this handle (a no-op on the same stream).
+    if (c->rendered_once) CU_CHECK(c, cudaStreamWaitEvent(stream, c->ev_end, 0));
+    c->rendered_once = true;
     CU_CHECK(c, cudaEventRecord(c->ev_begin, stream));
 
     // Visibility pre-pass: which of this rank's tiles can see geometry at all.  Escaped camera rays only carry radiance
     // when an environment map or a sun disc exists (path.cpp:24-35), so without those the other tiles are exactly black
     // and none of their samples needs a ray.  The job's pixel list shrinks to the active tiles (part of the timed render).
     const uint32_t local_tiles = local_pixels / kTilePixels;
-    uint32_t job_pixels = local_pixels;
+    uint32_t job_pixels = local_pixels, active_tiles = local_tiles;
     const DIntegrator &ig = c->scene.integrator;
     if (ro.tile_cull && c->tile_cull && ig.id_envmap == kInvalid && ig.id_sun == kInvalid) {
-        if (c->tile_flags.count < local_tiles) {
-            CU_CHECK(c, c->tile_flags.Alloc(local_tiles));
-            CU_CHECK(c, c->tile_list.Alloc(local_tiles + 1ull));
+        if (c->tile_masks.count < local_tiles) {
+            CU_CHECK(c, c->tile_masks.Alloc(local_tiles));
+            CU_CHECK(c, c->pixel_list.Alloc(static_cast<uint64_t>(local_pixels) + 2ull));
         }
         launches += 2;
         c->class_launches[kClassOther] += 2;
-        LaunchCullTiles(lc, c->scene, bp, local_tiles, c->tile_flags.ptr, c->tile_list.ptr);
-        CU_CHECK(c, cudaMemcpyAsync(c->pinned_count, c->tile_list.ptr + local_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        LaunchCullTiles(lc, c->scene, bp, local_tiles, c->tile_masks.ptr, c->pixel_list.ptr, c->pixel_list.ptr + local_pixels);
+        CU_CHECK(c, cudaMemcpyAsync(c->pinned_count, c->pixel_list.ptr + local_pixels, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU_CHECK(c, cudaStreamSynchronize(stream));
-        job_pixels = *c->pinned_count * kTilePixels;
-        bp.active_tiles = c->tile_list.ptr;
+        job_pixels = c->pinned_count[0];
+        active_tiles = c->pinned_count[1];
+        bp.active_pixels = c->pixel_list.ptr;
     }
-    c->stats.active_tiles = job_pixels / kTilePixels;
+    c->stats.active_tiles = active_tiles;
+    c->stats.active_pixels = job_pixels;
     c->stats.local_tiles = local_tiles;
 
     // Batches.  The job's pixels are cut into chunks, one arena works on one chunk at a time (all its sample batches in
@@ -628,9 +640,23 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
 
 extern "C" {
 
+static int CreateChecked(const b200pt_scene_desc *scene, const b200pt_create_opts *opts, b200pt_handle *out);
+
+// No C++ exception crosses the C boundary (std::bad_alloc on a huge scene, std::system_error from the builder's threads): it
+// comes back as an error code with the reference's "error when commit renderer" prefix.
 int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts, b200pt_handle *out) {
     if (!scene || !out) return SetGlobalError(B200PT_EINVAL, "b200pt_create: null argument");
     *out = nullptr;
+    try {
+        return CreateChecked(scene, opts, out);
+    } catch (const std::exception &e) {
+        return SetGlobalError(B200PT_EINVAL, std::string("error when commit renderer.\n\t") + e.what());
+    } catch (...) {
+        return SetGlobalError(B200PT_EINVAL, "error when commit renderer.\n\tunknown failure");
+    }
+}
+
+static int CreateChecked(const b200pt_scene_desc *scene, const b200pt_create_opts *opts, b200pt_handle *out) {
     std::unique_ptr<b200pt_context> c(new b200pt_context());
     int device = opts ? opts->device : -1;
     cudaError_t e = cudaSuccess;
@@ -686,7 +712,7 @@ int b200pt_create(const b200pt_scene_desc *scene, const b200pt_create_opts *opts
         if ((e = cudaMallocHost(&a.poll_count, sizeof(uint32_t) * kPollRing)) != cudaSuccess) return c->CudaFail(e, "cudaMallocHost");
     }
     if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");
-    if ((e = cudaMallocHost(&c->pinned_count, sizeof(uint32_t))) != cudaSuccess) return c->CudaFail(e, "cudaMallocHost");
+    if ((e = cudaMallocHost(&c->pinned_count, 2 * sizeof(uint32_t))) != cudaSuccess) return c->CudaFail(e, "cudaMallocHost");
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return c->CudaFail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return c->CudaFail(e, "cudaEventCreate");

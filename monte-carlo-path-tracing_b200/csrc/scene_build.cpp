@@ -24,6 +24,7 @@
 #include <mutex>
 #include <new>
 #include <numeric>
+#include <queue>
 #include <thread>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -1329,10 +1330,10 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
     memcpy(hs->scene_bmin, &scene_box.lo, 12);
     memcpy(hs->scene_bmax, &scene_box.hi, 12);
 
-    // ---- cover of the geometry by a few boxes, for the screen-tile visibility pre-pass (wavefront.cu: k_cull_tiles):
-    // best-first cut through the BVH (always open the box with the largest surface area) + the analytic primitives.
+    // ---- covers of the geometry by boxes, for the screen-space visibility pre-pass (wavefront.cu: k_cull_tiles): best-first cuts
+    // through the BVH (always open the box with the largest surface area) + the analytic primitives.  A coarse cut rejects
+    // whole 8x8 tiles, a fine one single pixels.
     {
-        constexpr size_t kMaxCullBoxes = 384;
         struct CutBox {
             float lo[3], hi[3];
             int32_t link;
@@ -1340,6 +1341,7 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
                 const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
                 return dx * dy + dy * dz + dz * dx;
             }
+            bool operator<(const CutBox &o) const { return Area() < o.Area(); } // max-heap on the area
         };
         // children of an inner node of whichever binary tree exists: the flattened layout, or the SAH tree behind the wide layout
         auto children = [&](int32_t node, CutBox *a, CutBox *b) {
@@ -1353,30 +1355,32 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             *a = {{n.c0xy.x, n.c0xy.z, n.cz.x}, {n.c0xy.y, n.c0xy.w, n.cz.y}, n.child0};
             *b = {{n.c1xy.x, n.c1xy.z, n.cz.z}, {n.c1xy.y, n.c1xy.w, n.cz.w}, n.child1};
         };
-        std::vector<CutBox> cut;
-        if (!binary.empty() && binary[binary_root].left < 0) { // the whole scene is one leaf
-            const Bvh2Node &n = binary[binary_root];
-            cut.push_back({{n.lo[0], n.lo[1], n.lo[2]}, {n.hi[0], n.hi[1], n.hi[2]}, -1});
-        } else if (!binary.empty() || !hs->nodes.empty()) {
-            CutBox a, b;
-            children(binary.empty() ? 0 : binary_root, &a, &b);
-            cut.push_back(a);
-            cut.push_back(b);
-            while (cut.size() < kMaxCullBoxes) {
-                int best = -1;
-                for (size_t i = 0; i < cut.size(); ++i)
-                    if (cut[i].link >= 0 && (best < 0 || cut[i].Area() > cut[best].Area())) best = static_cast<int>(i);
-                if (best < 0) break;
-                children(cut[best].link, &a, &b);
-                cut[best] = a;
-                cut.push_back(b);
+        auto make_cut = [&](size_t max_boxes, std::vector<float> *out) {
+            std::vector<CutBox> done; // leaves: cannot be opened
+            std::priority_queue<CutBox> open;
+            if (!binary.empty() && binary[binary_root].left < 0) { // the whole scene is one leaf
+                const Bvh2Node &n = binary[binary_root];
+                done.push_back({{n.lo[0], n.lo[1], n.lo[2]}, {n.hi[0], n.hi[1], n.hi[2]}, -1});
+            } else if (!binary.empty() || !hs->nodes.empty()) {
+                CutBox a, b;
+                children(binary.empty() ? 0 : binary_root, &a, &b);
+                for (const CutBox &c : {a, b}) (c.link >= 0 ? (void)open.push(c) : (void)done.push_back(c));
+                while (!open.empty() && open.size() + done.size() < max_boxes) {
+                    const CutBox top = open.top();
+                    open.pop();
+                    children(top.link, &a, &b);
+                    for (const CutBox &c : {a, b}) (c.link >= 0 ? (void)open.push(c) : (void)done.push_back(c));
+                }
             }
-        }
-        for (const CutBox &c : cut)
-            if (c.hi[0] >= c.lo[0] && c.hi[1] >= c.lo[1] && c.hi[2] >= c.lo[2]) // skip the empty box of a one-leaf tree
-                hs->cull_boxes.insert(hs->cull_boxes.end(), {c.lo[0], c.lo[1], c.lo[2], c.hi[0], c.hi[1], c.hi[2]});
-        for (const AnalyticPrim &p : hs->analytic)
-            hs->cull_boxes.insert(hs->cull_boxes.end(), {p.bmin[0], p.bmin[1], p.bmin[2], p.bmax[0], p.bmax[1], p.bmax[2]});
+            for (; !open.empty(); open.pop()) done.push_back(open.top());
+            for (const CutBox &c : done)
+                if (c.hi[0] >= c.lo[0] && c.hi[1] >= c.lo[1] && c.hi[2] >= c.lo[2]) // skip the empty box of a one-leaf tree
+                    out->insert(out->end(), {c.lo[0], c.lo[1], c.lo[2], c.hi[0], c.hi[1], c.hi[2]});
+            for (const AnalyticPrim &p : hs->analytic)
+                out->insert(out->end(), {p.bmin[0], p.bmin[1], p.bmin[2], p.bmax[0], p.bmax[1], p.bmax[2]});
+        };
+        make_cut(384, &hs->cull_boxes);
+        make_cut(4096, &hs->fine_cull_boxes);
     }
 
     // ---- triangle CDFs of mesh area lights (replaces the area-weighted BVH descent of blas.cpp:79-98) ----

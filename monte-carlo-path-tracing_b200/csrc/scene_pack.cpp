@@ -14,8 +14,10 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -152,9 +154,11 @@ extern "C" int b200pt_scene_save(const b200pt_scene_desc *s, const char *path) {
 
 namespace {
 
+constexpr uint64_t kMaxSectionBytes = 1ull << 36; // 64 GiB: far above any scene, far below an overflow
+
 template <typename T>
 bool Decode(const SectionHeader &h, const std::vector<uint8_t> &stored, size_t elem_bytes, std::vector<T> *out) {
-    if (h.raw_bytes != h.count * elem_bytes) return false;
+    if (elem_bytes == 0 || h.count > kMaxSectionBytes / elem_bytes || h.raw_bytes != h.count * elem_bytes) return false; // no overflow
     out->resize(h.raw_bytes / sizeof(T));
     uint8_t *dst = reinterpret_cast<uint8_t *>(out->data());
     std::vector<uint8_t> tmp;
@@ -195,9 +199,23 @@ bool DecodePixels(const SectionHeader &h, const std::vector<uint8_t> &stored, st
 
 } // namespace
 
+// A corrupt or hostile pack must come back as B200PT_EIO, not as std::bad_alloc through the C boundary: every size in a section
+// header is checked against the bytes the file still holds and against a hard cap before anything is allocated.
+static int SceneLoadChecked(const char *path, b200pt_scene **out);
+
 extern "C" int b200pt_scene_load(const char *path, b200pt_scene **out) {
     if (!path || !out) return b200pt::SetGlobalError(B200PT_EINVAL, "b200pt_scene_load: null argument");
     *out = nullptr;
+    try {
+        return SceneLoadChecked(path, out);
+    } catch (const std::exception &e) {
+        return b200pt::SetGlobalError(B200PT_EIO, std::string("scene pack '") + path + "': " + e.what());
+    } catch (...) {
+        return b200pt::SetGlobalError(B200PT_EIO, std::string("scene pack '") + path + "': unknown failure");
+    }
+}
+
+static int SceneLoadChecked(const char *path, b200pt_scene **out) {
     FILE *f = fopen(path, "rb");
     if (!f) return b200pt::SetGlobalError(B200PT_EIO, std::string("cannot open scene pack '") + path + "'");
     auto fail = [&](const std::string &why, b200pt_scene *s) {
@@ -205,6 +223,9 @@ extern "C" int b200pt_scene_load(const char *path, b200pt_scene **out) {
         delete s;
         return b200pt::SetGlobalError(B200PT_EIO, "scene pack '" + std::string(path) + "': " + why);
     };
+    fseek(f, 0, SEEK_END);
+    const uint64_t file_bytes = static_cast<uint64_t>(ftell(f));
+    fseek(f, 0, SEEK_SET);
     char magic[8];
     uint32_t version = 0;
     if (fread(magic, 8, 1, f) != 1 || memcmp(magic, kMagic, 8) != 0) return fail("bad magic", nullptr);
@@ -217,6 +238,9 @@ extern "C" int b200pt_scene_load(const char *path, b200pt_scene **out) {
         SectionHeader h;
         if (fread(&h, sizeof(h), 1, f) != 1) return fail("truncated section header", s);
         if (h.tag == 0) break;
+        const uint64_t here = static_cast<uint64_t>(ftell(f));
+        if (h.stored_bytes > file_bytes - std::min(here, file_bytes)) return fail("section larger than the file", s);
+        if (h.raw_bytes > kMaxSectionBytes) return fail("section larger than the format allows", s);
         std::vector<uint8_t> stored(h.stored_bytes);
         if (h.stored_bytes && fread(stored.data(), 1, h.stored_bytes, f) != h.stored_bytes)
             return fail("truncated section payload", s);

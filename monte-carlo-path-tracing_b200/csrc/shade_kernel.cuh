@@ -346,13 +346,15 @@ __device__ __forceinline__ bool LoadPathVertex(const DeviceScene &scene, const P
     return alive;
 }
 
-// Resident CTAs per SM a variant is compiled for.  The diffuse path-integrator kernel fits 64 registers with a few spilled
-// words and gains from the fourth CTA (Dragon shade 6.6 -> 5.4 ms, Cornell 33.1 -> 26.7 ms: profiles/r01_sweep_shade_occupancy.log);
-// the other models need ~120 registers and are left to the compiler.
+// Resident CTAs per SM a variant is compiled for.  Left to the compiler the variants take 96-128 registers (2 CTAs, 25 %
+// occupancy) and wait for their gathers; capped, they spill 100-200 bytes per thread and win all the same: 4 CTAs (64
+// registers) for the path integrator (matpreview 105.0 -> 98.2 ms, lte-orb 111.9 -> 103.8, box 105.1 -> 96.2, material-testball
+// 40.9 -> 37.4, Dragon 5.4 ms shade with 4 vs 6.6 with 3), 3 CTAs (80 registers) for volpath, whose vertex state is larger
+// (volumetric-caustic 267.3 -> 242.7 ms with 3, 258.8 with 4): profiles/r02_sweep_shade_ctas_leaf_step.log.
 #ifdef B200PT_SHADE_MIN_CTAS_OVERRIDE   // experiments: one bound for every variant of the translation unit
 #define B200PT_SHADE_MIN_CTAS(VOL, ONLY) B200PT_SHADE_MIN_CTAS_OVERRIDE
 #else
-#define B200PT_SHADE_MIN_CTAS(VOL, ONLY) (((ONLY) == B200PT_BSDF_DIFFUSE && !(VOL)) ? 4 : 1)
+#define B200PT_SHADE_MIN_CTAS(VOL, ONLY) ((VOL) ? 3 : 4)
 #endif
 template <bool VOL, int ONLY>
 __global__ void __launch_bounds__(kShadeThreads, B200PT_SHADE_MIN_CTAS(VOL, ONLY)) k_shade(const __grid_constant__ DeviceScene scene,

@@ -28,9 +28,7 @@ __device__ __forceinline__ bool TraceSingle(const DeviceScene &scene, const Ray 
     return TraverseSingle(scene, ray, any, opacity, rng, hit, stats, counters);
 }
 
-// ONLY: the one BSDF model of the scene's surfaces (as for k_shade), or kAnyBsdf: a single-model scene walks its tail through
-// that model's code alone instead of the 43 000-instruction generic shading path.
-template <bool VOL, int ONLY>
+template <bool VOL>
 __global__ void __launch_bounds__(kTailThreads) k_tail(const __grid_constant__ DeviceScene scene, const __grid_constant__ BatchParams bp,
                                                       uint32_t depth0, PathQueue q, int which, float *radiance, uint32_t capacity,
                                                       Counters *counters, uint32_t threshold, bool stats) {
@@ -62,7 +60,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const __grid_constant__ D
             PathNext next;
             V3 Ladd;
             const bool was_alive = alive;
-            alive = ShadeVertex<VOL, ONLY>(
+            alive = ShadeVertex<VOL, kAnyBsdf>(
                 scene, bp, depth, alive, v,
                 [&](const ShadowCandidate &sc) { // next-event estimation: trace the shadow ray right away
                     if (!(sc.valid && (sc.c.x != 0.0f || sc.c.y != 0.0f || sc.c.z != 0.0f))) return;
@@ -120,14 +118,10 @@ void LaunchTail(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
                 float *radiance, uint32_t capacity, Counters *counters, uint32_t threshold) {
     // enough CTAs for `threshold` paths at one path per WARP, capped at two waves of a full machine
     const int blocks = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(lc.blocks) * 2u, (threshold + kTailThreads / 32 - 1) / (kTailThreads / 32)));
-    const bool vol = scene.integrator.type == B200PT_INTEGRATOR_VOLPATH, diffuse = lc.shade_only == B200PT_BSDF_DIFFUSE;
-    auto go = [&](auto kernel) {
-        kernel<<<std::max(blocks, 1), kTailThreads, 0, lc.stream>>>(scene, bp, depth, q, which, radiance, capacity, counters, threshold, lc.stats);
-    };
-    if (vol && diffuse) go(k_tail<true, B200PT_BSDF_DIFFUSE>);
-    else if (vol) go(k_tail<true, kAnyBsdf>);
-    else if (diffuse) go(k_tail<false, B200PT_BSDF_DIFFUSE>);
-    else go(k_tail<false, kAnyBsdf>);
+    if (scene.integrator.type == B200PT_INTEGRATOR_VOLPATH)
+        k_tail<true><<<std::max(blocks, 1), kTailThreads, 0, lc.stream>>>(scene, bp, depth, q, which, radiance, capacity, counters, threshold, lc.stats);
+    else
+        k_tail<false><<<std::max(blocks, 1), kTailThreads, 0, lc.stream>>>(scene, bp, depth, q, which, radiance, capacity, counters, threshold, lc.stats);
 }
 
 } // namespace b200pt

@@ -400,83 +400,154 @@ __global__ void __launch_bounds__(kThreads) k_settle(Counters *c, int which_queu
     }
 }
 
-// Visibility pre-pass for camera rays.  Every camera ray of a tile starts at the eye and runs inside the pyramid spanned
-// by the tile's four corner directions (widened by half a pixel); a box that lies entirely outside one of the pyramid's
-// side planes, or behind the eye, cannot be hit by any of them.  A tile that sees none of the scene's cull boxes (which
-// cover all geometry) produces only escaped rays, i.e. exactly zero radiance when there is no environment / sun emitter,
-// so its samples need no ray at all.  Conservative by construction: a tile is dropped only on a proof of emptiness.
-// One warp per local tile, lanes over boxes.
+// Visibility pre-pass for camera rays.  Every camera ray of a screen rectangle starts at the eye and runs inside the pyramid
+// spanned by the rectangle's four corner directions; a box that lies entirely outside one of the pyramid's side planes, or
+// behind the eye, cannot be hit by any of them.  A rectangle that sees none of the scene's cull boxes (which cover all
+// geometry) produces only escaped rays, i.e. exactly zero radiance when there is no environment / sun emitter, so its samples
+// need no ray at all.  Conservative by construction: a pixel is dropped only on a proof of emptiness.
+// Two levels: an 8x8 tile against the coarse boxes (<= 384: most of the screen ends here), then the fine boxes (<= 4096)
+// that meet the tile's pyramid are short-listed in shared memory and every PIXEL of the tile is tested against the short
+// list.  One warp per local tile; the result is a 64-bit pixel mask per tile.
+struct Pyramid {
+    V3 plane[5]; // inward normals of the four sides through the eye, and the view direction
+};
+
+__device__ __forceinline__ Pyramid MakePyramid(const BatchParams &bp, float i0, float i1, float j0, float j1) {
+    const V3 front = mk3(bp.camera.front), dx = mk3(bp.camera.view_dx), dy = mk3(bp.camera.view_dy);
+    const float x0 = 2.0f * i0 / static_cast<float>(bp.width) - 1.0f, x1 = 2.0f * i1 / static_cast<float>(bp.width) - 1.0f;
+    const float y0 = 1.0f - 2.0f * j0 / static_cast<float>(bp.height), y1 = 1.0f - 2.0f * j1 / static_cast<float>(bp.height);
+    const V3 corner[4] = {front + x0 * dx + y0 * dy, front + x1 * dx + y0 * dy, front + x1 * dx + y1 * dy, front + x0 * dx + y1 * dy};
+    const V3 centre = corner[0] + corner[2];
+    Pyramid py;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        V3 n = Cross(corner[k], corner[(k + 1) & 3]);
+        if (Dot(n, centre) < 0.0f) n = -n; // inward
+        py.plane[k] = n;
+    }
+    py.plane[4] = front;
+    return py;
+}
+
+// Is the box (6 floats) entirely on the outer side of one of the pyramid's planes?
+__device__ __forceinline__ bool BoxOutsidePyramid(const Pyramid &py, const V3 &eye, const float *bx) {
+    const V3 lo = mk3(bx[0], bx[1], bx[2]), hi = mk3(bx[3], bx[4], bx[5]);
+    const V3 c = 0.5f * (lo + hi) - eye, h = 0.5f * (hi - lo);
+    bool outside = false;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const V3 n = py.plane[k];
+        const float s = Dot(n, c), r = fabsf(n.x) * h.x + fabsf(n.y) * h.y + fabsf(n.z) * h.z;
+        if (s + r < -1e-5f * (fabsf(s) + r)) outside = true; // the whole box is on the outer side
+    }
+    return outside;
+}
+
+constexpr uint32_t kCullShortList = 384; // fine boxes a tile may short-list before it gives up and keeps all its pixels
+
 __global__ void __launch_bounds__(kThreads) k_cull_tiles(const __grid_constant__ BatchParams bp, const float *__restrict__ boxes,
-                                                         uint32_t num_boxes, uint32_t num_local_tiles, uint32_t *flags) {
+                                                         uint32_t num_boxes, const float *__restrict__ fine_boxes, uint32_t num_fine,
+                                                         uint32_t num_local_tiles, unsigned long long *masks) {
+    __shared__ uint16_t short_all[kThreads / 32][kCullShortList];
+    uint16_t *short_list = short_all[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, num_warps = (gridDim.x * blockDim.x) >> 5;
-    const V3 eye = mk3(bp.camera.eye), front = mk3(bp.camera.front), dx = mk3(bp.camera.view_dx), dy = mk3(bp.camera.view_dy);
+    const V3 eye = mk3(bp.camera.eye);
     for (uint32_t t = warp; t < num_local_tiles; t += num_warps) {
         const uint32_t tile = t * bp.tile_world + bp.tile_rank;
-        bool visible = false;
+        unsigned long long mask = 0ull;
         if (tile < bp.num_tiles) {
-            const float i0 = static_cast<float>((tile % bp.tiles_x) * kTileSize), j0 = static_cast<float>((tile / bp.tiles_x) * kTileSize);
+            const uint32_t ti = (tile % bp.tiles_x) * kTileSize, tj = (tile / bp.tiles_x) * kTileSize;
+            const float i0 = static_cast<float>(ti), j0 = static_cast<float>(tj);
             const float i1 = fminf(i0 + kTileSize, static_cast<float>(bp.width)), j1 = fminf(j0 + kTileSize, static_cast<float>(bp.height));
             constexpr float kMargin = 0.5f; // pixels
-            const float x0 = 2.0f * (i0 - kMargin) / static_cast<float>(bp.width) - 1.0f, x1 = 2.0f * (i1 + kMargin) / static_cast<float>(bp.width) - 1.0f;
-            const float y0 = 1.0f - 2.0f * (j0 - kMargin) / static_cast<float>(bp.height), y1 = 1.0f - 2.0f * (j1 + kMargin) / static_cast<float>(bp.height);
-            const V3 corner[4] = {front + x0 * dx + y0 * dy, front + x1 * dx + y0 * dy, front + x1 * dx + y1 * dy, front + x0 * dx + y1 * dy};
-            const V3 centre = corner[0] + corner[2];
-            V3 plane[5];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                V3 n = Cross(corner[k], corner[(k + 1) & 3]);
-                if (Dot(n, centre) < 0.0f) n = -n; // inward
-                plane[k] = n;
-            }
-            plane[4] = front;
-            for (uint32_t b = lane; b < num_boxes; b += 32) {
-                const float *bx = boxes + 6 * b;
-                const V3 lo = mk3(bx[0], bx[1], bx[2]), hi = mk3(bx[3], bx[4], bx[5]);
-                const V3 c = 0.5f * (lo + hi) - eye, h = 0.5f * (hi - lo);
-                bool outside = false;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const V3 n = plane[k];
-                    const float s = Dot(n, c), r = fabsf(n.x) * h.x + fabsf(n.y) * h.y + fabsf(n.z) * h.z;
-                    if (s + r < -1e-5f * (fabsf(s) + r)) outside = true; // the whole box is on the outer side
+            const Pyramid tile_pyramid = MakePyramid(bp, i0 - kMargin, i1 + kMargin, j0 - kMargin, j1 + kMargin);
+            bool visible = false;
+            for (uint32_t b = lane; b < num_boxes; b += 32)
+                if (!BoxOutsidePyramid(tile_pyramid, eye, boxes + 6 * b)) visible = true;
+            visible = __any_sync(0xffffffffu, visible);
+            // the pixels of the tile that lie inside the image (lane k and k + 32 -> pixel (k % 8, k / 8))
+            const unsigned in_lo = __ballot_sync(0xffffffffu, ti + (lane % kTileSize) < bp.width && tj + (lane / kTileSize) < bp.height);
+            const unsigned in_hi = __ballot_sync(0xffffffffu, ti + (lane % kTileSize) < bp.width && tj + 4u + (lane / kTileSize) < bp.height);
+            const unsigned long long inside = (static_cast<unsigned long long>(in_hi) << 32) | in_lo;
+            if (visible && num_fine == 0) mask = inside;
+            else if (visible) {
+                // fine boxes that meet the tile's pyramid
+                uint32_t count = 0;
+                bool overflow = false;
+                for (uint32_t b0 = 0; b0 < num_fine; b0 += 32) {
+                    const uint32_t b = b0 + lane;
+                    const bool meets = b < num_fine && !BoxOutsidePyramid(tile_pyramid, eye, fine_boxes + 6 * b);
+                    const unsigned ballot = __ballot_sync(0xffffffffu, meets);
+                    const uint32_t at = count + __popc(ballot & ((1u << lane) - 1u));
+                    if (meets && at < kCullShortList) short_list[at] = static_cast<uint16_t>(b);
+                    count += __popc(ballot);
+                    if (count > kCullShortList) {
+                        overflow = true;
+                        break;
+                    }
                 }
-                if (!outside) visible = true;
+                __syncwarp();
+                if (overflow) mask = inside;
+                else {
+                    constexpr float kPixelMargin = 0.02f; // the samples of pixel i lie in [i, i + 1)
+                    unsigned lo_bits = 0u, hi_bits = 0u;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t k = lane + 32u * half, pi = ti + (k % kTileSize), pj = tj + (k / kTileSize);
+                        bool sees = false;
+                        if (pi < bp.width && pj < bp.height) {
+                            const Pyramid pixel = MakePyramid(bp, pi - kPixelMargin, pi + 1.0f + kPixelMargin, pj - kPixelMargin, pj + 1.0f + kPixelMargin);
+                            for (uint32_t q = 0; q < count && !sees; ++q) sees = !BoxOutsidePyramid(pixel, eye, fine_boxes + 6u * short_list[q]);
+                        }
+                        const unsigned ballot = __ballot_sync(0xffffffffu, sees);
+                        if (half == 0) lo_bits = ballot;
+                        else hi_bits = ballot;
+                    }
+                    mask = (static_cast<unsigned long long>(hi_bits) << 32) | lo_bits;
+                }
+                __syncwarp();
             }
         }
-        visible = __any_sync(0xffffffffu, visible);
-        if (lane == 0) flags[t] = visible ? 1u : 0u;
+        if (lane == 0) masks[t] = mask;
     }
 }
 
-// Deterministic stream compaction of the tile flags by ONE CTA (at most a few 10^5 tiles): list[0..count) = ascending
-// indices of the set flags, list[n] = count.
-__global__ void __launch_bounds__(1024) k_compact_tiles(const uint32_t *flags, uint32_t n, uint32_t *list) {
-    __shared__ uint32_t warp_sums[32];
+// Deterministic stream compaction of the pixel masks by ONE CTA (at most a few 10^5 tiles): list[0 .. pixels) = ascending local
+// indices (tile * 64 + pixel in tile) of the set bits, counts[0] = pixels, counts[1] = tiles with at least one.
+__global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned long long *masks, uint32_t n, uint32_t *list, uint32_t *counts) {
+    __shared__ uint32_t warp_sums[32], warp_tiles[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t chunk = (n + blockDim.x - 1) / blockDim.x, begin = min(n, tid * chunk), end = min(n, begin + chunk);
-    uint32_t mine = 0;
-    for (uint32_t i = begin; i < end; ++i) mine += flags[i];
+    uint32_t mine = 0, tiles = 0;
+    for (uint32_t i = begin; i < end; ++i) {
+        mine += __popcll(masks[i]);
+        tiles += masks[i] != 0ull;
+    }
     uint32_t incl = mine;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= static_cast<uint32_t>(o)) incl += v;
     }
+    for (int o = 16; o > 0; o >>= 1) tiles += __shfl_down_sync(0xffffffffu, tiles, o);
     if (lane == 31) warp_sums[warp] = incl;
+    if (lane == 0) warp_tiles[warp] = tiles;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = warp_sums[lane], wi = w;
+        uint32_t w = warp_sums[lane], wi = w, wt = warp_tiles[lane];
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= static_cast<uint32_t>(o)) wi += v;
         }
+        for (int o = 16; o > 0; o >>= 1) wt += __shfl_down_sync(0xffffffffu, wt, o);
         warp_sums[lane] = wi - w; // exclusive
-        if (lane == 31) list[n] = wi;
+        if (lane == 31) counts[0] = wi;
+        if (lane == 0) counts[1] = wt;
     }
     __syncthreads();
     uint32_t out = warp_sums[warp] + incl - mine;
     for (uint32_t i = begin; i < end; ++i)
-        if (flags[i]) list[out++] = i;
+        for (unsigned long long m = masks[i]; m != 0ull; m &= m - 1ull) list[out++] = i * kTilePixels + (__ffsll(static_cast<long long>(m)) - 1);
 }
 
 // renderer.cpp:76-84: clamp each SAMPLE to <= 1 per channel (Q2), then sum the pixel's samples.
@@ -652,11 +723,12 @@ void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b2
 }
 
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
-                     uint32_t *flags, uint32_t *list) {
+                     unsigned long long *masks, uint32_t *pixel_list, uint32_t *counts) {
     const int warps_per_cta = kThreads / 32;
     const int blocks = static_cast<int>(std::min<uint32_t>(lc.blocks, (num_local_tiles + warps_per_cta - 1) / warps_per_cta));
-    k_cull_tiles<<<std::max(blocks, 1), kThreads, 0, lc.stream>>>(bp, scene.cull_boxes, scene.num_cull_boxes, num_local_tiles, flags);
-    k_compact_tiles<<<1, 1024, 0, lc.stream>>>(flags, num_local_tiles, list);
+    k_cull_tiles<<<std::max(blocks, 1), kThreads, 0, lc.stream>>>(bp, scene.cull_boxes, scene.num_cull_boxes, scene.fine_cull_boxes,
+                                                                 scene.num_fine_cull_boxes, num_local_tiles, masks);
+    k_compact_tiles<<<1, 1024, 0, lc.stream>>>(masks, num_local_tiles, pixel_list, counts);
 }
 
 void LaunchSettle(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow, ShadowQueue sq, float *radiance,

@@ -107,9 +107,9 @@ struct BatchParams {
     uint32_t pixel_count;     // local pixels in this batch
     uint32_t sample_begin;    // first sample index of this batch
     uint32_t sample_count;    // samples per pixel in this batch (slots = pixel_count * sample_count)
-    // Tile visibility pre-pass (k_cull_tiles): the local tiles whose camera rays can reach geometry, in ascending order;
-    // the job's pixel list is then [active tile 0's 64 pixels, active tile 1's, ...].  nullptr = every local tile.
-    const uint32_t *active_tiles;
+    // Visibility pre-pass (k_cull_tiles): the local pixels whose camera rays can reach geometry, in ascending order: the
+    // job's pixel list.  nullptr = every local pixel.
+    const uint32_t *active_pixels;
     // Progressive preview (renderer.cpp:97-138): one sample per pixel per call, every pixel with the same sub-pixel offset
     // (VdC_2, VdC_3 of frame_index + 1); the sample index of the random-number stream is the frame index.
     uint32_t progressive;
@@ -118,8 +118,8 @@ struct BatchParams {
 
 // index in the job's pixel list -> local pixel (position in this rank's tile-ordered pixel buffer)
 __host__ __device__ inline uint32_t JobPixelToLocal(const BatchParams &p, uint32_t job_pixel) {
-    if (p.active_tiles == nullptr) return job_pixel;
-    return p.active_tiles[job_pixel / kTilePixels] * kTilePixels + job_pixel % kTilePixels;
+    if (p.active_pixels == nullptr) return job_pixel;
+    return p.active_pixels[job_pixel];
 }
 
 // local pixel -> image coordinates; false for padding pixels of edge tiles / tiles past the end.
@@ -172,7 +172,7 @@ int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
 // Visibility pre-pass: flags[t] = 1 if local tile t can see one of the scene's cull boxes, then the ascending list of
 // such tiles in list[0 .. count) with count stored at list[num_local_tiles].
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
-                     uint32_t *flags, uint32_t *list);
+                     unsigned long long *masks, uint32_t *pixel_list, uint32_t *counts);
 // Path-at-a-time tail (tail_kernel.cu): launched after the traversal of bounce `depth - 1`; takes queue `which` over and
 // finishes its paths if it holds at most `threshold` entries, else returns at once.  `depth` = the bounce shade would run.
 void LaunchTail(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,

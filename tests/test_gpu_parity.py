@@ -199,15 +199,16 @@ def test_full_size_dragon_properties(pkg):
     st = r.stats()
     assert np.array_equal(frame, culled)
     assert st["samples"] == 1024 * 1024 * 256
-    assert st["primary"]["rays"] == st["active_tiles"] * 64 * 256
+    assert st["primary"]["rays"] == st["active_pixels"] * 256      # camera rays only for the pixels that may see geometry
     assert coverage * 128 * 128 <= st["active_tiles"] < 0.35 * 128 * 128, st["active_tiles"]
+    assert coverage * 1024 * 1024 <= st["active_pixels"] < min(0.2 * 1024 * 1024, st["active_tiles"] * 64), st["active_pixels"]
     r.close()
 
 
 @pytest.mark.parametrize("scene,w,h", [("dragon", 200, 120), ("cornell-box", 64, 64), ("volumetric-caustic", 40, 56),
                                        ("synthetic_opacity_masks", 64, 48), ("synthetic_dielectrics_conductor_cylinder", 48, 64)])
 def test_tile_visibility_prepass_is_exact(pkg, scene, w, h):
-    """Dropping tiles that cannot see geometry never changes a bit of the frame (whole frame and tile-partitioned)."""
+    """Dropping tiles and pixels that cannot see geometry never changes a bit of the frame (whole frame and tile-partitioned)."""
     import torch
     r = renderer(pkg, scene)
     full = r.Draw(width=w, height=h, spp=8, seed=13, flags=pkg.RENDER_NO_TILE_CULL)
@@ -218,6 +219,7 @@ def test_tile_visibility_prepass_is_exact(pkg, scene, w, h):
     # every tile with a lit pixel survived the pre-pass
     lit_tiles = (np.add.reduceat(np.add.reduceat(full.sum(axis=2), np.arange(0, h, 8), axis=0), np.arange(0, w, 8), axis=1) > 0).sum()
     assert st["active_tiles"] >= lit_tiles
+    assert (full.sum(axis=2) > 0).sum() <= st["active_pixels"] <= st["active_tiles"] * 64  # every lit pixel survived it too
     world = 3
     n = pkg.tile_buffer_floats(w, h, world)
     gathered = torch.zeros(world * n, dtype=torch.float32, device="cuda")

@@ -72,3 +72,21 @@ def test_palette_coded_bitmap_pool(pkg):
     pixels = np.ctypeslib.as_array(ctypes.cast(int(raw[3]), ctypes.POINTER(ctypes.c_float)), shape=(1 << 22,))
     assert len(np.unique(pixels)) <= 256
     assert 0.0 <= pixels.min() and pixels.max() <= 1.0
+
+
+def test_hostile_section_sizes_come_back_as_errors(pkg, tmp_path):
+    """Round-1 advisor finding: the section headers carry 64-bit sizes.  A pack that claims petabytes, or a count whose product
+    with the element size overflows, must be refused with B200PT_EIO before anything is allocated — no std::bad_alloc through
+    the C boundary."""
+    import struct
+    good = bytearray(open(pack("cornell-box"), "rb").read())
+    header = 8 + 4 + 52 + 20            # magic, version, camera, integrator
+    tag, codec, count, raw_bytes, stored_bytes = struct.unpack_from("<IIQQQ", good, header)
+    assert tag != 0 and stored_bytes < len(good)
+    for field, value in ((24, 1 << 60), (16, 1 << 50), (8, (1 << 64) // 120 + 7)):  # stored_bytes, raw_bytes, count
+        bad = bytearray(good)
+        struct.pack_into("<Q", bad, header + field, value)
+        path = tmp_path / f"hostile_{field}.b200scene"
+        path.write_bytes(bytes(bad))
+        with pytest.raises(pkg.MyException, match="scene pack"):
+            pkg.Scene(str(path))
