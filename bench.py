@@ -177,7 +177,7 @@ def fast_build_usable():
 def shared_config(desc, width, height, spp):
     """The part of `config` both arms print identically: the workload both measure."""
     return {"workload": desc, "width": width, "height": height, "spp": spp,
-            "l2": "b200 arm: 256 MB buffer written between timed steps (L2 flush), and scene + wavefront state exceed the 126 MB L2; reference arm: CPU"}
+            "l2": "b200 arm: 256 MB buffer written between timed steps (L2 flush), and scene (160 MB) + wavefront state (~190 B per sample slot in flight: GBs) exceed the 126 MB L2; reference arm: CPU"}
 
 
 def run_reference(args, workload):
