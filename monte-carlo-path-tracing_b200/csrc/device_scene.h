@@ -169,7 +169,8 @@ struct DeviceScene {
     // A cut through the top of the BVH (plus the boxes of the analytic primitives): min.xyz max.xyz per box, together
     // they cover all geometry.  Screen tiles whose pyramid of camera rays misses every box trace nothing (k_cull_tiles).
     const float *cull_boxes;     uint32_t num_cull_boxes;
-    const float *fine_cull_boxes; uint32_t num_fine_cull_boxes;
+    const float *fine_cull_boxes; uint32_t num_fine_cull_boxes; // finer cover, grouped by coarse box: single pixels
+    const uint32_t *cull_fine_begin; // num_cull_boxes + 1 entries: the fine boxes under coarse box b are [begin[b], begin[b + 1])
     DIntegrator integrator;
 };
 

@@ -33,6 +33,7 @@ struct HostScene {
     float scene_bmin[3], scene_bmax[3];
     std::vector<float> cull_boxes;   // 6 floats per box (DeviceScene::cull_boxes): coarse cover, rejects whole screen tiles
     std::vector<float> fine_cull_boxes; // finer cover (<= 4096 boxes + analytic primitives): rejects single pixels
+    std::vector<uint32_t> cull_fine_begin; // per coarse box (+ 1): its range of fine boxes
     DIntegrator integrator{};
     b200pt_camera camera{};
     double bvh_build_ms = 0.0;  // whole BVH stage (boxes, build, flatten)

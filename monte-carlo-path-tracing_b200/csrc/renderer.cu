@@ -107,6 +107,8 @@ struct b200pt_context {
     DeviceArray<float> fine_cull_boxes;
     DeviceArray<unsigned long long> tile_masks;  // visibility pre-pass: per local tile, the pixels that can see geometry
     DeviceArray<uint32_t> pixel_list;            // ... their local indices in ascending order, followed by {pixels, non-empty tiles}
+    DeviceArray<uint32_t> tile_offsets;          // ... position of each tile's first surviving pixel in that list
+    DeviceArray<uint32_t> cull_fine_begin;
     bool tile_cull = true;        // B200PT_TILE_CULL=0 turns the pre-pass off
     int shade_only = -1;          // see LaunchConfig::shade_only
     uint32_t tail_paths = 32768;  // B200PT_TAIL_PATHS: survivor count below which k_tail finishes a batch's paths (0 = never);
@@ -218,6 +220,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     CU_CHECK(c, c->light_tri_ids.Upload(h.light_tri_ids));
     CU_CHECK(c, c->cull_boxes.Upload(h.cull_boxes));
     CU_CHECK(c, c->fine_cull_boxes.Upload(h.fine_cull_boxes));
+    CU_CHECK(c, c->cull_fine_begin.Upload(h.cull_fine_begin));
     CU_CHECK(c, c->pixels.Alloc(desc.num_pixels));
     if (desc.num_pixels)
         CU_CHECK(c, cudaMemcpy(c->pixels.ptr, desc.pixels, desc.num_pixels * sizeof(float), cudaMemcpyHostToDevice));
@@ -242,6 +245,7 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     s.light_tri_cdf = c->light_tri_cdf.ptr, s.light_tri_ids = c->light_tri_ids.ptr;
     memcpy(s.scene_bmin, h.scene_bmin, 12), memcpy(s.scene_bmax, h.scene_bmax, 12);
     s.cull_boxes = c->cull_boxes.ptr, s.num_cull_boxes = static_cast<uint32_t>(h.cull_boxes.size() / 6);
+    s.cull_fine_begin = c->cull_fine_begin.ptr;
     s.fine_cull_boxes = c->fine_cull_boxes.ptr, s.num_fine_cull_boxes = static_cast<uint32_t>(h.fine_cull_boxes.size() / 6);
     if (getenv("B200PT_PIXEL_CULL") && atoi(getenv("B200PT_PIXEL_CULL")) == 0) s.num_fine_cull_boxes = 0; // experiments: tiles only
     s.integrator = h.integrator;
@@ -440,10 +444,11 @@ int RenderOnStream(b200pt_context *c, const ResolvedOpts &ro, float *frame_dev, 
         if (c->tile_masks.count < local_tiles) {
             CU_CHECK(c, c->tile_masks.Alloc(local_tiles));
             CU_CHECK(c, c->pixel_list.Alloc(static_cast<uint64_t>(local_pixels) + 2ull));
+            CU_CHECK(c, c->tile_offsets.Alloc(local_tiles));
         }
-        launches += 2;
-        c->class_launches[kClassOther] += 2;
-        LaunchCullTiles(lc, c->scene, bp, local_tiles, c->tile_masks.ptr, c->pixel_list.ptr, c->pixel_list.ptr + local_pixels);
+        launches += 3;
+        c->class_launches[kClassOther] += 3;
+        LaunchCullTiles(lc, c->scene, bp, local_tiles, c->tile_masks.ptr, c->tile_offsets.ptr, c->pixel_list.ptr, c->pixel_list.ptr + local_pixels);
         CU_CHECK(c, cudaMemcpyAsync(c->pinned_count, c->pixel_list.ptr + local_pixels, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU_CHECK(c, cudaStreamSynchronize(stream));
         job_pixels = c->pinned_count[0];

@@ -1331,8 +1331,8 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
     memcpy(hs->scene_bmax, &scene_box.hi, 12);
 
     // ---- covers of the geometry by boxes, for the screen-space visibility pre-pass (wavefront.cu: k_cull_tiles): best-first cuts
-    // through the BVH (always open the box with the largest surface area) + the analytic primitives.  A coarse cut rejects
-    // whole 8x8 tiles, a fine one single pixels.
+    // through the BVH (always open the box with the largest surface area) + the analytic primitives.  A coarse cut (<= 384 boxes)
+    // rejects whole 8x8 tiles, a fine one (<= 4096) single pixels.
     {
         struct CutBox {
             float lo[3], hi[3];
@@ -1355,32 +1355,62 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             *a = {{n.c0xy.x, n.c0xy.z, n.cz.x}, {n.c0xy.y, n.c0xy.w, n.cz.y}, n.child0};
             *b = {{n.c1xy.x, n.c1xy.z, n.cz.z}, {n.c1xy.y, n.c1xy.w, n.cz.w}, n.child1};
         };
-        auto make_cut = [&](size_t max_boxes, std::vector<float> *out) {
-            std::vector<CutBox> done; // leaves: cannot be opened
-            std::priority_queue<CutBox> open;
-            if (!binary.empty() && binary[binary_root].left < 0) { // the whole scene is one leaf
-                const Bvh2Node &n = binary[binary_root];
-                done.push_back({{n.lo[0], n.lo[1], n.lo[2]}, {n.hi[0], n.hi[1], n.hi[2]}, -1});
-            } else if (!binary.empty() || !hs->nodes.empty()) {
-                CutBox a, b;
-                children(binary.empty() ? 0 : binary_root, &a, &b);
-                for (const CutBox &c : {a, b}) (c.link >= 0 ? (void)open.push(c) : (void)done.push_back(c));
-                while (!open.empty() && open.size() + done.size() < max_boxes) {
-                    const CutBox top = open.top();
-                    open.pop();
-                    children(top.link, &a, &b);
-                    for (const CutBox &c : {a, b}) (c.link >= 0 ? (void)open.push(c) : (void)done.push_back(c));
-                }
+        // Opens boxes best-first (largest area) until `max_boxes` are held; every box keeps the index of the seed it descends from.
+        struct Tagged {
+            CutBox box;
+            uint32_t seed;
+            bool operator<(const Tagged &o) const { return box.Area() < o.box.Area(); }
+        };
+        auto open_best_first = [&](std::vector<Tagged> seeds, size_t max_boxes) {
+            std::vector<Tagged> done; // leaves: cannot be opened
+            std::priority_queue<Tagged> open;
+            auto add = [&](const Tagged &t) {
+                if (t.box.hi[0] < t.box.lo[0] || t.box.hi[1] < t.box.lo[1] || t.box.hi[2] < t.box.lo[2]) return; // the empty box of a one-leaf tree
+                if (t.box.link >= 0) open.push(t);
+                else done.push_back(t);
+            };
+            for (const Tagged &t : seeds) add(t);
+            CutBox a, b;
+            while (!open.empty() && open.size() + done.size() < max_boxes) {
+                const Tagged top = open.top();
+                open.pop();
+                children(top.box.link, &a, &b);
+                add(Tagged{a, top.seed});
+                add(Tagged{b, top.seed});
             }
             for (; !open.empty(); open.pop()) done.push_back(open.top());
-            for (const CutBox &c : done)
-                if (c.hi[0] >= c.lo[0] && c.hi[1] >= c.lo[1] && c.hi[2] >= c.lo[2]) // skip the empty box of a one-leaf tree
-                    out->insert(out->end(), {c.lo[0], c.lo[1], c.lo[2], c.hi[0], c.hi[1], c.hi[2]});
-            for (const AnalyticPrim &p : hs->analytic)
-                out->insert(out->end(), {p.bmin[0], p.bmin[1], p.bmin[2], p.bmax[0], p.bmax[1], p.bmax[2]});
+            return done;
         };
-        make_cut(384, &hs->cull_boxes);
-        make_cut(4096, &hs->fine_cull_boxes);
+        std::vector<Tagged> roots;
+        if (!binary.empty() && binary[binary_root].left < 0) { // the whole scene is one leaf
+            const Bvh2Node &n = binary[binary_root];
+            if (n.hi[0] >= n.lo[0] && n.hi[1] >= n.lo[1] && n.hi[2] >= n.lo[2]) // (not the empty box of an empty tree)
+                roots.push_back({{{n.lo[0], n.lo[1], n.lo[2]}, {n.hi[0], n.hi[1], n.hi[2]}, -1}, 0u});
+        } else if (!binary.empty() || !hs->nodes.empty()) {
+            CutBox a, b;
+            children(binary.empty() ? 0 : binary_root, &a, &b);
+            roots.push_back({a, 0u});
+            roots.push_back({b, 0u});
+        }
+        // coarse cover; then every coarse box is opened further into its share of the fine cover (grouped by coarse box, so
+        // that a tile only looks at the fine boxes under the coarse boxes it meets)
+        std::vector<Tagged> coarse = open_best_first(roots, 384);
+        for (size_t i = 0; i < coarse.size(); ++i) coarse[i].seed = static_cast<uint32_t>(i);
+        std::vector<Tagged> fine = open_best_first(coarse, 4096);
+        std::stable_sort(fine.begin(), fine.end(), [](const Tagged &x, const Tagged &y) { return x.seed < y.seed; });
+        auto put = [](const CutBox &c, std::vector<float> *out) { out->insert(out->end(), {c.lo[0], c.lo[1], c.lo[2], c.hi[0], c.hi[1], c.hi[2]}); };
+        size_t f = 0;
+        for (size_t i = 0; i < coarse.size(); ++i) {
+            put(coarse[i].box, &hs->cull_boxes);
+            hs->cull_fine_begin.push_back(static_cast<uint32_t>(f));
+            for (; f < fine.size() && fine[f].seed == i; ++f) put(fine[f].box, &hs->fine_cull_boxes);
+        }
+        for (const AnalyticPrim &p : hs->analytic) { // an analytic primitive is its own coarse and fine box
+            hs->cull_fine_begin.push_back(static_cast<uint32_t>(hs->fine_cull_boxes.size() / 6));
+            for (std::vector<float> *out : {&hs->cull_boxes, &hs->fine_cull_boxes})
+                out->insert(out->end(), {p.bmin[0], p.bmin[1], p.bmin[2], p.bmax[0], p.bmax[1], p.bmax[2]});
+        }
+        hs->cull_fine_begin.push_back(static_cast<uint32_t>(hs->fine_cull_boxes.size() / 6));
     }
 
     // ---- triangle CDFs of mesh area lights (replaces the area-weighted BVH descent of blas.cpp:79-98) ----

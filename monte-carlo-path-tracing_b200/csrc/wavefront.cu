@@ -447,9 +447,12 @@ constexpr uint32_t kCullShortList = 384; // fine boxes a tile may short-list bef
 
 __global__ void __launch_bounds__(kThreads) k_cull_tiles(const __grid_constant__ BatchParams bp, const float *__restrict__ boxes,
                                                          uint32_t num_boxes, const float *__restrict__ fine_boxes, uint32_t num_fine,
-                                                         uint32_t num_local_tiles, unsigned long long *masks) {
+                                                         const uint32_t *__restrict__ fine_begin, uint32_t num_local_tiles,
+                                                         unsigned long long *masks) {
     __shared__ uint16_t short_all[kThreads / 32][kCullShortList];
+    __shared__ uint32_t short_count[kThreads / 32];
     uint16_t *short_list = short_all[threadIdx.x >> 5];
+    uint32_t *count_ptr = &short_count[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, num_warps = (gridDim.x * blockDim.x) >> 5;
     const V3 eye = mk3(bp.camera.eye);
@@ -462,60 +465,54 @@ __global__ void __launch_bounds__(kThreads) k_cull_tiles(const __grid_constant__
             const float i1 = fminf(i0 + kTileSize, static_cast<float>(bp.width)), j1 = fminf(j0 + kTileSize, static_cast<float>(bp.height));
             constexpr float kMargin = 0.5f; // pixels
             const Pyramid tile_pyramid = MakePyramid(bp, i0 - kMargin, i1 + kMargin, j0 - kMargin, j1 + kMargin);
+            if (lane == 0) *count_ptr = 0u;
+            __syncwarp();
+            // coarse boxes, lanes over boxes; a lane whose coarse box meets the tile looks at the fine boxes under it
             bool visible = false;
-            for (uint32_t b = lane; b < num_boxes; b += 32)
-                if (!BoxOutsidePyramid(tile_pyramid, eye, boxes + 6 * b)) visible = true;
+            for (uint32_t b = lane; b < num_boxes; b += 32) {
+                if (BoxOutsidePyramid(tile_pyramid, eye, boxes + 6 * b)) continue;
+                visible = true;
+                if (num_fine == 0) continue;
+                for (uint32_t f = fine_begin[b]; f < fine_begin[b + 1]; ++f) {
+                    if (BoxOutsidePyramid(tile_pyramid, eye, fine_boxes + 6 * f)) continue;
+                    const uint32_t at = atomicAdd(count_ptr, 1u);
+                    if (at < kCullShortList) short_list[at] = static_cast<uint16_t>(f);
+                }
+            }
             visible = __any_sync(0xffffffffu, visible);
+            __syncwarp();
+            const uint32_t count = *count_ptr;
             // the pixels of the tile that lie inside the image (lane k and k + 32 -> pixel (k % 8, k / 8))
             const unsigned in_lo = __ballot_sync(0xffffffffu, ti + (lane % kTileSize) < bp.width && tj + (lane / kTileSize) < bp.height);
             const unsigned in_hi = __ballot_sync(0xffffffffu, ti + (lane % kTileSize) < bp.width && tj + 4u + (lane / kTileSize) < bp.height);
             const unsigned long long inside = (static_cast<unsigned long long>(in_hi) << 32) | in_lo;
-            if (visible && num_fine == 0) mask = inside;
+            if (visible && (num_fine == 0 || count > kCullShortList)) mask = inside; // pixel level off, or too many candidates
             else if (visible) {
-                // fine boxes that meet the tile's pyramid
-                uint32_t count = 0;
-                bool overflow = false;
-                for (uint32_t b0 = 0; b0 < num_fine; b0 += 32) {
-                    const uint32_t b = b0 + lane;
-                    const bool meets = b < num_fine && !BoxOutsidePyramid(tile_pyramid, eye, fine_boxes + 6 * b);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, meets);
-                    const uint32_t at = count + __popc(ballot & ((1u << lane) - 1u));
-                    if (meets && at < kCullShortList) short_list[at] = static_cast<uint16_t>(b);
-                    count += __popc(ballot);
-                    if (count > kCullShortList) {
-                        overflow = true;
-                        break;
-                    }
-                }
-                __syncwarp();
-                if (overflow) mask = inside;
-                else {
-                    constexpr float kPixelMargin = 0.02f; // the samples of pixel i lie in [i, i + 1)
-                    unsigned lo_bits = 0u, hi_bits = 0u;
+                constexpr float kPixelMargin = 0.02f; // the samples of pixel i lie in [i, i + 1)
+                unsigned lo_bits = 0u, hi_bits = 0u;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t k = lane + 32u * half, pi = ti + (k % kTileSize), pj = tj + (k / kTileSize);
-                        bool sees = false;
-                        if (pi < bp.width && pj < bp.height) {
-                            const Pyramid pixel = MakePyramid(bp, pi - kPixelMargin, pi + 1.0f + kPixelMargin, pj - kPixelMargin, pj + 1.0f + kPixelMargin);
-                            for (uint32_t q = 0; q < count && !sees; ++q) sees = !BoxOutsidePyramid(pixel, eye, fine_boxes + 6u * short_list[q]);
-                        }
-                        const unsigned ballot = __ballot_sync(0xffffffffu, sees);
-                        if (half == 0) lo_bits = ballot;
-                        else hi_bits = ballot;
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t k = lane + 32u * half, pi = ti + (k % kTileSize), pj = tj + (k / kTileSize);
+                    bool sees = false;
+                    if (pi < bp.width && pj < bp.height) {
+                        const Pyramid pixel = MakePyramid(bp, pi - kPixelMargin, pi + 1.0f + kPixelMargin, pj - kPixelMargin, pj + 1.0f + kPixelMargin);
+                        for (uint32_t q = 0; q < count && !sees; ++q) sees = !BoxOutsidePyramid(pixel, eye, fine_boxes + 6u * short_list[q]);
                     }
-                    mask = (static_cast<unsigned long long>(hi_bits) << 32) | lo_bits;
+                    const unsigned ballot = __ballot_sync(0xffffffffu, sees);
+                    if (half == 0) lo_bits = ballot;
+                    else hi_bits = ballot;
                 }
-                __syncwarp();
+                mask = (static_cast<unsigned long long>(hi_bits) << 32) | lo_bits;
             }
+            __syncwarp();
         }
         if (lane == 0) masks[t] = mask;
     }
 }
 
-// Deterministic stream compaction of the pixel masks by ONE CTA (at most a few 10^5 tiles): list[0 .. pixels) = ascending local
-// indices (tile * 64 + pixel in tile) of the set bits, counts[0] = pixels, counts[1] = tiles with at least one.
-__global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned long long *masks, uint32_t n, uint32_t *list, uint32_t *counts) {
+// Exclusive prefix sums of the per-tile pixel counts by ONE CTA (at most a few 10^5 tiles): offsets[t] = position of tile t's first
+// surviving pixel in the job's pixel list, counts[0] = pixels, counts[1] = tiles with at least one.
+__global__ void __launch_bounds__(1024) k_scan_tiles(const unsigned long long *masks, uint32_t n, uint32_t *offsets, uint32_t *counts) {
     __shared__ uint32_t warp_sums[32], warp_tiles[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t chunk = (n + blockDim.x - 1) / blockDim.x, begin = min(n, tid * chunk), end = min(n, begin + chunk);
@@ -546,8 +543,26 @@ __global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned long long
     }
     __syncthreads();
     uint32_t out = warp_sums[warp] + incl - mine;
-    for (uint32_t i = begin; i < end; ++i)
-        for (unsigned long long m = masks[i]; m != 0ull; m &= m - 1ull) list[out++] = i * kTilePixels + (__ffsll(static_cast<long long>(m)) - 1);
+    for (uint32_t i = begin; i < end; ++i) {
+        offsets[i] = out;
+        out += __popcll(masks[i]);
+    }
+}
+
+// The job's pixel list: ascending local indices (tile * 64 + pixel in tile) of the set mask bits.  One warp per tile.
+__global__ void __launch_bounds__(kThreads) k_list_pixels(const unsigned long long *masks, const uint32_t *offsets, uint32_t n, uint32_t *list) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, num_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = warp; t < n; t += num_warps) {
+        const unsigned long long m = masks[t];
+        if (m == 0ull) continue;
+        const uint32_t base = offsets[t];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t k = lane + 32u * half;
+            if ((m >> k) & 1ull) list[base + __popcll(m & ((1ull << k) - 1ull))] = t * kTilePixels + k;
+        }
+    }
 }
 
 // renderer.cpp:76-84: clamp each SAMPLE to <= 1 per channel (Q2), then sum the pixel's samples.
@@ -723,12 +738,13 @@ void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b2
 }
 
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
-                     unsigned long long *masks, uint32_t *pixel_list, uint32_t *counts) {
+                     unsigned long long *masks, uint32_t *offsets, uint32_t *pixel_list, uint32_t *counts) {
     const int warps_per_cta = kThreads / 32;
-    const int blocks = static_cast<int>(std::min<uint32_t>(lc.blocks, (num_local_tiles + warps_per_cta - 1) / warps_per_cta));
-    k_cull_tiles<<<std::max(blocks, 1), kThreads, 0, lc.stream>>>(bp, scene.cull_boxes, scene.num_cull_boxes, scene.fine_cull_boxes,
-                                                                 scene.num_fine_cull_boxes, num_local_tiles, masks);
-    k_compact_tiles<<<1, 1024, 0, lc.stream>>>(masks, num_local_tiles, pixel_list, counts);
+    const int blocks = std::max(1, static_cast<int>(std::min<uint32_t>(lc.blocks, (num_local_tiles + warps_per_cta - 1) / warps_per_cta)));
+    k_cull_tiles<<<blocks, kThreads, 0, lc.stream>>>(bp, scene.cull_boxes, scene.num_cull_boxes, scene.fine_cull_boxes, scene.num_fine_cull_boxes,
+                                                    scene.cull_fine_begin, num_local_tiles, masks);
+    k_scan_tiles<<<1, 1024, 0, lc.stream>>>(masks, num_local_tiles, offsets, counts);
+    k_list_pixels<<<blocks, kThreads, 0, lc.stream>>>(masks, offsets, num_local_tiles, pixel_list);
 }
 
 void LaunchSettle(const LaunchConfig &lc, Counters *counters, int which_queue, bool reset_shadow, ShadowQueue sq, float *radiance,

@@ -169,10 +169,10 @@ int LaunchTrace(const LaunchConfig &lc, const DeviceScene &scene, const BatchPar
 // One launch per shading bin in use (or a single launch when the scene is not binned); returns the number of launches.
 int LaunchShade(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue qin,
                 int which_in, PathQueue qout, ShadeBins bins, ShadowQueue sq, float *radiance, Counters *counters, uint32_t capacity);
-// Visibility pre-pass: flags[t] = 1 if local tile t can see one of the scene's cull boxes, then the ascending list of
-// such tiles in list[0 .. count) with count stored at list[num_local_tiles].
+// Visibility pre-pass: masks[t] = the pixels of local tile t whose camera rays can reach one of the scene's cull boxes, offsets[t] =
+// exclusive prefix sum of their counts, pixel_list = the ascending list of those pixels, counts = {pixels, non-empty tiles}.
 void LaunchCullTiles(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t num_local_tiles,
-                     unsigned long long *masks, uint32_t *pixel_list, uint32_t *counts);
+                     unsigned long long *masks, uint32_t *offsets, uint32_t *pixel_list, uint32_t *counts);
 // Path-at-a-time tail (tail_kernel.cu): launched after the traversal of bounce `depth - 1`; takes queue `which` over and
 // finishes its paths if it holds at most `threshold` entries, else returns at once.  `depth` = the bounce shade would run.
 void LaunchTail(const LaunchConfig &lc, const DeviceScene &scene, const BatchParams &bp, uint32_t depth, PathQueue q, int which,
