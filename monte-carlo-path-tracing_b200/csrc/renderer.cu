@@ -825,10 +825,17 @@ int b200pt_get_stats(b200pt_handle h, b200pt_stats *out) {
                 ks[k]->prim_tests = host_counters.cls[k].prim_tests;
             }
         }
+        const bool dump = getenv("B200PT_DUMP_TIMELINE") != nullptr; // every timed launch of the frame on stderr: class, start, duration
+        static const char *const kClassNames[kNumClasses] = {"primary", "trace", "shadow", "shade", "other", "tail"};
         for (const b200pt_context::TimedLaunch &t : h->timed) {
             float t_ms = 0.0f;
             CU_CHECK(h, cudaEventElapsedTime(&t_ms, t.begin, t.end));
             ks[t.cls]->ms += t_ms;
+            if (dump) {
+                float at = 0.0f;
+                cudaEventElapsedTime(&at, h->ev_begin, t.begin);
+                fprintf(stderr, "[b200pt timeline] %-8s at %8.3f ms  %8.3f ms\n", kClassNames[t.cls], at, t_ms);
+            }
         }
         h->timing_pending = false;
     }

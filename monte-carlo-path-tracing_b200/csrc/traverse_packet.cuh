@@ -89,7 +89,11 @@ __device__ __forceinline__ void TraversePacket(const DeviceScene &scene, uint32_
                     // near child first, as most of the lanes that hit something see it
                     const unsigned first1 = __ballot_sync(0xffffffffu, hit1 && (!hit0 || c1min < c0min));
                     const bool swap = 2 * __popc(first1) > __popc(m0 | m1);
-                    stack[sp++] = swap ? child0 : child1;
+                    // one writer, fenced on both sides: the slot may still be being read (a pop) by the slower lanes of the warp
+                    __syncwarp();
+                    if (lane == 0) stack[sp] = swap ? child0 : child1;
+                    ++sp;
+                    __syncwarp();
                     cur = swap ? child1 : child0;
                 } else {
                     cur = m0 != 0u ? child0 : child1;
