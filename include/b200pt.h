@@ -346,6 +346,16 @@ enum {
 #define B200PT_EVAL_OUT 16
 int b200pt_debug_eval(b200pt_handle h, uint32_t what, uint32_t id, uint64_t n, const float *in_host, float *out_host);
 
+/* Test hook ("exact mode"): renders the frame with the REFERENCE's loop shape and random-number stream — one thread per
+ * pixel, its samples in order, one LCG per pixel seeded with Tea<4>(pixel_offset, 0) that runs on through every sample and
+ * vertex (Renderer::DrawPixel renderer.cpp:62-85, RandomFloat math.hpp:57-63, the draws in the order GCC evaluates the
+ * reference's call arguments) — around the product's own device functions (ShadeVertex, the per-lane traversal of the
+ * scene's tree).  Each sample takes the decisions of the same sample of the reference's --cpu frame, so the two frames agree
+ * PER PIXEL to float rounding, except where a last-bit difference (CUDA vs glibc libm, fused vs separate rounding) flips a
+ * decision.  width / height / spp 0 = the scene's.  frame_host: width * height * 3 floats, rows top to bottom (the layout
+ * of Renderer::Draw).  Slow by design (no wavefront, no sorting); refuses alpha-tested scenes (B200PT_EINVAL). */
+int b200pt_debug_render_replay(b200pt_handle h, uint32_t width, uint32_t height, uint32_t spp, float *frame_host);
+
 /* ---- scene packs: a lossless binary serialisation of b200pt_scene_desc, so a
  * scene parsed once by the reference's XML parser can travel without it. ---- */
 typedef struct b200pt_scene b200pt_scene;

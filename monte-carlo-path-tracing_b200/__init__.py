@@ -83,6 +83,7 @@ EXPORTED_SYMBOLS = [
     "b200pt_render_tiles_device", "b200pt_assemble_tiles_device", "b200pt_get_stats", "b200pt_last_error",
     "b200pt_get_kulla_conty", "b200pt_get_envmap_tables", "b200pt_scene_load", "b200pt_scene_save",
     "b200pt_scene_get_desc", "b200pt_scene_free", "b200pt_debug_trace", "b200pt_debug_eval",
+    "b200pt_debug_render_replay",
 ]
 
 _lib = None
@@ -121,6 +122,7 @@ def lib():
     L.b200pt_scene_free.restype = None
     L.b200pt_debug_trace.argtypes = [vp, vp, u64, u32, vp]
     L.b200pt_debug_eval.argtypes = [vp, u32, u32, u64, vp, vp]
+    L.b200pt_debug_render_replay.argtypes = [vp, u32, u32, u32, vp]
     _lib = L
     return L
 
@@ -215,6 +217,14 @@ class Renderer:
         out = np.zeros((len(inputs), EVAL_OUT), dtype=np.float32)
         _check(lib().b200pt_debug_eval(self._h, what, index, len(inputs), inputs.ctypes.data, out.ctypes.data), self._h)
         return out
+
+    def render_replay(self, width=0, height=0, spp=0):
+        """Test hook (b200pt_debug_render_replay): the frame rendered with the reference's loop shape and per-pixel LCG
+        stream (Renderer::DrawPixel, renderer.cpp:62-85) around the product's device functions -> float32 [h, w, 3]."""
+        width, height, spp = width or self.scene.width, height or self.scene.height, spp or self.scene.spp
+        frame = np.zeros((height, width, 3), dtype=np.float32)
+        _check(lib().b200pt_debug_render_replay(self._h, width, height, spp, frame.ctypes.data), self._h)
+        return frame
 
     def stats(self):
         s = Stats()

@@ -5,10 +5,13 @@
 // same seed and can be compared pointwise (tests/test_gpu_pointwise.py against ref_eval of oracle/ref_glue.cpp).  The
 // functions are the very ones k_shade inlines; nothing here is on the render path.
 #define B200PT_RNG_REPLAY 1
+#include <cstdio>
+
 #include <cuda_runtime.h>
 
 #include "b200pt.h"
-#include "shading.cuh"
+#include "shade_kernel.cuh"
+#include "traverse_wide.cuh"
 
 namespace b200pt {
 
@@ -104,7 +107,106 @@ __global__ void k_debug_eval(const __grid_constant__ DeviceScene scene, uint32_t
     out[B200PT_EVAL_OUT - 1] = what == B200PT_EVAL_SURFACE ? out[B200PT_EVAL_OUT - 1] : __uint_as_float(rng.state);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_debug_replay (b200pt_debug_render_replay): the reference's own loop shape and random-number stream — one thread per
+// pixel, the samples of the pixel one after the other, ONE LCG per pixel seeded with Tea<4>(pixel_offset, 0) that runs on
+// through every sample and every vertex (Renderer::DrawPixel renderer.cpp:62-85, RandomFloat math.hpp:57-63) — around the
+// product's ShadeVertex and per-lane traversal.  Every sample then takes the same decisions as the same sample of the
+// reference's --cpu run (up to the last-bit differences between CUDA's and glibc's sinf/cosf/expf/powf, which flip a
+// decision once in ~10^5), so frames compare PER PIXEL far below the Monte Carlo noise
+// (tests/test_gpu_replay.py).  Alpha-tested scenes are refused: the reference draws the numbers of its opacity tests
+// inside its own BVH walk, whose visiting order the product's tree does not share.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t Tea4(uint32_t v0, uint32_t v1) { // math.hpp:43-54
+    uint32_t s0 = 0;
+    for (int n = 0; n < 4; ++n) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v0;
+}
+
+__device__ __forceinline__ bool ReplayTrace(const DeviceScene &scene, const Ray &ray, bool any, HitRec *hit) {
+    TraversalCounters unused;
+    if (scene.num_wide_nodes > 0) return TraverseSingleWide(scene, ray, any, false, Rng(0u), hit, false, &unused);
+    return TraverseSingle(scene, ray, any, false, Rng(0u), hit, false, &unused);
+}
+
+template <bool VOL>
+__global__ void __launch_bounds__(64) k_debug_replay(const __grid_constant__ DeviceScene scene, const __grid_constant__ BatchParams bp, float *frame,
+                                                             uint32_t trace_pixel) {
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inside = pixel < bp.width * bp.height;
+    const uint32_t i = inside ? pixel % bp.width : 0u, j = inside ? pixel / bp.width : 0u;
+    const DIntegrator &ig = scene.integrator;
+    uint32_t seed = Tea4(pixel * 3u, 0u);
+    V3 color = mk3(0.0f);
+    const bool trace = pixel == trace_pixel; // B200PT_REPLAY_TRACE="i,j": the vertices of one pixel's paths, as ORACLE_TRACE_PIXEL prints them
+    for (uint32_t k = 0; k < bp.spp; ++k) {
+        if (trace) printf("[trace] sample %u\n", k);
+        // renderer.cpp:66-75
+        const float u = k * bp.spp_inv, v = VanDerCorput2(k + 1);
+        const float x = 2.0f * (i + u) / static_cast<int>(bp.width) - 1.0f, y = 1.0f - 2.0f * (j + v) / static_cast<int>(bp.height);
+        PathVertex pv;
+        pv.ray.o = mk3(bp.camera.eye);
+        pv.ray.d = Normalize(mk3(bp.camera.front) + x * mk3(bp.camera.view_dx) + y * mk3(bp.camera.view_dy));
+        pv.ray.tmin = kEpsilonDistance, pv.ray.tmax = kMaxFloat;
+        pv.att = mk3(1.0f), pv.wo_prev = -pv.ray.d, pv.pdf_sample = 0.0f;
+        pv.slot = 0, pv.ray_medium = kInvalid;
+        pv.replay_state = seed;
+        V3 L = mk3(0.0f);
+        bool alive = inside && ReplayTrace(scene, pv.ray, false, &pv.hit);
+        if (inside && !alive) { // path.cpp:24-35
+            if (ig.id_envmap != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[ig.id_envmap], pv.ray.d);
+            if (ig.id_sun != kInvalid) L += EmitterEvaluateDir(scene, scene.emitters[ig.id_sun], pv.ray.d);
+        }
+        // the same loop as k_tail (tail_kernel.cu): every lane of the warp walks its path until all are done
+        for (uint32_t depth = 1; __any_sync(0xffffffffu, alive); ++depth) {
+            PathNext next;
+            V3 Ladd;
+            const bool was_alive = alive;
+            if (trace && alive)
+                printf("[trace] v%u state %08x t %.9g L %.9g %.9g %.9g att %.9g %.9g %.9g\n", depth, pv.replay_state, pv.hit.t, L.x, L.y, L.z, pv.att.x,
+                       pv.att.y, pv.att.z);
+            alive = ShadeVertex<VOL, kAnyBsdf>(
+                scene, bp, depth, alive, pv,
+                [&](const ShadowCandidate &sc) {
+                    if (!(sc.valid && (sc.c.x != 0.0f || sc.c.y != 0.0f || sc.c.z != 0.0f))) return;
+                    Ray ray;
+                    ray.o = sc.o, ray.d = sc.d, ray.tmin = kEpsilonDistance, ray.tmax = sc.tmax;
+                    HitRec unused;
+                    if (!ReplayTrace(scene, ray, true, &unused)) L += sc.c;
+                },
+                &next, &Ladd);
+            if (was_alive) {
+                L += Ladd;
+                pv.replay_state = next.replay_state;
+            }
+            if (depth >= kMaxTailDepth) alive = false;
+            if (alive) {
+                pv.ray.o = next.o, pv.ray.d = next.d, pv.ray.tmin = kEpsilonDistance, pv.ray.tmax = kMaxFloat;
+                pv.att = next.att, pv.pdf_sample = next.pdf, pv.ray_medium = next.medium, pv.wo_prev = next.wo;
+                ReplayTrace(scene, pv.ray, false, &pv.hit);
+                if (!VOL && pv.hit.prim == kPrimMiss && ig.id_envmap == kInvalid) alive = false;
+            }
+        }
+        seed = pv.replay_state;
+        color += mk3(fminf(L.x, 1.0f), fminf(L.y, 1.0f), fminf(L.z, 1.0f)); // renderer.cpp:76-80 (Q2)
+    }
+    color = color * bp.spp_inv;
+    if (inside) frame[3 * pixel] = color.x, frame[3 * pixel + 1] = color.y, frame[3 * pixel + 2] = color.z;
+}
+
 } // namespace
+
+void LaunchDebugReplay(cudaStream_t stream, const DeviceScene &scene, const BatchParams &bp, float *frame, uint32_t trace_pixel) {
+    const uint32_t pixels = bp.width * bp.height;
+    if (scene.integrator.type == B200PT_INTEGRATOR_VOLPATH)
+        k_debug_replay<true><<<(pixels + 63) / 64, 64, 0, stream>>>(scene, bp, frame, trace_pixel);
+    else
+        k_debug_replay<false><<<(pixels + 63) / 64, 64, 0, stream>>>(scene, bp, frame, trace_pixel);
+}
 
 void LaunchDebugEval(cudaStream_t stream, const DeviceScene &scene, uint32_t what, uint32_t id, uint32_t n, const float *in, float *out) {
     k_debug_eval<<<(n + 127) / 128, 128, 0, stream>>>(scene, what, id, n, in, out);

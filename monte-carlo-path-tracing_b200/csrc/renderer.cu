@@ -893,6 +893,36 @@ int b200pt_debug_eval(b200pt_handle h, uint32_t what, uint32_t id, uint64_t n, c
     return B200PT_OK;
 }
 
+int b200pt_debug_render_replay(b200pt_handle h, uint32_t width, uint32_t height, uint32_t spp, float *frame_host) {
+    if (!h || !frame_host) return SetGlobalError(B200PT_EINVAL, "b200pt_debug_render_replay: null argument");
+    if (h->scene.integrator.has_opacity)
+        return h->Fail(B200PT_EINVAL, "b200pt_debug_render_replay: alpha-tested scenes draw their opacity numbers in the reference's own BVH order.");
+    if (width == 0) width = static_cast<uint32_t>(h->host.camera.width);
+    if (height == 0) height = static_cast<uint32_t>(h->host.camera.height);
+    if (spp == 0) spp = h->host.camera.spp;
+    if (width == 0 || height == 0 || spp == 0 || static_cast<uint64_t>(width) * height > (1ull << 24))
+        return h->Fail(B200PT_EINVAL, "b200pt_debug_render_replay: bad frame size.");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    BatchParams bp{};
+    bp.camera = MakeCamera(h->host.camera, width, height);
+    bp.width = width, bp.height = height, bp.spp = spp;
+    bp.spp_inv = 1.0f / spp;
+    bp.sample_count = 1;
+    DeviceArray<float> frame;
+    CU_CHECK(h, frame.Alloc(3ull * width * height));
+    uint32_t trace_pixel = 0xffffffffu; // B200PT_REPLAY_TRACE="i,j": print the path vertices of that pixel (debug_eval.cu)
+    if (const char *e = getenv("B200PT_REPLAY_TRACE")) {
+        int ti = -1, tj = -1;
+        if (sscanf(e, "%d,%d", &ti, &tj) == 2 && ti >= 0 && tj >= 0 && static_cast<uint32_t>(ti) < width && static_cast<uint32_t>(tj) < height)
+            trace_pixel = static_cast<uint32_t>(tj) * width + static_cast<uint32_t>(ti);
+    }
+    LaunchDebugReplay(h->stream, h->scene, bp, frame.ptr, trace_pixel);
+    CU_CHECK(h, cudaGetLastError());
+    CU_CHECK(h, cudaMemcpyAsync(frame_host, frame.ptr, 3ull * width * height * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    return B200PT_OK;
+}
+
 const char *b200pt_last_error(b200pt_handle h) { return h ? h->error.c_str() : GlobalError(); }
 
 int b200pt_get_kulla_conty(b200pt_handle h, float *brdf_avg, float *albedo_avg) {

@@ -1413,19 +1413,50 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
         hs->cull_fine_begin.push_back(static_cast<uint32_t>(hs->fine_cull_boxes.size() / 6));
     }
 
-    // ---- triangle CDFs of mesh area lights (replaces the area-weighted BVH descent of blas.cpp:79-98) ----
+    // ---- triangle CDFs of mesh area lights (stand for the area-weighted BVH descent of blas.cpp:79-98) ----
+    // BLAS::Sample walks the instance's LBVH from the root with thresh = area * xi_0, left when thresh < area(left): a CDF over the
+    // LEAVES IN TREE ORDER, and the leaves of a Morton-built tree (bvh_builder.cpp:92-141) stand in the order of their sort keys
+    // (30-bit Morton code of the box centre relative to the instance's bounds) << 32 | triangle index.  The CDF is laid out in that
+    // order, so the same xi_0 picks the same triangle here as in the reference (what the exact-mode comparison needs; any
+    // order gives the same distribution).
+    auto expand_bits = [](uint32_t v) { // bvh_builder.cpp:16-22
+        v = (v * 0x00010001u) & 0xFF0000FFu;
+        v = (v * 0x00000101u) & 0x0F00F00Fu;
+        v = (v * 0x00000011u) & 0xC30C30C3u;
+        v = (v * 0x00000005u) & 0x49249249u;
+        return v;
+    };
     for (uint32_t light = 0; light < hs->map_area_light_instance.size(); ++light) {
         const uint32_t inst = hs->map_area_light_instance[light];
         DInstance &o = hs->instances[inst];
         if (o.analytic != kInvalid) continue;
         o.light_tri_begin = static_cast<uint32_t>(hs->light_tri_ids.size());
-        double total = 0.0;
+        std::vector<uint32_t> members; // positions in leaf order
+        Box all;
         for (size_t i = 0; i < nt; ++i)
             if (tris[order[i]].inst == inst) {
-                hs->light_tri_ids.push_back(static_cast<uint32_t>(i));
-                total += tris[order[i]].area;
-                hs->light_tri_cdf.push_back(static_cast<float>(total));
+                members.push_back(static_cast<uint32_t>(i));
+                all.Grow(boxes[order[i]]);
             }
+        const V3 size = all.hi - all.lo;
+        std::vector<std::pair<uint64_t, uint32_t>> keyed(members.size());
+        for (size_t k = 0; k < members.size(); ++k) {
+            const Box &b = boxes[order[members[k]]];
+            const V3 c = (b.lo + b.hi) * 0.5f;
+            // Vec3 / Vec3 of the reference multiplies by the reciprocal (vec3.cpp:128-133); a flat axis gives 0 * inf = NaN -> cell 0
+            const float rel[3] = {(c.x - all.lo.x) * (1.0f / size.x), (c.y - all.lo.y) * (1.0f / size.y), (c.z - all.lo.z) * (1.0f / size.z)};
+            uint32_t q[3];
+            for (int a = 0; a < 3; ++a) q[a] = static_cast<uint32_t>(fminf(fmaxf(rel[a] * 1024.0f, 0.0f), 1023.0f)); // :39-48 (0/0 -> 0)
+            const uint64_t morton = expand_bits(q[0]) * 4u + expand_bits(q[1]) * 2u + expand_bits(q[2]);
+            keyed[k] = {(morton << 32) | order[members[k]], members[k]}; // scene-wide triangle index: same order as the instance-local one
+        }
+        std::sort(keyed.begin(), keyed.end());
+        double total = 0.0;
+        for (const auto &kv : keyed) {
+            hs->light_tri_ids.push_back(kv.second);
+            total += tris[order[kv.second]].area;
+            hs->light_tri_cdf.push_back(static_cast<float>(total));
+        }
         o.light_tri_count = static_cast<uint32_t>(hs->light_tri_ids.size()) - o.light_tri_begin;
         for (uint32_t k = 0; k < o.light_tri_count; ++k)
             hs->light_tri_cdf[o.light_tri_begin + k] = static_cast<float>(hs->light_tri_cdf[o.light_tri_begin + k] / total);

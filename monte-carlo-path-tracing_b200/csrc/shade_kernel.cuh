@@ -64,6 +64,9 @@ struct PathVertex {
     float pdf_sample;     // pdf of the direction sample that produced the segment
     uint32_t slot, ray_medium;
     HitRec hit;
+#ifdef B200PT_RNG_REPLAY
+    uint32_t replay_state; // test build (debug_eval.cu): the per-pixel LCG runs on from vertex to vertex, as in the reference
+#endif
 };
 
 // The continuation a vertex produces (valid when ShadeVertex returns true).
@@ -71,6 +74,9 @@ struct PathNext {
     V3 o, d, att, wo;
     float pdf;
     uint32_t medium;
+#ifdef B200PT_RNG_REPLAY
+    uint32_t replay_state;
+#endif
 };
 
 // One iteration of the reference's path loop (ShadePath path.cpp:8-236 / ShadeVolPath volpath.cpp:8-485) for the vertex `v`,
@@ -85,14 +91,17 @@ __device__ __forceinline__ bool ShadeVertex(const DeviceScene &scene, const Batc
     Ray ray = v.ray;
     V3 att = v.att, wo = alive ? -ray.d : mk3(0.0f), wo_prev = v.wo_prev, Ladd = mk3(0.0f);
     float pdf_sample = v.pdf_sample;
-    const uint32_t slot = v.slot;
     uint32_t ray_medium = v.ray_medium;
     const HitRec hit = v.hit;
-    const uint32_t local_pixel = JobPixelToLocal(bp, bp.pixel_begin + slot / bp.sample_count);
-    const uint32_t sample = bp.sample_begin + slot % bp.sample_count;
+#ifdef B200PT_RNG_REPLAY
+    Rng rng(v.replay_state);
+#else
+    const uint32_t local_pixel = JobPixelToLocal(bp, bp.pixel_begin + v.slot / bp.sample_count);
+    const uint32_t sample = bp.sample_begin + v.slot % bp.sample_count;
     uint32_t px = 0, py = 0;
     LocalPixelToImage(bp, local_pixel, &px, &py);
     Rng rng(py * bp.width + px, sample, depth, bp.key);
+#endif
 
     // ---- the vertex this segment arrives at ----
     const bool has_hit = hit.prim != kPrimMiss;
@@ -312,6 +321,9 @@ __device__ __forceinline__ bool ShadeVertex(const DeviceScene &scene, const Batc
     next->o = vertex_pos, next->d = next_d, next->att = att, next->wo = wo;
     next->pdf = pdf_sample;
     next->medium = scattering ? ray_medium : kInvalid;
+#ifdef B200PT_RNG_REPLAY
+    next->replay_state = rng.state;
+#endif
     *Ladd_out = Ladd;
     return alive;
 }

@@ -182,6 +182,8 @@ void LaunchDebugTrace(const LaunchConfig &lc, const DeviceScene &scene, const b2
                       bool raw_prim, bool packet, b200pt_debug_hit *out, uint32_t *work_counter);
 // Test hook (b200pt_debug_eval, debug_eval.cu): leaf functions of the shading stage at caller-supplied inputs.
 void LaunchDebugEval(cudaStream_t stream, const DeviceScene &scene, uint32_t what, uint32_t id, uint32_t n, const float *in, float *out);
+// Test hook (b200pt_debug_render_replay, debug_eval.cu): a frame with the reference's loop shape and random-number stream.
+void LaunchDebugReplay(cudaStream_t stream, const DeviceScene &scene, const BatchParams &bp, float *frame, uint32_t trace_pixel);
 constexpr uint32_t kMaxTailDepth = 4096; // = kMaxRounds of the host loop
 // Adds the contributions of the shadow rays the last k_trace marked unoccluded, then resets queue `which_queue` (>= 0), the
 // shadow queue (reset_shadow) and the traversal work counter for the next bounce.

@@ -15,6 +15,7 @@
  */
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1719,6 +1720,13 @@ static Vec3 EvaluateDirectLight(const Scene *s, const Hit *hit, Vec3 position, V
     return L;
 }
 
+/* Debugging aid for the exact-mode comparison (tools/replay_trace.py): ORACLE_TRACE_PIXEL="i,j" prints, for that pixel, the
+ * state of every path vertex (LCG state, hit distance, radiance so far, throughput) to stderr. */
+static __thread int g_trace = 0;
+static void TraceVertex(uint32_t depth, uint32_t seed, float t, Vec3 L, Vec3 att) {
+    if (g_trace) fprintf(stderr, "[trace] v%u state %08x t %.9g L %.9g %.9g %.9g att %.9g %.9g %.9g\n", depth, seed, t, L.x, L.y, L.z, att.x, att.y, att.z);
+}
+
 static Vec3 ShadePath(const Scene *s, Vec3 eye, Vec3 look_dir, uint32_t *seed) { /* path.cpp:8-136 */
     Vec3 L = v3s(0);
     Ray ray = MakeRay(s, eye, look_dir);
@@ -1738,6 +1746,7 @@ static Vec3 ShadePath(const Scene *s, Vec3 eye, Vec3 look_dir, uint32_t *seed) {
         }
     }
     Vec3 attenuation = v3s(1), wo = neg(look_dir);
+    TraceVertex(1, *seed, ray.t_max, L, attenuation);
     for (uint32_t depth = 1; depth < s->depth_rr || (depth < s->depth_max && RandomFloat(seed) < s->pdf_rr); ++depth) {
         L = add(L, mul(attenuation, EvaluateDirectLight(s, &hit, hit.position, wo, seed, 0, NULL, NULL)));
         BsdfSampleRec rec = SampleRayPath(s, wo, &hit, bsdf, seed);
@@ -1770,6 +1779,7 @@ static Vec3 ShadePath(const Scene *s, Vec3 eye, Vec3 look_dir, uint32_t *seed) {
             }
         }
         wo = rec.wi;
+        TraceVertex(depth + 1, *seed, ray.t_max, L, attenuation);
         if (depth >= s->depth_rr) attenuation = muls(attenuation, s->pdf_rr_rcp);
     }
     return L;
@@ -1823,6 +1833,7 @@ static Vec3 ShadeVolPath(const Scene *s, Vec3 eye, Vec3 look_dir, uint32_t *seed
     }
     Vec3 wi = v3s(0);
     float pdf_sample = 0;
+    TraceVertex(1, *seed, ray.t_max, L, attenuation);
     for (uint32_t depth = 1; depth < s->depth_rr || (depth < s->depth_max && RandomFloat(seed) < s->pdf_rr); ++depth) {
         if (scattering) {
             L = add(L, mul(attenuation, EvaluateDirectLight(s, NULL, medium_hit_position, wo, seed, 1, medium_hit_medium, medium_hit_medium)));
@@ -1901,6 +1912,7 @@ static Vec3 ShadeVolPath(const Scene *s, Vec3 eye, Vec3 look_dir, uint32_t *seed
             wo = wi;
             if (depth >= s->depth_rr) attenuation = muls(attenuation, s->pdf_rr_rcp);
         }
+        TraceVertex(depth + 1, *seed, ray.t_max, L, attenuation);
     }
     return L;
 }
@@ -1910,7 +1922,12 @@ static void DrawPixel(const Scene *s, uint32_t i, uint32_t j, float *frame) {
     const uint32_t pixel_offset = (j * s->width + i) * 3;
     uint32_t seed = oracle_tea4(pixel_offset, 0);
     Vec3 color = v3s(0), temp;
+    int trace_i = -1, trace_j = -1;
+    const char *trace_env = getenv("ORACLE_TRACE_PIXEL");
+    if (trace_env != NULL) sscanf(trace_env, "%d,%d", &trace_i, &trace_j);
+    g_trace = (int)i == trace_i && (int)j == trace_j;
     for (uint32_t k = 0; k < s->spp; ++k) {
+        if (g_trace) fprintf(stderr, "[trace] sample %u\n", k);
         const float u = k * s->spp_inv, v = oracle_van_der_corput2(k + 1), x = 2.0f * (i + u) / s->width - 1.0f,
                     y = 1.0f - 2.0f * (j + v) / s->height;
         const Vec3 look_dir = normalize(add(add(s->front, smul(x, s->view_dx)), smul(y, s->view_dy)));

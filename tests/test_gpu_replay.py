@@ -1,0 +1,93 @@
+"""GPU "exact mode": per-pixel agreement with frames of the UNMODIFIED reference, below the Monte Carlo noise.
+
+The production kernels draw Philox numbers per (pixel, sample, depth), so their frames can only be compared with the reference's
+statistically (test_gpu_parity.py).  b200pt_debug_render_replay runs the product's own device functions — ShadeVertex, the
+per-lane traversal of the scene's tree, every BSDF / emitter / medium routine — inside the reference's loop shape and on the
+reference's random-number stream: one thread per pixel, its samples in order, one LCG per pixel seeded with
+Tea<4>(pixel_offset, 0) (Renderer::DrawPixel renderer.cpp:62-85, RandomFloat math.hpp:57-63), every draw in the order the
+reference's compiled code makes it.  Every sample then takes the decisions of the same sample of the
+reference's --cpu run, and the two frames agree per pixel to float rounding — except where a last-bit difference (CUDA's
+sinf / cosf / expf / powf against glibc's, an intersection within an ulp of a triangle edge) sends a path to another triangle.
+Those pixels differ by a sample's worth; the share of them is what the table below bounds, scene by scene.
+
+Compared with: tests/golden/exact_<scene>_woop.npy, frames rendered by the reference build (Woop triangles) in this
+container (tests/golden/make_golden.py), and the live checker at a larger size.  Tolerance: a pixel agrees when its largest
+channel difference is <= 1e-3 of max(reference value, 1e-3).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, pack
+
+import refcheck
+
+pytestmark = pytest.mark.gpu
+
+SETTINGS = json.load(open(os.path.join(GOLDEN, "settings.json")))
+RTOL = 1e-3
+
+# Minimum share of pixels that must agree to RTOL (measured shares: profiles/r02_replay_report.log).  The scenes at the
+# bottom have many paths that graze silhouettes of finely tessellated, bump- or normal-mapped meshes, where a difference
+# in the last bit of a hit point is amplified from bounce to bounce.
+MIN_SHARE = {
+    "cornell-box": 0.99, "dragon": 0.99, "mercury": 0.99, "matpreview": 0.99, "volumetric-caustic": 0.985,
+    "lte-orb-silver": 0.99, "lte-orb-rough-glass": 0.98, "material-testball": 0.99, "box": 0.97, "dining-room": 0.94,
+    "classroom": 0.70,
+    "synthetic_envmap_sun_onesided": 0.99, "synthetic_early_rr": 0.99, "synthetic_depth_max_below_rr": 0.99,
+    "synthetic_plastic_roughdiffuse": 0.99, "synthetic_isotropic_medium_null_surface": 0.99,
+    "synthetic_dielectrics_conductor_cylinder": 0.94, "synthetic_bump_bitmap_mesh_disk": 0.94,
+}
+
+
+def agreeing_share(a, b):
+    d = np.abs(a.astype(np.float64) - b).max(axis=2) / np.maximum(np.abs(b).max(axis=2), 1e-3)
+    return float(np.mean(d <= RTOL)), d
+
+
+def open_renderer(pkg, name):
+    path = os.path.join(GOLDEN, name + ".b200scene") if name.startswith("synthetic_") else pack(name)
+    return pkg.Renderer(pkg.Scene(path), device=0, max_paths_in_flight=1 << 20)
+
+
+@pytest.mark.parametrize("scene", sorted(MIN_SHARE))
+def test_replay_matches_reference_frames_per_pixel(pkg, scene):
+    if scene.startswith("synthetic_"):
+        w, h, spp = SETTINGS["synthetic"][scene[len("synthetic_"):]]["exact"]
+    else:
+        w, h, spp = SETTINGS["exact"][scene]
+    golden = np.load(os.path.join(GOLDEN, f"exact_{scene}_woop.npy"))
+    r = open_renderer(pkg, scene)
+    frame = r.render_replay(w, h, spp)
+    r.close()
+    assert frame.shape == golden.shape and np.isfinite(frame).all()
+    share, d = agreeing_share(frame, golden)
+    assert share >= MIN_SHARE[scene], f"{scene}: {share:.4f} of the pixels agree to {RTOL} (median relative difference {np.median(d):.2e})"
+    # the pixels that agree do so at float-rounding level, not at "statistically close" level
+    assert np.median(d) < 2e-5, (scene, float(np.median(d)))
+
+
+@pytest.mark.parametrize("scene,w,h,spp,min_share", [("cornell-box", 64, 64, 16, 0.995), ("dragon", 64, 64, 8, 0.99),
+                                                     ("volumetric-caustic", 64, 64, 16, 0.99), ("matpreview", 64, 64, 16, 0.99),
+                                                     ("mercury", 64, 64, 16, 0.99)])
+def test_replay_matches_live_checker_per_pixel(pkg, scene, w, h, spp, min_share):
+    """The BASELINE scenes at a larger size and more samples, against the checker rendered right here (the reference build if it
+    travelled, else the C port, which is bit-equal to it on these scenes)."""
+    expected, kind = refcheck.render_checker(pack(scene), w, h, spp)
+    r = open_renderer(pkg, scene)
+    frame = r.render_replay(w, h, spp)
+    r.close()
+    share, d = agreeing_share(frame, expected)
+    assert share >= min_share, f"{scene} vs {kind}: {share:.4f} of the pixels agree to {RTOL}"
+    assert abs(frame.mean() / expected.mean() - 1.0) < 2e-3, (scene, kind, frame.mean(), expected.mean())
+
+
+def test_replay_refuses_alpha_tested_scenes(pkg):
+    """The reference draws the numbers of its opacity tests inside its own BVH walk; the product's tree visits primitives in
+    another order, so the stream cannot be replayed: the entry says so instead of returning a frame that cannot agree."""
+    r = open_renderer(pkg, "synthetic_opacity_masks")
+    with pytest.raises(pkg.MyException, match="alpha-tested"):
+        r.render_replay(16, 16, 1)
+    r.close()
