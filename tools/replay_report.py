@@ -23,6 +23,25 @@ def report(name, a, b):
           f"rel_l2 {np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30):.2e}  mean ratio {a.mean() / max(b.mean(), 1e-30):.6f}", flush=True)
 
 
+if "--fullsize" in sys.argv:
+    # the BASELINE configs at their own resolution against the float16 frames of the reference build (tests/golden/make_fullsize_golden.py)
+    import time
+    for name, scene in (("mercury", "mercury"), ("dragon", "dragon"), ("matpreview", "matpreview"), ("volumetric-caustic", "volumetric-caustic")):
+        g = np.load(os.path.join(GOLDEN, f"fullsize_{name}.npz"))
+        w, h, spp = (int(v) for v in g["size"])
+        r = pkg.Renderer(pkg.Scene(os.path.join(ROOT, "scenes", scene + ".b200scene")), device=0, max_paths_in_flight=1 << 20)
+        t0 = time.time()
+        a = r.render_replay(w, h, spp)
+        dt = time.time() - t0
+        b = g["frame"].astype(np.float32)
+        d = np.abs(a.astype(np.float64) - b).max(axis=2) / np.maximum(np.abs(b).max(axis=2), 1e-3)
+        print(f"fullsize {name} {w}x{h}x{spp} ({dt:.1f} s): px<=1e-3 {np.mean(d <= 1e-3):.4f}  <=2e-3 {np.mean(d <= 2e-3):.4f}  <=1e-2 {np.mean(d <= 1e-2):.4f}  "
+              f"median {np.median(d):.2e}  rel_l2 {np.linalg.norm(a - b) / np.linalg.norm(b):.2e}  mean ratio {a.mean() / b.mean():.6f}", flush=True)
+        # what float16 storage alone does to the frame
+        q = a.astype(np.float16).astype(np.float32)
+        print(f"    (float16 rounding of our own frame: rel_l2 {np.linalg.norm(a - q) / np.linalg.norm(a):.2e})", flush=True)
+        r.close()
+    sys.exit(0)
 live = None
 if "--live" in sys.argv:
     k = sys.argv.index("--live")
