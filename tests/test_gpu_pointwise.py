@@ -82,10 +82,10 @@ def bsdf_inputs(n, rng, both_sides):
     return inp
 
 
-def compare(a, b, value_cols, what, dir_cols=None, flag_cols=(0,), scale_cols=None):
-    """a = ours, b = reference: [n, 16] outputs."""
+def compare(a, b, value_cols, what, dir_cols=None, flag_cols=(0,), scale_cols=None, max_share=0.002):
+    """a = ours, b = reference: [n, 16] outputs.  max_share: probes that may differ (float-conditioning cases of the reference itself)."""
     flags_equal = np.all(a[:, list(flag_cols)] == b[:, list(flag_cols)], axis=1)
-    assert flags_equal.mean() >= 0.998, f"{what}: valid flags differ on {(~flags_equal).sum()} of {len(a)} probes"
+    assert flags_equal.mean() >= 1.0 - max_share, f"{what}: valid flags differ on {(~flags_equal).sum()} of {len(a)} probes"
     both = flags_equal & (b[:, 0] != 0) if 0 in flag_cols else flags_equal
     if not both.any():
         return
@@ -94,11 +94,11 @@ def compare(a, b, value_cols, what, dir_cols=None, flag_cols=(0,), scale_cols=No
     scale = np.maximum(np.abs(vb).max(axis=1, keepdims=True), 1e-3)
     err = np.abs(va - vb) / scale
     bad = err.max(axis=1) > RTOL
-    assert bad.mean() <= 0.002, f"{what}: {bad.sum()} of {both.sum()} probes off by more than {RTOL} (worst {err.max():.3e}: ours {va[err.max(axis=1).argmax()]}, reference {vb[err.max(axis=1).argmax()]})"
+    assert bad.mean() <= max_share, f"{what}: {bad.sum()} of {both.sum()} probes off by more than {RTOL} (worst {err.max():.3e}: ours {va[err.max(axis=1).argmax()]}, reference {vb[err.max(axis=1).argmax()]})"
     if dir_cols is not None:
         da, db = a[both][:, dir_cols].astype(np.float64), b[both][:, dir_cols].astype(np.float64)
         off = np.abs(da - db).max(axis=1) > RTOL
-        assert off.mean() <= 0.002, f"{what}: {off.sum()} sampled directions differ (worst {np.abs(da - db).max():.3e})"
+        assert off.mean() <= max_share, f"{what}: {off.sum()} sampled directions differ (worst {np.abs(da - db).max():.3e})"
 
 
 @pytest.mark.parametrize("scene_name", SCENES)
@@ -114,10 +114,12 @@ def test_bsdf_evaluate_and_sample(pkg, scene_name):
             continue
         inp = bsdf_inputs(6000, rng, both_sides=kind in (5, 6))
         what = f"{scene_name}: {BSDF_NAMES[kind]} #{index}"
-        compare(ours.debug_eval(pkg.EVAL_BSDF_EVALUATE, index, inp), ref.eval(pkg.EVAL_BSDF_EVALUATE, index, inp), [1, 2, 3, 4], what + " Evaluate")
+        # 200 000 probes per BSDF (tools/pointwise_report.py, profiles/r02_pointwise_report.log): no probe with another number of draws,
+        # another validity or another direction, 2 values off by more than 2e-4 -> at most 3 of these 6 000 may differ
+        compare(ours.debug_eval(pkg.EVAL_BSDF_EVALUATE, index, inp), ref.eval(pkg.EVAL_BSDF_EVALUATE, index, inp), [1, 2, 3, 4], what + " Evaluate", max_share=0.0005)
         a, b = ours.debug_eval(pkg.EVAL_BSDF_SAMPLE, index, inp), ref.eval(pkg.EVAL_BSDF_SAMPLE, index, inp)
         assert np.array_equal(a[:, 15].view(np.uint32), b[:, 15].view(np.uint32)), f"{what} Sample: number of random draws differs"
-        compare(a, b, [1, 2, 3, 4], what + " Sample", dir_cols=[5, 6, 7])
+        compare(a, b, [1, 2, 3, 4], what + " Sample", dir_cols=[5, 6, 7], max_share=0.0005)
         tested += 1
     if tested == 0:
         pytest.skip("no scattering BSDF in this scene")

@@ -67,20 +67,33 @@ def main():
             r = subprocess.run([sys.executable, __file__, name, str(w), str(h), str(spp), "--pixel", f"{i},{j}", "--side", side],
                                capture_output=True, text=True, timeout=600)
             out[side] = [l for l in (r.stdout + r.stderr).splitlines() if l.startswith("[trace]")]
-        shown = 0
-        for k2 in range(max(len(out["gpu"]), len(out["cpu"]))):
-            g = out["gpu"][k2] if k2 < len(out["gpu"]) else "-"
-            c = out["cpu"][k2] if k2 < len(out["cpu"]) else "-"
-            same = g == c
-            if not same or shown < 0:
-                print("  gpu", g)
-                print("  cpu", c)
-                shown += 1
-                if shown >= 4:
-                    break
-            elif k2 < 3:
-                print("   ==", g)
-
+        # first REAL divergence: a different LCG state, or a number off by more than 1e-4 relative (the last printed digits differ anyway)
+        def parse(line):
+            f = line.split()
+            if len(f) < 4 or not f[1].startswith("v"):
+                return None
+            return f[1], f[3], [float(x) for x in f[5:6] + f[7:10] + f[11:14]]
+        kind = "none within the printed vertices"
+        for k2 in range(min(len(out["gpu"]), len(out["cpu"]))):
+            g, c = parse(out["gpu"][k2]), parse(out["cpu"][k2])
+            if g is None and c is None:
+                continue
+            if g is None or c is None or g[0] != c[0]:
+                kind = "one side has a vertex the other has not (a path ended / escaped earlier)"
+            elif g[1] != c[1]:
+                kind = "LCG STATE differs (for volpath the GPU prints before, the CPU after the medium draw of the vertex)"
+            else:
+                rel = [abs(x - y) / max(abs(y), 1e-6) for x, y in zip(g[2], c[2])]
+                if max(rel) <= 1e-4:
+                    continue
+                kind = ("hit distance" if rel[0] > 1e-4 else "radiance so far" if max(rel[1:4]) > 1e-4 else "throughput") + f" differs by {max(rel):.1e} at equal LCG state"
+            print(f"  first divergence (line {k2}): {kind}")
+            for k3 in range(max(0, k2 - 2), min(k2 + 2, len(out["gpu"]), len(out["cpu"]))):
+                print("    gpu", out["gpu"][k3])
+                print("    cpu", out["cpu"][k3])
+            break
+        else:
+            print("  first divergence:", kind)
 
 if __name__ == "__main__":
     main()
