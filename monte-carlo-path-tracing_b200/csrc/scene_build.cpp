@@ -225,9 +225,20 @@ const float kCubeNrm[] = {0,  -1, 0, 0,  -1, 0, 0,  -1, 0, 0,  -1, 0, 0, 1, 0,  
 const uint32_t kCubeIdx[] = {0,  1,  2,  3,  0,  2,  4,  5,  6,  7,  4,  6,  8,  9,  10, 11, 8,  10,
                              12, 13, 14, 15, 12, 14, 16, 17, 18, 19, 16, 18, 20, 21, 22, 23, 20, 22};
 
-// scene.cpp:247-324 (bake to_world) + scene.cpp:15-111 (SetupMeshes).
-bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::vector<RawTriangle> *tris,
-                float *area_sum, std::string *error) {
+struct Box {
+    V3 lo{kFltMax, kFltMax, kFltMax}, hi{-kFltMax, -kFltMax, -kFltMax};
+    void Grow(V3 p) { lo = Min(lo, p), hi = Max(hi, p); }
+    void Grow(const Box &b) { lo = Min(lo, b.lo), hi = Max(hi, b.hi); }
+    float HalfArea() const {
+        const V3 d = hi - lo;
+        return d.x * d.y + d.y * d.z + d.z * d.x;
+    }
+};
+
+// scene.cpp:247-324 (bake to_world) + scene.cpp:15-111 (SetupMeshes).  Also leaves every triangle's box and box centre (what the BVH
+// builder reads) while the triangle is still in cache.
+bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::vector<RawTriangle> *tris, std::vector<Box> *boxes,
+                std::vector<V3> *centers, float *area_sum, std::string *error) {
     if (mesh.num_triangles == 0 || mesh.indices == nullptr) {
         *error = "cannot find vertex index info when adding instance to scene.";
         return false;
@@ -259,6 +270,8 @@ bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::ve
         }
     const size_t first_triangle = tris->size();
     tris->resize(first_triangle + mesh.num_triangles); // within the capacity BuildHostScene reserved
+    boxes->resize(first_triangle + mesh.num_triangles);
+    centers->resize(first_triangle + mesh.num_triangles);
     ParallelFor(mesh.num_triangles, [&](size_t f) {
         RawTriangle tri;
         tri.inst = inst;
@@ -297,6 +310,10 @@ bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::ve
             }
         }
         (*tris)[first_triangle + f] = tri;
+        Box box;
+        for (int j = 0; j < 3; ++j) box.Grow(tri.p[j]);
+        (*boxes)[first_triangle + f] = box;
+        (*centers)[first_triangle + f] = (box.lo + box.hi) * 0.5f;
     });
     float area_total = 0.0f; // summed in triangle order, as scene.cpp:48-49 does (Q3: the float sum is what the pdf uses)
     for (uint64_t f = 0; f < mesh.num_triangles; ++f) area_total += (*tris)[first_triangle + f].area;
@@ -307,16 +324,6 @@ bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::ve
 // ---------------------------------------------------------------------------------------------
 // BVH: binned SAH, two child boxes per node.
 // ---------------------------------------------------------------------------------------------
-struct Box {
-    V3 lo{kFltMax, kFltMax, kFltMax}, hi{-kFltMax, -kFltMax, -kFltMax};
-    void Grow(V3 p) { lo = Min(lo, p), hi = Max(hi, p); }
-    void Grow(const Box &b) { lo = Min(lo, b.lo), hi = Max(hi, b.hi); }
-    float HalfArea() const {
-        const V3 d = hi - lo;
-        return d.x * d.y + d.y * d.z + d.z * d.x;
-    }
-};
-
 // Four floats in one SSE register (plain loops elsewhere): the builder's inner loop is min / max of box corners.
 #if defined(__SSE2__)
 struct alignas(16) F4 {
@@ -702,9 +709,10 @@ void SetChildBox(BvhNode *node, int which, const Box &b) {
 }
 
 // Leaves with more than 8 triangles cannot be encoded; the builder never makes them for max_leaf <= 8.
-void FlattenBvh(const BuildNodePool &bn, int32_t root, uint32_t top_nodes, std::vector<BvhNode> *out) {
+// Returns the number of inner-node levels (what FlatBvhDepth would count on the result).
+uint32_t FlattenBvh(const BuildNodePool &bn, int32_t root, uint32_t top_nodes, std::vector<BvhNode> *out) {
     out->clear();
-    if (root < 0) return;
+    if (root < 0) return 0;
     const Box empty; // inverted box: never hit
     if (bn[root].left < 0) { // whole scene is one leaf
         BvhNode n{};
@@ -713,21 +721,30 @@ void FlattenBvh(const BuildNodePool &bn, int32_t root, uint32_t top_nodes, std::
         n.child0 = EncodeLeaf(bn[root].first, bn[root].count);
         n.child1 = EncodeLeaf(0, 1);
         out->push_back(n);
-        return;
+        return 1;
     }
     // Output order: breadth-first for the first `top_nodes` inner nodes (the part staged in
     // shared memory), depth-first below so that subtrees stay contiguous in HBM/L2.
     std::vector<int32_t> out_index(bn.size(), -1);
     std::vector<int32_t> order;
     order.reserve(bn.size());
+    std::vector<uint32_t> level(bn.size(), 0); // of inner nodes, root = 1
+    uint32_t deepest = 1;
+    level[root] = 1;
+    auto visit = [&](int32_t id, int32_t child, std::vector<int32_t> *to) {
+        if (bn[child].left < 0) return;
+        level[child] = level[id] + 1;
+        deepest = std::max(deepest, level[child]);
+        to->push_back(child);
+    };
     std::vector<int32_t> frontier{root};
     size_t head = 0;
     while (head < frontier.size() && order.size() < top_nodes) {
         const int32_t id = frontier[head++];
         out_index[id] = static_cast<int32_t>(order.size());
         order.push_back(id);
-        if (bn[bn[id].left].left >= 0) frontier.push_back(bn[id].left);
-        if (bn[bn[id].right].left >= 0) frontier.push_back(bn[id].right);
+        visit(id, bn[id].left, &frontier);
+        visit(id, bn[id].right, &frontier);
     }
     std::vector<int32_t> stack;
     for (size_t i = frontier.size(); i-- > head;) stack.push_back(frontier[i]);
@@ -736,8 +753,8 @@ void FlattenBvh(const BuildNodePool &bn, int32_t root, uint32_t top_nodes, std::
         stack.pop_back();
         out_index[id] = static_cast<int32_t>(order.size());
         order.push_back(id);
-        if (bn[bn[id].right].left >= 0) stack.push_back(bn[id].right);
-        if (bn[bn[id].left].left >= 0) stack.push_back(bn[id].left);
+        visit(id, bn[id].right, &stack);
+        visit(id, bn[id].left, &stack);
     }
     out->resize(order.size());
     ParallelFor(order.size(), [&](size_t i) {
@@ -750,6 +767,7 @@ void FlattenBvh(const BuildNodePool &bn, int32_t root, uint32_t top_nodes, std::
         n.child1 = r.left >= 0 ? out_index[src.right] : EncodeLeaf(r.first, r.count);
         (*out)[i] = n;
     });
+    return deepest;
 }
 
 // Number of inner-node levels of a flattened tree = the most entries a traversal can have on its stack, plus one.
@@ -1095,11 +1113,13 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
 
     // ---- instances + geometry ----
     std::vector<RawTriangle> tris;
+    std::vector<Box> boxes; // per triangle: its box and the centre of the box, filled by AppendMesh
+    std::vector<V3> centers;
     {
         uint64_t total = 0; // one allocation for all meshes (176 B per triangle: growing by doubling copies it all again and again)
         for (uint64_t i = 0; i < d.num_instances; ++i)
             total += d.instances[i].type == B200PT_INST_MESHES ? d.instances[i].num_triangles : (d.instances[i].type == B200PT_INST_CUBE ? 12u : 2u);
-        tris.reserve(total);
+        tris.reserve(total), boxes.reserve(total), centers.reserve(total);
     }
     std::vector<float> inst_area(d.num_instances, 0.0f);
     hs->instances.resize(d.num_instances);
@@ -1219,7 +1239,7 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             *error = "unknow instance type."; // scene.cpp:184
             return false;
         }
-        if (is_mesh && !AppendMesh(mesh, to_world, static_cast<uint32_t>(i), &tris, &inst_area[i], error)) return false;
+        if (is_mesh && !AppendMesh(mesh, to_world, static_cast<uint32_t>(i), &tris, &boxes, &centers, &inst_area[i], error)) return false;
         o.pdf_area = 1.0f / inst_area[i];
     }
 
@@ -1239,13 +1259,8 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
     PhaseTimer phase;
     const auto t0 = std::chrono::steady_clock::now();
     const size_t nt = tris.size();
-    std::vector<Box> boxes(nt);
-    std::vector<V3> centers(nt);
-    ParallelFor(nt, [&](size_t i) {
-        for (int j = 0; j < 3; ++j) boxes[i].Grow(tris[i].p[j]);
-        centers[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
-    });
-    for (size_t i = 0; i < nt; ++i) scene_box.Grow(boxes[i]);
+    if (gpu_lbvh) // (the host builder leaves the bounds of all triangles in its root)
+        for (size_t i = 0; i < nt; ++i) scene_box.Grow(boxes[i]);
     phase("triangle boxes");
     std::vector<uint32_t> order;
     std::vector<Bvh2Node> binary; // the SAH tree as handed to the wide collapse / the cull-box cut
@@ -1279,6 +1294,7 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
             phase("builder setup");
             binary_root = builder.Build();
             order = builder.order();
+            if (!gpu_lbvh && binary_root >= 0) scene_box.Grow(builder.nodes()[binary_root].box);
             phase("SAH build");
             if (wide) {
                 const BuildNodePool &bn = builder.nodes();
@@ -1294,9 +1310,9 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
                     return false;
                 hs->wide_depth = info.depth, hs->wide_top_nodes = info.top_nodes;
             } else {
-                FlattenBvh(builder.nodes(), binary_root, 1024, &hs->nodes);
+                const uint32_t levels = FlattenBvh(builder.nodes(), binary_root, 1024, &hs->nodes);
                 phase("flatten");
-                if (FlatBvhDepth(hs->nodes) >= kBvh2StackSize) {
+                if (levels >= kBvh2StackSize) {
                     *error = "BVH too deep for the traversal stack.";
                     return false;
                 }
