@@ -49,7 +49,8 @@ struct DeviceArray {
         if (n == 0) return cudaSuccess;
         return cudaMalloc(&ptr, n * sizeof(T));
     }
-    cudaError_t Upload(const std::vector<T> &src) {
+    template <class A>
+    cudaError_t Upload(const std::vector<T, A> &src) {
         const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = Alloc(src.size());
         const auto t1 = std::chrono::steady_clock::now();
@@ -282,8 +283,8 @@ int UploadScene(b200pt_context *c, const b200pt_scene_desc &desc) {
     // the big host copies are not needed any more
     std::vector<BvhNode>().swap(h.nodes);
     std::vector<WideNode>().swap(h.wide_nodes);
-    std::vector<TriVerts>().swap(h.tri_verts);
-    std::vector<TriShade>().swap(h.tri_shade);
+    decltype(h.tri_verts)().swap(h.tri_verts);
+    decltype(h.tri_shade)().swap(h.tri_shade);
     return B200PT_OK;
 }
 

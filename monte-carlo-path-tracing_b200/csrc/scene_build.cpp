@@ -237,7 +237,7 @@ struct Box {
 
 // scene.cpp:247-324 (bake to_world) + scene.cpp:15-111 (SetupMeshes).  Also leaves every triangle's box and box centre (what the BVH
 // builder reads) while the triangle is still in cache.
-bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::vector<RawTriangle> *tris, std::vector<Box> *boxes,
+bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, RawVector<RawTriangle> *tris, std::vector<Box> *boxes,
                 std::vector<V3> *centers, float *area_sum, std::string *error) {
     if (mesh.num_triangles == 0 || mesh.indices == nullptr) {
         *error = "cannot find vertex index info when adding instance to scene.";
@@ -248,7 +248,7 @@ bool AppendMesh(const MeshView &mesh, const M4 &to_world, uint32_t inst, std::ve
         return false;
     }
     const uint64_t nv = mesh.num_vertices;
-    std::vector<V3> pos(nv), nrm, tan, bit;
+    RawVector<V3> pos(nv), nrm, tan, bit;
     ParallelFor(nv, [&](size_t i) { pos[i] = TransformPoint(to_world, Load3(mesh.positions + 3 * i)); });
     if (mesh.normals) {
         const M4 normal_to_world = Inverse(Transpose(to_world));
@@ -1112,7 +1112,7 @@ bool BuildHostScene(const b200pt_scene_desc &d, uint32_t max_leaf_size, bool gpu
     }
 
     // ---- instances + geometry ----
-    std::vector<RawTriangle> tris;
+    RawVector<RawTriangle> tris;
     std::vector<Box> boxes; // per triangle: its box and the centre of the box, filled by AppendMesh
     std::vector<V3> centers;
     {
