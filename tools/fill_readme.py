@@ -12,7 +12,7 @@ values = {
     "C2V": fmt(d["value"]), "C2MS": f"{d['ms_per_step']:.1f}", "C2E": fmt(d["e2e"]["value"]),
     "C1": fmt(c["C1"]["Msamples_s"]), "C3": fmt(c["C3"]["Msamples_s"]), "C4": fmt(c["C4"]["Msamples_s"]), "C5": fmt(c["C5"]["Msamples_s"]),
     "CPU": f"{d['cpu_baseline']['value']:.1f}", "CPUF": f"{d['cpu_baseline']['fast_build']['value']:.1f}",
-    "CREATE": f"{d['config']['scene_create_s']:.2f}",
+    "CREATE": f"{d['config']['scene_create_s']:.2f}", "INIT": f"{d['config'].get('library_init_s', float('nan')):.2f}",
 }
 path = os.path.join(ROOT, "README.md")
 text = open(path).read()
