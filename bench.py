@@ -378,8 +378,12 @@ def kernel_table(counted, timed):
 def ncu_counters(pack, width, height, spp, kernel_prefix):
     """What ncu measured for this kernel on this workload (committed capture, tools/ncu_counters.py): the bytes that really
     moved and how busy the issue slots were — the numbers that say what binds, next to the contract's byte formula."""
-    for spp_try in (spp, 256, 128, 64):
-        path = os.path.join(ROOT, "profiles", f"r02_counters_{pack}_{width}x{height}x{spp_try}.json")
+    import glob
+    candidates = [os.path.join(ROOT, "profiles", f"r02_counters_{pack}_{width}x{height}x{spp_try}.json") for spp_try in (spp, 256, 128, 64)]
+    # no capture at this frame size: one of the same scene at another size still says what binds the kernel (rates and ratios,
+    # not bytes per launch)
+    candidates += sorted(glob.glob(os.path.join(ROOT, "profiles", f"r02_counters_{pack}_*.json")))
+    for path in candidates:
         if os.path.exists(path):
             with open(path) as f:
                 doc = json.load(f)
@@ -387,7 +391,8 @@ def ncu_counters(pack, width, height, spp, kernel_prefix):
             if not rows:
                 return None
             k, v = max(rows.items(), key=lambda kv: kv[1]["time_ms"])
-            return {"file": os.path.relpath(path, ROOT), "kernel": k, "capture": doc.get("_what", ""), **v}
+            return {"file": os.path.relpath(path, ROOT), "kernel": k, "capture": doc.get("_what", ""),
+                    "same_size": f"_{width}x{height}x" in os.path.basename(path), **v}
     return None
 
 
@@ -403,17 +408,21 @@ def roofline_block(pack, width, height, spp, kernels, render_ms):
     c = ncu_counters(pack, width, height, spp, "k_" + dominant)
     if c:
         dram = c["dram_read_bytes"] + c["dram_write_bytes"]
-        block["traffic"] = dram / max(1, dk["launches"])
+        if c["same_size"]:
+            block["traffic"] = dram / max(1, dk["launches"])
         block.update({"dram_gbs": c["dram_gbs"], "dram_frac": c["dram_gbs"] / peak, "l2_gbs": c["l2_gbs"], "issue_active": c["issue_active"],
                       "active_lanes": c["active_lanes"], "warps_active": c["warps_active"], "l1_hit": c["l1_hit"], "l2_hit": c["l2_hit"],
                       "counters_source": f"{c['file']} ({c['kernel']}, {c['launches']} launches, {c['time_ms']:.2f} ms under ncu): "
-                                         "per-frame DRAM bytes / this step's launch count = traffic"})
+                                         + ("per-frame DRAM bytes / this step's launch count = traffic" if c["same_size"] else
+                                            "same scene and kernel at another frame size: rates and ratios only, no bytes per launch")})
         # what the counters say binds: HBM only when the DRAM pipe is actually busy
         if block["dram_frac"] < 0.5:
             block["bound"] = "issue/latency"
             block["bound_note"] = (f"DRAM moves {c['dram_gbs']:.0f} GB/s = {100 * block['dram_frac']:.1f} % of the measured peak while the §8d formula "
                                    f"counts {dk['GBps']:.0f} GB/s of node and triangle fetches: they are served by L1 ({100 * c['l1_hit']:.0f} % hit) and L2; the kernel "
                                    f"issues on {100 * c['issue_active']:.0f} % of the cycles with {c['active_lanes']:.1f} of 32 lanes active")
+    else:
+        block["bound_note"] = "no ncu capture of this scene under profiles/: the fraction is the §8d formula alone and does not say what binds"
     return block
 
 
