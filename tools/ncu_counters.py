@@ -66,9 +66,10 @@ def main():
                "active_lanes": a["thread_inst"] / max(a["warp_inst"], 1.0), "issue_active": a["issue_active_pct_x_time"] / t / 100.0,
                "warps_active": a["warps_active_pct_x_time"] / t / 100.0, "l1_hit": a["l1_hit_pct_x_time"] / t / 100.0, "l2_hit": a["l2_hit_pct_x_time"] / t / 100.0}
         out["kernels"][k] = rec
+    json.dump(out, open(sys.argv[2], "w"), indent=1)  # before the table: a reader that closes the pipe (| head) must not cost the file
+    for k, rec in out["kernels"].items():
         print(f"{k:34s} x{rec['launches']:4d} {rec['time_ms']:9.3f} ms {100 * rec['share_of_frame']:5.1f}%  DRAM {rec['dram_gbs']:7.1f} GB/s  L2 {rec['l2_gbs']:8.1f} GB/s  "
               f"issue {100 * rec['issue_active']:5.1f}%  lanes {rec['active_lanes']:5.2f}  warps {100 * rec['warps_active']:5.1f}%  L1 hit {100 * rec['l1_hit']:5.1f}%  L2 hit {100 * rec['l2_hit']:5.1f}%")
-    json.dump(out, open(sys.argv[2], "w"), indent=1)
 
 
 if __name__ == "__main__":
