@@ -409,11 +409,11 @@ def roofline_block(pack, width, height, spp, kernels, render_ms):
     if c:
         dram = c["dram_read_bytes"] + c["dram_write_bytes"]
         if c["same_size"]:
-            block["traffic"] = dram / max(1, dk["launches"])
+            block["traffic"] = dram / max(1, c["launches"])  # per launch of the CAPTURED frame (same batch size, maybe fewer spp)
         block.update({"dram_gbs": c["dram_gbs"], "dram_frac": c["dram_gbs"] / peak, "l2_gbs": c["l2_gbs"], "issue_active": c["issue_active"],
                       "active_lanes": c["active_lanes"], "warps_active": c["warps_active"], "l1_hit": c["l1_hit"], "l2_hit": c["l2_hit"],
                       "counters_source": f"{c['file']} ({c['kernel']}, {c['launches']} launches, {c['time_ms']:.2f} ms under ncu): "
-                                         + ("per-frame DRAM bytes / this step's launch count = traffic" if c["same_size"] else
+                                         + ("DRAM bytes of the captured frame / its launch count = traffic" if c["same_size"] else
                                             "same scene and kernel at another frame size: rates and ratios only, no bytes per launch")})
         # what the counters say binds: HBM only when the DRAM pipe is actually busy
         if block["dram_frac"] < 0.5:
