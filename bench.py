@@ -391,7 +391,8 @@ def ncu_counters(pack, width, height, spp, kernel_prefix):
             if not rows:
                 return None
             k, v = max(rows.items(), key=lambda kv: kv[1]["time_ms"])
-            return {"file": os.path.relpath(path, ROOT), "kernel": k, "capture": doc.get("_what", ""),
+            spp_capture = int(os.path.basename(path)[:-len(".json")].rsplit("x", 1)[1])
+            return {"file": os.path.relpath(path, ROOT), "kernel": k, "capture": doc.get("_what", ""), "spp": spp_capture,
                     "same_size": f"_{width}x{height}x" in os.path.basename(path), **v}
     return None
 
@@ -409,11 +410,13 @@ def roofline_block(pack, width, height, spp, kernels, render_ms):
     if c:
         dram = c["dram_read_bytes"] + c["dram_write_bytes"]
         if c["same_size"]:
-            block["traffic"] = dram / max(1, c["launches"])  # per launch of the CAPTURED frame (same batch size, maybe fewer spp)
+            # per launch LIKE `achieved`: the captured frame's DRAM bytes, scaled to this step's spp (traffic is linear in spp),
+            # over this step's launch count (the timed split renders with one arena; the capture may have used more launches)
+            block["traffic"] = dram * (spp / c["spp"]) / max(1, dk["launches"])
         block.update({"dram_gbs": c["dram_gbs"], "dram_frac": c["dram_gbs"] / peak, "l2_gbs": c["l2_gbs"], "issue_active": c["issue_active"],
                       "active_lanes": c["active_lanes"], "warps_active": c["warps_active"], "l1_hit": c["l1_hit"], "l2_hit": c["l2_hit"],
                       "counters_source": f"{c['file']} ({c['kernel']}, {c['launches']} launches, {c['time_ms']:.2f} ms under ncu): "
-                                         + ("DRAM bytes of the captured frame / its launch count = traffic" if c["same_size"] else
+                                         + ("DRAM bytes of the captured frame x (spp of this step / spp of the capture) / this step's launch count = traffic" if c["same_size"] else
                                             "same scene and kernel at another frame size: rates and ratios only, no bytes per launch")})
         # what the counters say binds: HBM only when the DRAM pipe is actually busy
         if block["dram_frac"] < 0.5:
