@@ -391,7 +391,10 @@ def ncu_counters(pack, width, height, spp, kernel_prefix):
             if not rows:
                 return None
             k, v = max(rows.items(), key=lambda kv: kv[1]["time_ms"])
-            spp_capture = int(os.path.basename(path)[:-len(".json")].rsplit("x", 1)[1])
+            try:
+                spp_capture = int(os.path.basename(path)[:-len(".json")].rsplit("x", 1)[1])
+            except (IndexError, ValueError):
+                continue  # not a <scene>_<w>x<h>x<spp>.json capture
             return {"file": os.path.relpath(path, ROOT), "kernel": k, "capture": doc.get("_what", ""), "spp": spp_capture,
                     "same_size": f"_{width}x{height}x" in os.path.basename(path), **v}
     return None
