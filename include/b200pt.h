@@ -298,6 +298,15 @@ int b200pt_get_kulla_conty(b200pt_handle h, float *brdf_avg_128x128, float *albe
 int b200pt_get_envmap_tables(b200pt_handle h, float *out, uint64_t capacity_floats, uint64_t *num_floats,
                              float *normalization);
 
+/* Test hook, HOST ONLY (needs no GPU): the sampling order of mesh area light `light` (index into the scene's list of
+ * emissive instances, in instance order) as b200pt_create lays it out — the triangles of the instance, numbered as in its
+ * own index list, in the order of the cumulative distribution that stands for BLAS::Sample's area-weighted BVH descent
+ * (blas.cpp:79-98): the leaf order of the reference's Morton-built tree (bvh_builder.cpp:92-141), so that the same random
+ * number picks the same triangle.  *count = triangles of the light (0 for a sphere / disk / cylinder light); tri_ids / cdf
+ * (either may be NULL) receive min(*count, capacity) entries. */
+int b200pt_debug_light_order(const b200pt_scene_desc *scene, uint32_t light, uint32_t *tri_ids, float *cdf, uint64_t capacity,
+                             uint64_t *count);
+
 /* ---- test hooks: pointwise access to the device leaf functions, so that tests can compare them with the reference's
  * functions at fixed inputs instead of through whole images.  Not needed by a renderer host. ---- */
 typedef struct b200pt_debug_ray {

@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "b200pt_render_tiles_device", "b200pt_assemble_tiles_device", "b200pt_get_stats", "b200pt_last_error",
     "b200pt_get_kulla_conty", "b200pt_get_envmap_tables", "b200pt_scene_load", "b200pt_scene_save",
     "b200pt_scene_get_desc", "b200pt_scene_free", "b200pt_debug_trace", "b200pt_debug_eval",
-    "b200pt_debug_render_replay",
+    "b200pt_debug_render_replay", "b200pt_debug_light_order",
 ]
 
 _lib = None
@@ -123,6 +123,7 @@ def lib():
     L.b200pt_debug_trace.argtypes = [vp, vp, u64, u32, vp]
     L.b200pt_debug_eval.argtypes = [vp, u32, u32, u64, vp, vp]
     L.b200pt_debug_render_replay.argtypes = [vp, u32, u32, u32, vp]
+    L.b200pt_debug_light_order.argtypes = [vp, u32, vp, vp, u64, ctypes.POINTER(u64)]
     _lib = L
     return L
 
@@ -130,6 +131,17 @@ def lib():
 def _check(rc, handle=None):
     if rc != 0:
         raise MyException(lib().b200pt_last_error(handle).decode(errors="replace"))
+
+
+def light_order(desc, light):
+    """Test hook b200pt_debug_light_order (host only): (triangle numbers within the instance, cdf) of mesh area light `light`
+    in the order of its sampling distribution.  `desc`: address of / ctypes reference to a b200pt_scene_desc."""
+    n = ctypes.c_uint64()
+    _check(lib().b200pt_debug_light_order(desc, light, None, None, 0, ctypes.byref(n)))
+    ids, cdf = np.zeros(n.value, dtype=np.uint32), np.zeros(n.value, dtype=np.float32)
+    if n.value:
+        _check(lib().b200pt_debug_light_order(desc, light, ids.ctypes.data, cdf.ctypes.data, n.value, ctypes.byref(n)))
+    return ids, cdf
 
 
 class Scene:

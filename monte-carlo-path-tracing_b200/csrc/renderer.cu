@@ -894,6 +894,33 @@ int b200pt_debug_eval(b200pt_handle h, uint32_t what, uint32_t id, uint64_t n, c
     return B200PT_OK;
 }
 
+int b200pt_debug_light_order(const b200pt_scene_desc *scene, uint32_t light, uint32_t *tri_ids, float *cdf, uint64_t capacity, uint64_t *count) {
+    if (!scene || !count) return SetGlobalError(B200PT_EINVAL, "b200pt_debug_light_order: null argument");
+    try {
+        HostScene hs;
+        std::string error;
+        if (!BuildHostScene(*scene, 0, false, false, &hs, &error)) return SetGlobalError(B200PT_EINVAL, error);
+        if (light >= hs.map_area_light_instance.size()) return SetGlobalError(B200PT_EINVAL, "b200pt_debug_light_order: no such area light.");
+        const DInstance &inst = hs.instances[hs.map_area_light_instance[light]];
+        *count = inst.analytic == kInvalid ? inst.light_tri_count : 0;
+        // TriVerts::v1.w carries the triangle's number in the scene description (instances in order); the smallest one of the
+        // instance is its first triangle
+        uint32_t first = 0xffffffffu;
+        std::vector<uint32_t> ids(*count);
+        for (uint64_t k = 0; k < *count; ++k) {
+            memcpy(&ids[k], &hs.tri_verts[hs.light_tri_ids[inst.light_tri_begin + k]].v1.w, 4);
+            first = std::min(first, ids[k]);
+        }
+        for (uint64_t k = 0; k < *count && k < capacity; ++k) {
+            if (tri_ids) tri_ids[k] = ids[k] - first;
+            if (cdf) cdf[k] = hs.light_tri_cdf[inst.light_tri_begin + k];
+        }
+        return B200PT_OK;
+    } catch (const std::exception &e) {
+        return SetGlobalError(B200PT_ENOMEM, std::string("b200pt_debug_light_order: ") + e.what());
+    }
+}
+
 int b200pt_debug_render_replay(b200pt_handle h, uint32_t width, uint32_t height, uint32_t spp, float *frame_host) {
     if (!h || !frame_host) return SetGlobalError(B200PT_EINVAL, "b200pt_debug_render_replay: null argument");
     if (h->scene.integrator.has_opacity)
