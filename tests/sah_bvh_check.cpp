@@ -4,7 +4,8 @@
 //   1. structure: every triangle is in exactly one leaf, leaves hold 1..8 triangles, every inner node is referenced once, child
 //      boxes contain everything below them, the tree is shallower than the traversal stack;
 //   2. closest hits: a plain two-children-per-node walk of the flattened nodes (the scheme of traverse.cuh, restated here)
-//      finds, for random rays, the same distance as brute force over all triangles with the same triangle test.
+//      finds, for random rays, the same distance as brute force over all triangles with the same triangle test;
+//   3. the two box covers of the camera-ray visibility pre-pass contain every triangle.
 // Usage: sah_bvh_check scene.b200scene num_rays seed   -> prints "OK ..." or the first violation.
 #include <math.h>
 #include <stdio.h>
@@ -188,6 +189,33 @@ int main(int argc, char **argv) {
     if (g_error != nullptr) {
         printf("FAIL structure: %s\n", g_error);
         return 1;
+    }
+    // 3. covers of the visibility pre-pass (k_cull_tiles): every triangle lies inside a coarse box, and inside a fine box filed
+    //    under that coarse box — otherwise a pixel that sees it could be dropped
+    {
+        const size_t ncoarse = hs.cull_boxes.size() / 6 - hs.analytic.size(), nfine = hs.fine_cull_boxes.size() / 6;
+        if (hs.cull_fine_begin.size() != hs.cull_boxes.size() / 6 + 1 || hs.cull_fine_begin.back() != nfine) {
+            printf("FAIL cull covers: fine ranges do not tile the fine boxes\n");
+            return 1;
+        }
+        auto inside = [](const Box3 &b, const float *q) {
+            for (int k = 0; k < 3; ++k)
+                if (b.lo[k] < q[k] || b.hi[k] > q[k + 3]) return false;
+            return true;
+        };
+        for (size_t i = 0; i < nt; ++i) {
+            Box3 tb;
+            tb.Grow(hs.tri_verts[i].v0), tb.Grow(hs.tri_verts[i].v1), tb.Grow(hs.tri_verts[i].v2);
+            bool covered = false;
+            for (size_t cidx = 0; cidx < ncoarse && !covered; ++cidx) {
+                if (!inside(tb, &hs.cull_boxes[6 * cidx])) continue;
+                for (uint32_t f = hs.cull_fine_begin[cidx]; f < hs.cull_fine_begin[cidx + 1] && !covered; ++f) covered = inside(tb, &hs.fine_cull_boxes[6 * f]);
+            }
+            if (!covered) {
+                printf("FAIL cull covers: triangle %zu is in no (coarse, fine) box pair\n", i);
+                return 1;
+            }
+        }
     }
     // rays from around the scene towards points inside its bounds
     float c[3], ext[3];
