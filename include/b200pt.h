@@ -294,7 +294,7 @@ const char *b200pt_last_error(b200pt_handle h);   /* h may be NULL: last error o
 
 /* ---- derived tables the reference computes on the host between config and kernel
  * (renderer.cpp:311-314, 571-611); exposed so tests can compare them. ---- */
-int b200pt_get_kulla_conty(b200pt_handle h, float *brdf_avg_128x128, float *albedo_avg_128);
+int b200pt_get_kulla_conty(b200pt_handle h, float *brdf_avg_128x128, float *albedo_avg_128); /* h may be NULL (host only) */
 int b200pt_get_envmap_tables(b200pt_handle h, float *out, uint64_t capacity_floats, uint64_t *num_floats,
                              float *normalization);
 

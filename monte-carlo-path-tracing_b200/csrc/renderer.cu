@@ -954,7 +954,18 @@ int b200pt_debug_render_replay(b200pt_handle h, uint32_t width, uint32_t height,
 const char *b200pt_last_error(b200pt_handle h) { return h ? h->error.c_str() : GlobalError(); }
 
 int b200pt_get_kulla_conty(b200pt_handle h, float *brdf_avg, float *albedo_avg) {
-    if (!h || !brdf_avg || !albedo_avg) return SetGlobalError(B200PT_EINVAL, "b200pt_get_kulla_conty: null argument");
+    if (!brdf_avg || !albedo_avg) return SetGlobalError(B200PT_EINVAL, "b200pt_get_kulla_conty: null argument");
+    if (!h) { // the tables depend on no scene: without a handle they are computed right here, on the host (no GPU needed)
+        try {
+            std::vector<float> brdf(kLutResolution * kLutResolution), albedo(kLutResolution);
+            ComputeKullaContyTables(brdf.data(), albedo.data());
+            memcpy(brdf_avg, brdf.data(), sizeof(float) * brdf.size());
+            memcpy(albedo_avg, albedo.data(), sizeof(float) * albedo.size());
+            return B200PT_OK;
+        } catch (const std::exception &e) {
+            return SetGlobalError(B200PT_ENOMEM, std::string("b200pt_get_kulla_conty: ") + e.what());
+        }
+    }
     // The tables are only built at create time when a conductor/dielectric BSDF reads them.
     bool built = false;
     for (float v : h->host.kc_albedo_avg) built = built || v != 0.0f;

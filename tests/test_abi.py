@@ -79,3 +79,15 @@ def test_pfm_frame_dump_round_trips(pkg, tmp_path):
     frame = np.random.RandomState(3).rand(5, 7, 3).astype(np.float32) * 4.0
     pkg.write_pfm(str(tmp_path / "f.pfm"), frame)
     assert np.array_equal(pkg.read_pfm(str(tmp_path / "f.pfm")), frame)
+
+
+def test_kulla_conty_tables_equal_the_reference_tables_without_a_gpu(pkg):
+    """The energy-compensation tables of the rough conductor / dielectric / plastic models (bsdf.cpp:112-186), which
+    b200pt_create computes on the host: bit-equal to the tables the reference build produced (tests/golden/kulla_conty.npz).
+    Without a handle the entry computes them right away, so this runs on a CPU box."""
+    import numpy as np
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "kulla_conty.npz"))
+    brdf, albedo = np.zeros((128, 128), dtype=np.float32), np.zeros(128, dtype=np.float32)
+    assert pkg.lib().b200pt_get_kulla_conty(None, brdf.ctypes.data, albedo.ctypes.data) == 0
+    assert np.array_equal(brdf, golden["brdf_avg"])
+    assert np.array_equal(albedo, golden["albedo_avg"])
